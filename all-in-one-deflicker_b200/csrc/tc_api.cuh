@@ -1,0 +1,34 @@
+// Interface between c_api.cu and the tcgen05 path (mlp_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// Buffers of the tensor-core path, carved from the caller's workspace (see mlp_tc.cu).
+struct TcPlan {
+  char* base = nullptr;
+  int64_t bytes = 0;
+  int64_t rows_map = 0, rows_atlas = 0;
+};
+
+struct TcStep {
+  const MlpShape* ms; const MlpShape* as;
+  const TcPlan* plan;
+  const float* params; float* grads;
+  const float* x_map;        // [n_groups*cap][4]
+  float* uv;                 // [n_groups*cap][2]  mapping output
+  float* y_atlas;            // [3*cap][3]         atlas output
+  const float* d_uv;         // [n_groups*cap][2]  direct gradient of the loss head
+  const float* d_y;          // [3*cap][3]
+  int cap, n_groups;
+  const int* counters;
+};
+
+int64_t tc_plan(const MlpShape& ms, const MlpShape& as, int64_t rows_map, int64_t rows_atlas, char* base,
+                TcPlan* out);
+int tc_atlas_forward(const TcStep& s, cudaStream_t st);    // mapping on all groups, atlas on groups 0..2
+int tc_atlas_backward(const TcStep& s, cudaStream_t st);   // all parameter gradients
+int tc_mapping_forward(const TcStep& s, cudaStream_t st);  // pre-training: mapping only
+int tc_mapping_backward(const TcStep& s, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,188 @@
+/* b200_deflicker.h — C ABI of libb200deflicker.so
+ *
+ * B200-native (sm_100a) replacement for the stage-1 neural-atlas hot path of
+ * ChenyangLEI/All-In-One-Deflicker.  The reference has no FFI layer of its own: its operator
+ * boundary for this path is the Python surface listed beside each entry point below (paths
+ * relative to the reference root).  The Python mirror of that surface lives in
+ * all-in-one-deflicker_b200/src/ and calls these functions through ctypes
+ * (all-in-one-deflicker_b200/b200/_native.py); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *     (PyTorch allocates, the library borrows the pointers for the duration of the call / graph);
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and CUDA-graph
+ *     capturable: no allocation, no synchronisation, no host read-back inside any call;
+ *   - return value 0 = success, otherwise a B200_ERR_* code; b200_last_error() returns a
+ *     thread-local message; no exceptions cross the ABI;
+ *   - floating point is fp32 in memory everywhere.  `precision` selects how the 256-wide Linear
+ *     layers are contracted: B200_PREC_FP32 = CUDA-core FFMA (bit-for-bit an fp32 GEMM),
+ *     B200_PREC_TC = tcgen05 tensor cores on a 2-term fp16 split of both operands (22-bit
+ *     significands, fp32 accumulation in TMEM).
+ */
+#ifndef B200_DEFLICKER_H
+#define B200_DEFLICKER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID 1      /* bad argument (shape, null pointer, unsupported size)   */
+#define B200_ERR_CUDA 2         /* a CUDA runtime call failed                               */
+#define B200_ERR_WORKSPACE 3    /* workspace too small                                      */
+#define B200_ERR_UNSUPPORTED 4  /* valid request this build cannot serve (e.g. no sm_100a)  */
+
+#define B200_PREC_FP32 0
+#define B200_PREC_TC 1
+
+#define B200_MAX_LAYERS 16
+#define B200_RECORD_FLOATS 16   /* floats per pixel record, see B200Video                    */
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* 1 if the current device is compute capability 10.x (tcgen05 path usable), else 0 */
+int b200_device_supports_tc(void);
+
+/* Diagnostics (no reference counterpart).  b200_launch_count: kernels this library has launched
+ * (or captured into a CUDA graph) in this process.  b200_set_kernel_timer: record the two
+ * cudaEvent_t around the launch site tagged `tag` (B200_TAG_*) on every following call, also
+ * inside captured graphs; NULL events switch it off. */
+#define B200_TAG_MAP_FWD 1
+#define B200_TAG_MAP_BWD 2
+#define B200_TAG_ATLAS_FWD 3
+#define B200_TAG_ATLAS_BWD 4
+#define B200_TAG_WGRAD 5
+#define B200_TAG_ADAM 6
+long long b200_launch_count(void);
+int b200_set_kernel_timer(void* ev_start, void* ev_stop, int tag);
+
+/* ------------------------------------------------------------------------------------------
+ * IMLP  — replaces  src/models/stage_1/implicit_neural_networks.py:15-81  (class IMLP)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct B200MlpDesc {
+  int32_t input_dim;       /* IMLP(input_dim=...)                                            */
+  int32_t output_dim;      /* IMLP(output_dim=...)                                           */
+  int32_t hidden_dim;      /* must be 256 for B200_PREC_TC                                   */
+  int32_t num_layers;      /* includes the output layer, <= B200_MAX_LAYERS                  */
+  int32_t pe_freqs;        /* positional_dim when use_positional else 0                      */
+  uint32_t skip_mask;      /* bit i set  <=>  i in skip_layers                               */
+  int32_t use_tanh;        /* tanh on the output                                             */
+  int32_t reserved;
+} B200MlpDesc;
+
+/* Flat parameter layout of one network: for each layer the weight (out x in, row major — the
+ * layout of nn.Linear.weight, `hidden.{i}.weight`) followed by the bias (`hidden.{i}.bias`),
+ * every tensor starting at a multiple of 4 floats (gaps are zero and are never read as
+ * parameters).  Fills w_off[i], b_off[i] (float offsets) and returns the padded float count, or
+ * -1 on an invalid descriptor. */
+int64_t b200_mlp_layout(const B200MlpDesc* d, int64_t* w_off, int64_t* b_off);
+
+/* bytes of scratch b200_mlp_forward / backward need for `rows` rows (training!=0 keeps the
+ * activations for a following backward) */
+int64_t b200_mlp_workspace_bytes(const B200MlpDesc* d, int64_t rows, int training);
+
+/* y[rows, output_dim] = IMLP(x[rows, input_dim])         (implicit_neural_networks.py:62-81) */
+int b200_mlp_forward(const B200MlpDesc* d, const float* params, const float* x, float* y,
+                     int64_t rows, int training, int precision, void* ws, int64_t ws_bytes,
+                     void* stream);
+
+/* Gradients of a forward(training=1) that used the same ws and the same x: dparams += dL/dparams
+ * (flat layout, caller zeroes), dx = dL/dx (may be NULL; needs rows*enc*4 extra workspace bytes
+ * when the network has a positional encoding).  Skip-concatenated inputs receive no input gradient
+ * (`x.detach().clone()`, implicit_neural_networks.py:69). */
+int b200_mlp_backward(const B200MlpDesc* d, const float* params, const float* x, const float* dy,
+                      float* dparams, float* dx, int64_t rows, int precision, void* ws,
+                      int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident video — replaces the eight CPU tensors of
+ * src/models/stage_1/unwrap_utils.py:105-163 (load_input_data_single) and the (3,N) int64 index
+ * table of get_tuples (unwrap_utils.py:166-173, recomputed arithmetically from the index).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct B200Video {
+  /* frame-major pixel records [t_end - t_begin][H][W][16] fp32:
+   *   0..2 rgb | 3..5 d/dx rgb | 6..8 d/dy rgb | 9,10 forward flow | 11,12 backward flow |
+   *   13 forward mask | 14 backward mask | 15 unused                                         */
+  const float* records;
+  /* validity bitmaps of the WHOLE video (bit n = pixel n of the index table), replicated on
+   * every rank so the global flow-row counts need no collective                              */
+  const uint32_t* mask_fwd_bits;
+  const uint32_t* mask_bwd_bits;
+  int32_t H, W, T;          /* full video                                                     */
+  int32_t t_begin, t_end;   /* frames resident on this device                                 */
+  int32_t reserved;
+} B200Video;
+
+/* Repack reference-layout device tensors (frames, dx, dy: (H,W,3,T); flows: (H,W,2,T,1);
+ * masks: (H,W,T,1); T innermost) into records for frames [t_begin, t_end) and into the two
+ * whole-video bitmaps (each ceil(H*W*T/32) words). */
+int b200_video_pack(const float* frames, const float* frames_dx, const float* frames_dy,
+                    const float* flow_fwd, const float* flow_bwd, const float* mask_fwd,
+                    const float* mask_bwd, int32_t H, int32_t W, int32_t T, int32_t t_begin,
+                    int32_t t_end, float* records, uint32_t* mask_fwd_bits,
+                    uint32_t* mask_bwd_bits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One loop trip — replaces src/stage1_neural_atlas.py:159-227 + loss.backward() (:230):
+ * sampling/gather, 7 mapping + 3 atlas evaluations, RGB / gradient / rigidity / flow losses
+ * (src/models/stage_1/loss_utils.py:134-170,227-278,299-356) and all parameter gradients.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct B200AtlasConfig {
+  int32_t batch;             /* samples_batch (global)                                        */
+  int32_t with_global;       /* include_global_rigidity_loss && i <= stop_global_rigidity     */
+  int32_t precision;         /* B200_PREC_*                                                   */
+  int32_t resx;              /* width  — the gradient loss normalises by resx (loss_utils.py:138) */
+  float uv_mapping_scale;
+  float derivative_amount;
+  float global_derivative_amount;
+  float rgb_coeff, gradient_coeff, rigidity_coeff, global_rigidity_coeff, flow_coeff;
+} B200AtlasConfig;
+
+/* loss vector written by b200_atlas_loss_grad (this rank's partial sums, already normalised by
+ * the GLOBAL batch / flow counts, so a sum over ranks gives the reference's values):
+ *   0 total  1 rgb  2 gradient  3 rigidity  4 global rigidity  5 flow  6 n_fwd  7 n_bwd        */
+#define B200_LOSS_FLOATS 8
+
+int64_t b200_atlas_param_floats(void);   /* mapping block followed by atlas block, padded */
+int64_t b200_atlas_workspace_bytes(const B200AtlasConfig* cfg);
+
+/* indices: `batch` int64 pixel-table indices n -> (x = n % W, y = (n / W) % H, t = n / (H*W)),
+ * identical on every rank; rows whose frame is not resident are skipped.  grads (same layout
+ * as params) and losses are overwritten. */
+int b200_atlas_loss_grad(const B200AtlasConfig* cfg, const B200Video* video,
+                         const int64_t* indices, const float* params, float* grads,
+                         float* losses, void* ws, int64_t ws_bytes, void* stream);
+
+/* One pre_train_mapping step (src/models/stage_1/unwrap_utils.py:182-195): rows ys / columns
+ * xs (int64[batch]) of frame `frame`; gradients of the mapping block only; loss -> losses[0]. */
+int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int32_t T,
+                            int32_t frame, const int64_t* ys, const int64_t* xs,
+                            const float* params, float* grads, float* losses, void* ws,
+                            int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser — replaces torch.optim.Adam.step() (src/stage1_neural_atlas.py:132-134,231) on a
+ * flat buffer.  `step` is a device int64 counter (steps already taken); it is incremented by
+ * the kernel so the call can sit inside a replayed CUDA graph.  grad_scale multiplies the
+ * gradient first (1/world for an averaged all-reduce; 1.0 otherwise).
+ * ------------------------------------------------------------------------------------------ */
+int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale,
+                   int64_t* step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Render — replaces the reconstruction loop of src/models/stage_1/evaluate.py:640-666,733:
+ * rgb[(y*W + x)*3 + c] of frame f for pixels [pix_begin, pix_end); also u8 = trunc(rgb * 255)
+ * when rgb_u8 != NULL.
+ * ------------------------------------------------------------------------------------------ */
+int64_t b200_render_workspace_bytes(int64_t pixels);
+int b200_render(const float* params, int32_t H, int32_t W, int32_t T, int32_t frame,
+                int64_t pix_begin, int64_t pix_end, float* rgb, uint8_t* rgb_u8, int precision,
+                void* ws, int64_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_DEFLICKER_H */

@@ -1,0 +1,331 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle on the same seeded inputs.
+Needs a GPU (`-m gpu`); nothing here reads /root/reference.
+
+Tolerances (fp32 path, B200_PREC_FP32 = CUDA-core FFMA GEMMs with fp32 accumulation):
+  forward outputs        |err| <= 2e-5                  (tanh outputs, O(1) values)
+  losses                 rtol 2e-4
+  parameter gradients    |err| <= 1e-3 * max|grad| per tensor   (atomic fp32 summation order differs)
+  sampled coordinates / gathered colours / flow-row counts      bit-exact
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from b200 import _native as N
+from b200 import atlas as A
+from b200 import synth
+from oracle import atlas_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _params(golden_dir):
+    z = np.load(os.path.join(golden_dir, "params_seed1234.npz"))
+    mp = [torch.from_numpy(z[f"map{i}"]) for i in range(12)]
+    ap = [torch.from_numpy(z[f"atl{i}"]) for i in range(16)]
+    return mp, ap
+
+
+def _golden_video(golden_dir):
+    z = np.load(os.path.join(golden_dir, "iteration.npz"))
+    data = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("video_")}
+    return data, torch.from_numpy(z["inds"])
+
+
+def _trainer(data, golden_dir, batch, precision=N.PREC_FP32, t_begin=0, t_end=None):
+    vid = A.DeviceVideo.from_reference_layout(data, DEV, t_begin, t_end)
+    tr = A.AtlasTrainer(vid, {"samples_batch": batch}, precision=precision, device=DEV)
+    mp, ap = _params(golden_dir)
+    tr.load_state(O.state_dict_of(mp), O.state_dict_of(ap))
+    return tr
+
+
+def _flat_grads(tr):
+    out = []
+    for which in ("mapping", "atlas"):
+        out += [v for v in tr.grad_views(which).values()]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+def test_library_runs_native_code():
+    assert os.path.exists(N.LIB_PATH)
+    assert N.lib().b200_device_supports_tc() in (0, 1)
+    before = N.lib().b200_launch_count()
+    p = torch.zeros(1024, device=DEV); g = torch.ones(1024, device=DEV)
+    m = torch.zeros(1024, device=DEV); v = torch.zeros(1024, device=DEV)
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    N.check(N.lib().b200_adam_step(N.ptr(p), N.ptr(g), N.ptr(m), N.ptr(v), 1024, 1e-4, 0.9, 0.999, 1e-8, 1.0,
+                                   N.ptr(step), N.current_stream()))
+    torch.cuda.synchronize()
+    assert N.lib().b200_launch_count() > before and int(step) == 1
+    assert torch.allclose(p, torch.full_like(p, -1e-4), rtol=1e-5)
+
+
+@pytest.mark.parametrize("which", ["mapping", "atlas"])
+@pytest.mark.parametrize("rows", [300, 1])
+def test_imlp_forward_backward_parity(golden_dir, which, rows):
+    mp, ap = _params(golden_dir)
+    spec, params, dd = (O.MAPPING_SPEC, mp, A.MAPPING_DESC) if which == "mapping" else (O.ATLAS_SPEC, ap, A.ATLAS_DESC)
+    desc = A.make_desc(**dd)
+    w_off, b_off, total = A.mlp_layout(desc)
+    flat = torch.zeros(total)
+    for i, (k, n) in enumerate(A.layer_dims(desc)):
+        flat[w_off[i]:w_off[i] + k * n] = params[2 * i].flatten()
+        flat[b_off[i]:b_off[i] + n] = params[2 * i + 1]
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.rand(rows, spec.input_dim, generator=g) * (2 if which == "mapping" else 1)
+         - (1 if which == "mapping" else 0))
+    dy = torch.randn(rows, spec.output_dim, generator=g)
+    # oracle
+    xo = x.clone().requires_grad_(True)
+    po = [p.clone().requires_grad_(True) for p in params]
+    yo = O.mlp_forward(spec, po, xo)
+    yo.backward(dy)
+    # CUDA
+    lib = N.lib()
+    enc = 2 * spec.input_dim * spec.positional_dim if spec.use_positional else 0
+    nbytes = lib.b200_mlp_workspace_bytes(C.byref(desc), rows, 1) + rows * enc * 4 + 256
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    xd, dyd, fd = x.to(DEV), dy.to(DEV), flat.to(DEV)
+    yd = torch.empty(rows, spec.output_dim, device=DEV)
+    N.check(lib.b200_mlp_forward(C.byref(desc), N.ptr(fd), N.ptr(xd), N.ptr(yd), rows, 1, N.PREC_FP32, N.ptr(ws),
+                                 ws.numel(), N.current_stream()), "forward")
+    gd = torch.zeros(total, device=DEV)
+    dxd = torch.empty(rows, spec.input_dim, device=DEV)
+    N.check(lib.b200_mlp_backward(C.byref(desc), N.ptr(fd), N.ptr(xd), N.ptr(dyd), N.ptr(gd), N.ptr(dxd), rows,
+                                  N.PREC_FP32, N.ptr(ws), ws.numel(), N.current_stream()), "backward")
+    torch.cuda.synchronize()
+    assert (yd.cpu() - yo.detach()).abs().max() <= 2e-5
+    gd = gd.cpu()
+    for i, (k, n) in enumerate(A.layer_dims(desc)):
+        for got, ref in ((gd[w_off[i]:w_off[i] + k * n].view(n, k), po[2 * i].grad),
+                         (gd[b_off[i]:b_off[i] + n], po[2 * i + 1].grad)):
+            assert (got - ref).abs().max() <= 1e-4 * ref.abs().max() + 1e-7, (which, i)
+    assert (dxd.cpu() - xo.grad).abs().max() <= 2e-4 * xo.grad.abs().max() + 1e-6
+
+
+def test_video_pack_bit_exact(golden_dir):
+    data, _ = _golden_video(golden_dir)
+    H, W, _, T = data["frames"].shape
+    vid = A.DeviceVideo.from_reference_layout(data, DEV, 1, T - 1, frame_chunk=2)
+    rec = vid.records.cpu().view(T - 2, H, W, 16)
+    for t in range(1, T - 1):
+        assert torch.equal(rec[t - 1, :, :, 0:3], data["frames"][:, :, :, t])
+        assert torch.equal(rec[t - 1, :, :, 3:6], data["frames_dx"][:, :, :, t])
+        assert torch.equal(rec[t - 1, :, :, 6:9], data["frames_dy"][:, :, :, t])
+        assert torch.equal(rec[t - 1, :, :, 9:11], data["flow_fwd"][:, :, :, t, 0])
+        assert torch.equal(rec[t - 1, :, :, 11:13], data["flow_bwd"][:, :, :, t, 0])
+        assert torch.equal(rec[t - 1, :, :, 13], data["mask_fwd"][:, :, t, 0])
+        assert torch.equal(rec[t - 1, :, :, 14], data["mask_bwd"][:, :, t, 0])
+    bits = vid.bits_f.cpu().numpy().view(np.uint32)
+    ref = data["mask_fwd"][:, :, :, 0].permute(2, 0, 1).reshape(-1).numpy() != 0     # (t, y, x) order
+    got = np.unpackbits(bits.view(np.uint8), bitorder="little")[:ref.size].astype(bool)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("it", [0, 6000])
+def test_loss_grad_parity_and_exact_sampling(golden_dir, it):
+    data, inds = _golden_video(golden_dir)
+    B = inds.shape[0]
+    tr = _trainer(data, golden_dir, B)
+    tr.indices.copy_(inds.reshape(-1))
+    wg = tr.uses_global(it)
+    tr.loss_grad(wg)
+    torch.cuda.synchronize()
+    # ---- oracle
+    video = O.Video(**data)
+    mp, ap = _params(golden_dir)
+    mp = [p.clone().requires_grad_(True) for p in mp]
+    ap = [p.clone().requires_grad_(True) for p in ap]
+    terms = O.iteration_losses(video, mp, ap, inds, it)
+    terms["total"].backward()
+    losses = tr.losses.cpu().numpy()
+    ref = [float(terms[k].detach()) if k in terms else 0.0
+           for k in ("total", "rgb", "gradient", "rigidity", "rigidity_global", "flow")]
+    np.testing.assert_allclose(losses[:6], ref, rtol=2e-4)
+    # ---- exact sampling: coordinate rows, gathered targets, counts (workspace layout of c_api.cu)
+    cap = (B + 127) // 128 * 128
+    ws = tr._workspace()
+    base = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr()
+    r256 = lambda n: (n + 255) // 256 * 256
+    off_cnt, off_list = base, base + 256
+    off_x = off_list + r256(cap * 4)
+    off_t = off_x + r256(9 * cap * 16)
+    counters = ws[off_cnt:off_cnt + 12].view(torch.int32).cpu()
+    H, W, T = video.H, video.W, video.T
+    jif = O.pixel_table(T, H, W)[:, inds]
+    wf = video.mask_fwd[jif[1].squeeze(), jif[0].squeeze(), jif[2].squeeze(), 0] != 0
+    wb = video.mask_bwd[jif[1].squeeze(), jif[0].squeeze(), jif[2].squeeze(), 0] != 0
+    assert counters.tolist() == [B, int(wf.sum()), int(wb.sum())]
+    assert losses[6] == int(wf.sum()) and losses[7] == int(wb.sum())
+    x_map = ws[off_x:off_x + 9 * cap * 16].view(torch.float32).view(9, cap, 4).cpu()
+    larger = max(W, H)
+    assert torch.equal(x_map[0, :B, :3], O.normalise_xyt(jif, larger, T))
+    hx = O._half(W)
+    xp = torch.cat(((jif[0] + 1) / hx - 1, jif[1] / hx - 1, jif[2] / (T / 2.0) - 1), dim=1)
+    yp = torch.cat((jif[0] / hx - 1, (jif[1] + 1) / hx - 1, jif[2] / (T / 2.0) - 1), dim=1)
+    assert torch.equal(x_map[1, :B, :3], xp) and torch.equal(x_map[2, :B, :3], yp)
+    hl = O._half(larger)
+    for g, d in ((3, 1), (7, 100)):
+        if g == 7 and not wg:
+            continue
+        ymd = torch.cat((jif[0] / hl - 1, (jif[1] - d) / hl - 1, jif[2] / (T / 2.0) - 1), dim=1)
+        xmd = torch.cat(((jif[0] - d) / hl - 1, jif[1] / hl - 1, jif[2] / (T / 2.0) - 1), dim=1)
+        assert torch.equal(x_map[g, :B, :3], ymd) and torch.equal(x_map[g + 1, :B, :3], xmd)
+    uv_dummy = torch.zeros(B, 2)
+    _, xyt_f, rows_f = O.flow_matches(jif, video.mask_fwd, video.flow_fwd, larger, T, True, uv_dummy)
+    _, xyt_b, rows_b = O.flow_matches(jif, video.mask_bwd, video.flow_bwd, larger, T, False, uv_dummy)
+    assert torch.equal(x_map[5, rows_f, :3], xyt_f) and torch.equal(x_map[6, rows_b, :3], xyt_b)
+    assert torch.all(x_map[:, B:] == 0)
+    tg = ws[off_t:off_t + cap * 48].view(torch.float32).view(cap, 12).cpu()
+    assert torch.equal(tg[:B, 0:3], video.frames[jif[1], jif[0], :, jif[2]].squeeze(1))
+    assert torch.equal(tg[:B, 3:6], video.frames_dx[jif[1], jif[0], :, jif[2]].squeeze(1))
+    assert torch.equal(tg[:B, 6:9], video.frames_dy[jif[1], jif[0], :, jif[2]].squeeze(1))
+    # ---- gradients
+    for got, p in zip(_flat_grads(tr), mp + ap):
+        ref_g = p.grad
+        assert (got.cpu() - ref_g).abs().max() <= 1e-3 * ref_g.abs().max() + 1e-9
+
+
+def test_adam_matches_torch():
+    n = 5000
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-4)
+    p = p0.to(DEV); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for _ in range(5):
+        gr = torch.randn(n, generator=g) * 10 ** float(torch.randint(-6, 2, (1,), generator=g))
+        ref.grad = gr.clone()
+        opt.step()
+        N.check(N.lib().b200_adam_step(N.ptr(p), N.ptr(gr.to(DEV)), N.ptr(m), N.ptr(v), n, 1e-4, 0.9, 0.999, 1e-8, 1.0,
+                                       N.ptr(step), N.current_stream()))
+    torch.cuda.synchronize()
+    assert int(step) == 5
+    assert (p.cpu() - ref.detach()).abs().max() <= 2e-7
+    st = opt.state[ref]
+    assert (m.cpu() - st["exp_avg"]).abs().max() <= 1e-6 * st["exp_avg"].abs().max()
+    assert (v.cpu() - st["exp_avg_sq"]).abs().max() <= 1e-6 * st["exp_avg_sq"].abs().max()
+
+
+def test_five_step_trajectory_with_graph_replay(golden_dir):
+    data, _ = _golden_video(golden_dir)
+    B = 64
+    tr = _trainer(data, golden_dir, B)
+    video = O.Video(**data)
+    mp, ap = _params(golden_dir)
+    mp = [p.clone().requires_grad_(True) for p in mp]
+    ap = [p.clone().requires_grad_(True) for p in ap]
+    opt = O.make_optimizer(mp, ap)
+    gi = torch.Generator().manual_seed(21)
+    npix = video.H * video.W * video.T
+    for it in range(5):
+        inds = torch.randint(npix, (B, 1), generator=gi)
+        ref = O.train_iteration(video, mp, ap, opt, inds, it)
+        got = tr.step_host(inds, it, use_graph=True)
+        np.testing.assert_allclose(got[0], ref["total"], rtol=1e-3)
+        np.testing.assert_allclose(got[5], ref["flow"], rtol=1e-3)
+    assert int(tr.step_count) == 5
+    for which, ref_p in (("mapping", mp), ("atlas", ap)):
+        for (k, v), r in zip(tr.param_views(which).items(), ref_p):
+            # 5 Adam steps of 1e-4 each: parameters may differ by a fraction of one step where the
+            # gradient sign is noise-dominated; bound by 1.5e-5 absolute (< 1/6 of one step)
+            assert (v.cpu() - r.detach()).abs().max() <= 1.5e-5, (which, k)
+    sd = tr.optimizer_state_dict()
+    assert len(sd["state"]) == 28 and sd["param_groups"][1]["params"][0] == 12
+    assert float(sd["state"][0]["step"]) == 5.0
+
+
+def test_pretrain_two_steps(golden_dir):
+    data, _ = _golden_video(golden_dir)
+    tr = _trainer(data, golden_dir, 10000)
+    mp, _ = _params(golden_dir)
+    mp = [p.clone().requires_grad_(True) for p in mp]
+    H, W, T = 20, 36, 2
+    torch.manual_seed(5)
+    opt = torch.optim.Adam(mp, lr=1e-4)
+    ref_losses = []
+    for f in range(T):
+        ys = torch.randint(H, (10000, 1)); xs = torch.randint(W, (10000, 1))
+        loss = O.pretrain_losses(mp, f, ys, xs, T, max(W, H), 0.8)
+        opt.zero_grad(); loss.backward(); opt.step()
+        ref_losses.append(float(loss.detach()))
+    torch.manual_seed(5)
+    last = tr.pretrain(T, H, W, 1)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(float(last[0]), ref_losses[-1], rtol=1e-4)
+    for (k, v), r in zip(tr.param_views("mapping").items(), mp):
+        assert (v.cpu() - r.detach()).abs().max() <= 1e-5, k
+
+
+def test_render_parity(golden_dir):
+    data, _ = _golden_video(golden_dir)
+    tr = _trainer(data, golden_dir, 64)
+    mp, ap = _params(golden_dir)
+    H, W, _, T = data["frames"].shape
+    img, u8 = tr.render_frame(2, H, W, T, chunk=500, want_u8=True)
+    ref = O.render_frame(mp, ap, 2, H, W, T)
+    assert (img.cpu() - ref).abs().max() <= 2e-5
+    ref8 = O.to_uint8(ref).astype(int)
+    diff = np.abs(u8.cpu().numpy().astype(int) - ref8)
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+    assert abs(A.psnr(data["frames"][:, :, :, 2], img.cpu()) - O.psnr(data["frames"][:, :, :, 2], ref)) < 1e-3
+
+
+def test_frame_sharding_is_linear(golden_dir):
+    """Two frame shards evaluated one after the other on one GPU: their gradient / loss partials
+    add up to the unsharded result (what the all-reduce computes at N>1)."""
+    data, inds = _golden_video(golden_dir)
+    B = inds.shape[0]
+    T = data["frames"].shape[3]
+    full = _trainer(data, golden_dir, B)
+    full.indices.copy_(inds.reshape(-1)); full.loss_grad(True)
+    acc = torch.zeros_like(full.grad_loss)
+    for r in range(2):
+        t0, t1 = A.frame_range(r, 2, T)
+        part = _trainer(data, golden_dir, B, t_begin=t0, t_end=t1)
+        part.indices.copy_(inds.reshape(-1)); part.loss_grad(True)
+        acc += part.grad_loss
+    torch.cuda.synchronize()
+    n = full.n_params
+    assert (acc[:n] - full.grads).abs().max() <= 2e-5 * full.grads.abs().max()
+    np.testing.assert_allclose(acc[n:n + 6].cpu().numpy(), full.losses[:6].cpu().numpy(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("T,H,W", [(80, 432, 768)])
+def test_full_size_properties(golden_dir, T, H, W):
+    """BASELINE.json configs[1] size.  Size-independent properties: replay determinism of the
+    sampled rows, shard linearity, finite losses, flow-row counts equal to a bitmap popcount."""
+    data = synth.throughput_set(H, W, T, seed=0)
+    B = 10000
+    inds = torch.randint(H * W * T, (B, 1), generator=torch.Generator().manual_seed(1))
+    full = _trainer(data, golden_dir, B)
+    full.indices.copy_(inds.reshape(-1)); full.loss_grad(True)
+    torch.cuda.synchronize()
+    l1 = full.losses.cpu().numpy().copy()
+    g1 = full.grads.clone()
+    assert np.all(np.isfinite(l1[:6])) and l1[0] > 0
+    n = inds.reshape(-1)
+    t, y, x = n // (H * W), (n // W) % H, n % W
+    assert l1[6] == int((data["mask_fwd"][y, x, t, 0] != 0).sum())
+    assert l1[7] == int((data["mask_bwd"][y, x, t, 0] != 0).sum())
+    full.loss_grad(True); torch.cuda.synchronize()
+    assert np.allclose(full.losses.cpu().numpy()[:6], l1[:6], rtol=1e-5)
+    assert (full.grads - g1).abs().max() <= 1e-4 * g1.abs().max()         # atomics: order-dependent rounding only
+    del full
+    acc = None
+    for r in range(2):
+        t0, t1 = A.frame_range(r, 2, T)
+        part = _trainer(data, golden_dir, B, t_begin=t0, t_end=t1)
+        part.indices.copy_(inds.reshape(-1)); part.loss_grad(True)
+        torch.cuda.synchronize()
+        acc = part.grad_loss.clone() if acc is None else acc + part.grad_loss
+        del part
+    assert (acc[:-8] - g1).abs().max() <= 1e-4 * g1.abs().max()
+    np.testing.assert_allclose(acc[-8:-2].cpu().numpy(), l1[:6], rtol=1e-4)
