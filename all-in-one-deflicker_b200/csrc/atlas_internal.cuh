@@ -25,12 +25,12 @@ int launch_select_sample(const int64_t* indices, int B, const B200Video& vid, co
 int launch_pretrain_sample(const int64_t* ys, const int64_t* xs, int B, int cap, float half_larger,
                            float t_norm, float* x_map, int* counters, cudaStream_t st);
 int launch_pretrain_loss(const float* x_map, const float* uv, int B, int cap, float uv_scale, float* d_uv,
-                         float* losses, cudaStream_t st);
-int launch_loss(const float* uv, const float* y_atlas, const float* targets, const int* counters, int cap,
+                         float* losses, int* counters, cudaStream_t st);
+int launch_loss(const float* uv, const float* y_atlas, const float* targets, int* counters, int cap,
                 int n_groups, const LossConfig& cfg, float* d_uv, float* d_y, float* losses,
                 cudaStream_t st);
-int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-                float eps, float grad_scale, int64_t* step, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2,
+                double eps, float grad_scale, int64_t* step, cudaStream_t st);
 int launch_render_rows(int W, float half_larger, float t_norm, int64_t pix_begin, int64_t count,
                        int64_t rows_padded, float* x_map, cudaStream_t st);
 int launch_render_out(const float* y, int64_t count, float* rgb, uint8_t* u8, cudaStream_t st);

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const int64_t* _
       tb += __shfl_xor_sync(0xffffffffu, tb, o);
     }
     if (lane == 31) counters[0] = wi;
-    if (lane == 0) { counters[1] = tf; counters[2] = tb; }
+    if (lane == 0) { counters[1] = tf; counters[2] = tb; counters[3] = 0; }
   }
   __syncthreads();
   int pos = warp_tot[0][wid] + incl - c_loc;
@@ -204,16 +204,22 @@ __global__ void pretrain_sample_kernel(const int64_t* __restrict__ ys, const int
                                        int cap, float half_larger, float t_norm, float4* __restrict__ x_map,
                                        int* __restrict__ counters) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) counters[0] = B;
+  if (s == 0) { counters[0] = B; counters[3] = 0; }
   if (s >= cap) return;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s < B) r = make_float4(norm_coord((float)xs[s], half_larger), norm_coord((float)ys[s], half_larger), t_norm, 0.f);
   x_map[s] = r;
 }
 
+__device__ __forceinline__ void publish_gmax(float mx, int* gmax_bits) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(gmax_bits, __float_as_int(mx));
+}
+
 __global__ void pretrain_loss_kernel(const float4* __restrict__ x_map, const float* __restrict__ uv, int B,
                                      int cap, float uv_scale, float* __restrict__ d_uv,
-                                     float* __restrict__ losses) {
+                                     float* __restrict__ losses, int* __restrict__ gmax_bits) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   float val = 0.f;
   if (s < cap) {
@@ -225,6 +231,9 @@ __global__ void pretrain_loss_kernel(const float4* __restrict__ x_map, const flo
     }
     d_uv[2 * s] = g[0];
     d_uv[2 * s + 1] = g[1];
+    publish_gmax(fmaxf(fabsf(g[0]), fabsf(g[1])), gmax_bits);
+  } else {
+    publish_gmax(0.f, gmax_bits);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
@@ -240,9 +249,9 @@ int launch_pretrain_sample(const int64_t* ys, const int64_t* xs, int B, int cap,
 }
 
 int launch_pretrain_loss(const float* x_map, const float* uv, int B, int cap, float uv_scale, float* d_uv,
-                         float* losses, cudaStream_t st) {
+                         float* losses, int* counters, cudaStream_t st) {
   pretrain_loss_kernel<<<(cap + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4*>(x_map), uv, B, cap,
-                                                           uv_scale, d_uv, losses);
+                                                           uv_scale, d_uv, losses, counters + 3);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -337,7 +346,7 @@ int launch_pe_backward(const float* pe, int ld_pe, const float* dpe, int ld_dpe,
 // d/d y for the atlas rows and accumulates the loss vector.
 // ---------------------------------------------------------------------------------------------
 __global__ void loss_kernel(const float* __restrict__ uv, const float* __restrict__ y_atlas,
-                            const float* __restrict__ targets, const int* __restrict__ counters, int cap,
+                            const float* __restrict__ targets, int* __restrict__ counters, int cap,
                             int n_groups, LossConfig cfg, float* __restrict__ d_uv, float* __restrict__ d_y,
                             float* __restrict__ losses) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,6 +354,7 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
   cfg.inv_nf = n_f > 0 ? 1.0f / (float)n_f : 0.f;
   cfg.inv_nb = n_b > 0 ? 1.0f / (float)n_b : 0.f;
   float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gmx = 0.f;
   if (s < cap) {
     SampleOut out;
     if (s < n_local) {
@@ -377,13 +387,20 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
     }
 #pragma unroll
     for (int g = 0; g < G_COUNT; ++g)
-      if (g < n_groups)
+      if (g < n_groups) {
         *reinterpret_cast<float2*>(d_uv + ((int64_t)g * cap + s) * 2) = make_float2(out.duv[g][0], out.duv[g][1]);
+        gmx = fmaxf(gmx, fmaxf(fabsf(out.duv[g][0]), fabsf(out.duv[g][1])));
+      }
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gmx = fmaxf(gmx, fabsf(out.dy[g][c]));
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
       for (int c = 0; c < 3; ++c) d_y[((int64_t)g * cap + s) * 3 + c] = out.dy[g][c];
   }
+  publish_gmax(gmx, counters + 3);     // scale of this iteration's gradients (tensor-core path)
   // block reduction of the six partial sums -> atomics on the loss vector
   __shared__ float red[6][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -418,7 +435,7 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
   }
 }
 
-int launch_loss(const float* uv, const float* y_atlas, const float* targets, const int* counters, int cap,
+int launch_loss(const float* uv, const float* y_atlas, const float* targets, int* counters, int cap,
                 int n_groups, const LossConfig& cfg, float* d_uv, float* d_y, float* losses,
                 cudaStream_t st) {
   loss_kernel<<<(cap + 127) / 128, 128, 0, st>>>(uv, y_atlas, targets, counters, cap, n_groups, cfg, d_uv, d_y,
@@ -434,19 +451,20 @@ int launch_loss(const float* uv, const float* y_atlas, const float* targets, con
 //   denom = sqrt(v) / sqrt(1-b2^t) + eps;  p.addcdiv_(m, denom, value=-lr/(1-b1^t))
 // ---------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float* __restrict__ v, int64_t n, double lr, double b1d, double b2d, double epsd,
                             float grad_scale, const int64_t* __restrict__ step_in) {
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const double t = (double)(*step_in + 1);
-    const double bc1 = 1.0 - pow((double)b1, t);
-    const double bc2 = 1.0 - pow((double)b2, t);
-    s_step_size = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - pow(b1d, t);
+    const double bc2 = 1.0 - pow(b2d, t);
+    s_step_size = (float)(lr / bc1);
     s_bc2_sqrt = (float)sqrt(bc2);
   }
   __syncthreads();
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-  const float w1 = 1.0f - b1, w2 = 1.0f - b2;
+  // python floats (doubles) rounded to fp32 where torch passes them to fp32 kernels
+  const float w1 = (float)(1.0 - b1d), w2 = (float)(1.0 - b2d), b2 = (float)b2d, eps = (float)epsd;
   const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
   if (i4 + 3 < n) {
@@ -480,10 +498,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 __global__ void bump_step_kernel(int64_t* step) { *step += 1; }
 
-int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-                float eps, float grad_scale, int64_t* step, cudaStream_t st) {
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2,
+                double eps, float grad_scale, int64_t* step, cudaStream_t st) {
   const int64_t threads = (n + 3) / 4;
+  timer_begin(TAG_ADAM, st);
   adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step);
+  timer_end(TAG_ADAM, st);
   B200_CHECK_LAUNCH();
   bump_step_kernel<<<1, 1, 0, st>>>(step);
   B200_CHECK_LAUNCH();

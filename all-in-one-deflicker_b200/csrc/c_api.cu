@@ -377,7 +377,7 @@ int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int3
   if (cfg->precision == B200_PREC_FP32) {
     B200_PROPAGATE(simt_mlp_forward(pl.ms, params, pl.x_map, 4, span, pl.map, pl.map.y, st));
     B200_PROPAGATE(launch_pretrain_loss(pl.x_map, pl.map.y, cfg->batch, cap, cfg->uv_mapping_scale, pl.d_uv,
-                                        losses, st));
+                                        losses, pl.counters, st));
     B200_PROPAGATE(simt_mlp_backward(pl.ms, params, pl.x_map, 4, span, pl.map, pl.d_uv, grads, nullptr, 0, st));
   } else {
     TcStep ts{};
@@ -387,14 +387,14 @@ int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int3
     ts.cap = cap; ts.n_groups = 1; ts.counters = pl.counters;
     B200_PROPAGATE(tc_mapping_forward(ts, st));
     B200_PROPAGATE(launch_pretrain_loss(pl.x_map, pl.map.y, cfg->batch, cap, cfg->uv_mapping_scale, pl.d_uv,
-                                        losses, st));
+                                        losses, pl.counters, st));
     B200_PROPAGATE(tc_mapping_backward(ts, st));
   }
   return B200_OK;
 }
 
-int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, float grad_scale, int64_t* step, void* stream) {
+int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, float grad_scale, int64_t* step, void* stream) {
   B200_REQUIRE(params && grads && exp_avg && exp_avg_sq && step && n > 0, "null pointer / empty");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(exp_avg) & 15) == 0 && (reinterpret_cast<uintptr_t>(exp_avg_sq) & 15) == 0,

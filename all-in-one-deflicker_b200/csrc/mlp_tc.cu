@@ -1,14 +1,1238 @@
-// tcgen05 path (placeholder until the kernels land): every entry reports B200_ERR_UNSUPPORTED.
+// tcgen05 path of the two IMLPs (B200_PREC_TC).
+//
+// Every 256-wide Linear layer is a UMMA (tcgen05.mma kind::f16, M=128 rows per CTA tile, fp32
+// accumulators in TMEM).  fp32 fidelity comes from a 2-term fp16 split of BOTH operands,
+//     v * S = hi + lo,   hi = rn_f16(v*S),  lo = rn_f16(v*S - hi)          (22-bit significand)
+// and three MMAs per product  hi*hi + hi*lo + lo*hi  (the dropped lo*lo term is 2^-22 relative).
+// S is a power of two per operand class (activations 2^4, weights 2^8, gradients chosen per
+// iteration from max|dL/dy|), undone exactly in the epilogues.
+//
+// Kernels
+//   tc_prep_kernel   fp32 parameters -> split fp16 "stage images" (the exact 128B-swizzled smem
+//                    layout a UMMA descriptor reads), W for the forward and W^T for the dgrad
+//   tc_fwd_kernel    persistent; one 128-row tile walks through ALL layers on chip: activations live
+//                    in TMEM (A operand, TS-mode MMA), weights stream L2->smem through the TMA engine
+//                    (cp.async.bulk + mbarrier ring), epilogue = bias + ReLU + split + TMEM store;
+//                    first/last (K=3 / N=2,3) layers and the positional encoding run on CUDA cores
+//                    inside the same kernel
+//   tc_bwd_kernel    same structure for dL/dz: tanh', last layer and its weight gradient on CUDA
+//                    cores, hidden layers as dZ * W (B = W^T images), ReLU mask from 1-bit flags,
+//                    bias gradients by an in-register butterfly column sum
+//   tc_wgrad_kernel  dW = dZ^T * H as UMMA with both operands MN-major straight from the images
+//                    the two kernels above left in HBM; split over rows, fp32 reductions (red.v4)
+//
+// Restates nn.Linear/ReLU/tanh/skip-concat forward+autograd of
+//   src/models/stage_1/implicit_neural_networks.py:62-81 for the two networks of
+//   src/stage1_neural_atlas.py:112-128.
 #include "tc_api.cuh"
+#include "tc_ptx.cuh"
+#include "loss_math.h"
 
 namespace b200 {
-int64_t tc_plan(const MlpShape&, const MlpShape&, int64_t rows_map, int64_t rows_atlas, char* base, TcPlan* out) {
-  if (out) { out->base = base; out->bytes = 0; out->rows_map = rows_map; out->rows_atlas = rows_atlas; }
-  return 0;
+using namespace ptx;
+
+constexpr int TM = 128;                 // rows per tile (UMMA M)
+constexpr int HID = 256;
+constexpr int STAGE_BYTES = 32768;      // one weight image: 256 rows x 64 k (fp16), 128B swizzle
+constexpr int NSTAGE = 5;
+constexpr float S_ACT = 16.0f;          // activation scale before the fp16 split
+constexpr float S_W = 256.0f;           // weight scale
+constexpr int TILE_IMG_BYTES = TM * HID * 2;     // one term of one activation tile image: 64 KB
+constexpr int PE_IMG_BYTES = TM * 64 * 2;        // one term of one 64-wide tile image: 16 KB
+constexpr int PE_COLS = 40;
+
+constexpr int TC_THREADS = 192;         // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_D = 0, TM_AHI = 256, TM_ALO = 384;
+
+// byte offset of element (row m, column n) inside one term of a [128 x 256] tile image:
+// [16 groups of 8 rows][4 atoms of 64 columns][8 rows x 128 B, 16-byte chunks XOR row]
+__host__ __device__ __forceinline__ int img_off(int m, int n) {
+  const int r = m & 7;
+  return (m >> 3) * 4096 + (n >> 6) * 1024 + r * 128 + ((((n & 63) >> 3) ^ r) << 4) + ((n & 7) << 1);
 }
-static int unsupported() { set_error("tensor-core path not built"); return B200_ERR_UNSUPPORTED; }
-int tc_atlas_forward(const TcStep&, cudaStream_t) { return unsupported(); }
-int tc_atlas_backward(const TcStep&, cudaStream_t) { return unsupported(); }
-int tc_mapping_forward(const TcStep&, cudaStream_t) { return unsupported(); }
-int tc_mapping_backward(const TcStep&, cudaStream_t) { return unsupported(); }
+// same for a [rows x 64] image (one atom per group): also the K-major SW128 layout of a weight image
+__host__ __device__ __forceinline__ int img64_off(int m, int k) {
+  const int r = m & 7;
+  return (m >> 3) * 1024 + r * 128 + (((k >> 3) ^ r) << 4) + ((k & 7) << 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout of the tensor-core workspace
+// ---------------------------------------------------------------------------------------------
+struct NetImages {
+  // forward weight images, consumption order: per TC layer, per 64-wide k chunk: hi image, lo image
+  char* w_fwd; int64_t w_fwd_layer[B200_MAX_LAYERS]; int n_chunks_fwd[B200_MAX_LAYERS];
+  // dgrad weight images (W^T): per layer, per 64-wide chunk of the reduction (out) index: hi, lo
+  char* w_bwd; int64_t w_bwd_layer[B200_MAX_LAYERS];
+  // activation images h_0..h_{L-2}: [slot][term][tile][64 KB]; dZ images for layers 1..L-2 (mapping),
+  // 0..L-2 (atlas): same shape
+  char* act; char* dz;
+  int64_t slot_stride, term_stride;       // bytes
+  char* pe; int64_t pe_term_stride;       // atlas: [term][tile][16 KB]
+  uint32_t* bits;                         // [slot][rows][8]
+  int64_t rows;
+};
+
+struct TcLayout {
+  NetImages map, atl;
+  int64_t bytes;
+};
+
+static char* carve_tc(char*& p, int64_t bytes) { char* r = p; p += round_up(bytes, 1024); return r; }
+
+static void plan_net(const MlpShape& s, int64_t rows, bool is_atlas, char*& p, NetImages* n) {
+  const int64_t tiles = rows / TM;
+  n->rows = rows;
+  int64_t off = 0;
+  for (int l = 0; l < s.L; ++l) {
+    int chunks = 0;
+    const bool tc_layer = is_atlas ? (l <= s.L - 2) : (l >= 1 && l <= s.L - 2);
+    if (tc_layer) chunks = (l == 0 ? 0 : HID / 64) + ((l == 0 || s.skip[l]) && is_atlas ? 1 : 0);
+    n->n_chunks_fwd[l] = chunks;
+    n->w_fwd_layer[l] = off;
+    off += (int64_t)chunks * 2 * STAGE_BYTES;
+  }
+  n->w_fwd = carve_tc(p, off);
+  off = 0;
+  for (int l = 0; l < s.L; ++l) {
+    n->w_bwd_layer[l] = off;
+    const bool dgrad_layer = is_atlas ? (l <= s.L - 2) : (l >= 2 && l <= s.L - 2);
+    if (dgrad_layer || (!is_atlas && l == 1)) off += (int64_t)(HID / 64) * 2 * STAGE_BYTES;
+  }
+  n->w_bwd = carve_tc(p, off);
+  n->term_stride = tiles * TILE_IMG_BYTES;
+  n->slot_stride = 2 * n->term_stride;
+  n->act = carve_tc(p, (int64_t)(s.L - 1) * n->slot_stride);
+  n->dz = carve_tc(p, (int64_t)(s.L - 1) * n->slot_stride);
+  n->pe = nullptr; n->pe_term_stride = 0;
+  if (is_atlas) { n->pe_term_stride = tiles * PE_IMG_BYTES; n->pe = carve_tc(p, 2 * n->pe_term_stride); }
+  n->bits = reinterpret_cast<uint32_t*>(carve_tc(p, (int64_t)(s.L - 1) * rows * 32));
+}
+
+int64_t tc_plan(const MlpShape& ms, const MlpShape& as, int64_t rows_map, int64_t rows_atlas, char* base,
+                TcPlan* out) {
+  char* p = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(base), 1024));
+  TcLayout lay{};
+  plan_net(ms, rows_map, false, p, &lay.map);
+  plan_net(as, rows_atlas, true, p, &lay.atl);
+  if (out) {
+    out->base = base; out->bytes = p - base; out->rows_map = rows_map; out->rows_atlas = rows_atlas;
+  }
+  return p - base;
+}
+
+static TcLayout layout_of(const TcStep& s) {
+  char* p = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(s.plan->base), 1024));
+  TcLayout lay{};
+  plan_net(*s.ms, s.plan->rows_map, false, p, &lay.map);
+  plan_net(*s.as, s.plan->rows_atlas, true, p, &lay.atl);
+  return lay;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight preparation
+// ---------------------------------------------------------------------------------------------
+struct PrepJob {
+  const float* W; int ldw;          // fp32 weight [N][ldw]
+  int n_rows, k0, k_cnt;            // image rows (N index range 0..n_rows) and the K window [k0, k0+k_cnt)
+  int transpose;                    // 0: image(row=n, col=k-k0) = W[n][k];  1: image(row=k, col=n-k0) = W[n][k]
+  char* hi; char* lo;               // destination images (32 KB each, zero padded)
+};
+constexpr int MAX_PREP_JOBS = 96;
+struct PrepJobs { PrepJob j[MAX_PREP_JOBS]; int n; };
+
+__global__ void tc_prep_kernel(const PrepJobs* __restrict__ jobs_ptr) {
+  const PrepJob jb = jobs_ptr->j[blockIdx.x];
+  // one image = 256 rows x 64 cols; thread handles 8 consecutive columns (one 16-byte chunk)
+  for (int e = threadIdx.x; e < 256 * 8; e += blockDim.x) {
+    const int row = e >> 3, c8 = (e & 7) * 8;
+    __half h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int col = c8 + q;
+      float v = 0.f;
+      if (!jb.transpose) {
+        if (row < jb.n_rows && col < jb.k_cnt) v = jb.W[(int64_t)row * jb.ldw + jb.k0 + col];
+      } else {
+        // row = k index of W (output column of the dgrad), col = n - k0
+        if (row < jb.n_rows && col < jb.k_cnt) v = jb.W[(int64_t)(jb.k0 + col) * jb.ldw + row];
+      }
+      split_f16(v * S_W, h[q], l[q]);
+    }
+    const int off = img64_off(row, c8);
+    *reinterpret_cast<uint4*>(jb.hi + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+    *reinterpret_cast<uint4*>(jb.lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared pieces of the fused kernels
+// ---------------------------------------------------------------------------------------------
+struct Pipe {                        // weight-image ring shared by producer and MMA warp
+  uint64_t* full; uint64_t* empty; char* stage;
+  uint32_t it;                       // running item counter (stage = it % NSTAGE, parity from it / NSTAGE)
+  __device__ __forceinline__ int slot() const { return it % NSTAGE; }
+  __device__ __forceinline__ uint32_t parity() const { return (it / NSTAGE) & 1; }
+};
+
+struct TileIter {                    // static round-robin over the live tiles of a group-major batch
+  int ntg, total, cap_tiles;
+  __device__ __forceinline__ void init(int cap, int n_groups, const int* n_valid) {
+    cap_tiles = cap / TM;
+    ntg = n_valid ? min(cap_tiles, (*n_valid + TM - 1) / TM) : cap_tiles;
+    total = ntg * n_groups;
+  }
+  __device__ __forceinline__ int global_tile(int t) const { return (t / ntg) * cap_tiles + (t % ntg); }
+};
+
+struct FwdParams {
+  const float* x;            // mapping: [rows][4] (x, y, t, 0);  atlas: uv [rows][2]
+  float* y;                  // mapping: uv [rows][2];  atlas: y [rows][3]
+  const float* params;       // fp32 parameters of this network
+  int64_t w_off[B200_MAX_LAYERS], b_off[B200_MAX_LAYERS];
+  NetImages img;
+  int cap, n_groups; const int* n_valid;
+};
+
+// One 32-column chunk of a layer output (already activated, fp32): split, pack, optionally store
+// as the next layer's A operand in TMEM and into the tile image in HBM.
+__device__ __forceinline__ void emit_chunk(const float (&v)[32], float scale, int c, int m, uint32_t tmem_lane,
+                                           bool to_tmem, char* img_hi, char* img_lo) {
+  uint32_t ph[16], pl[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __half h0, l0, h1, l1;
+    split_f16(v[2 * i] * scale, h0, l0);
+    split_f16(v[2 * i + 1] * scale, h1, l1);
+    ph[i] = pack2(h0, h1);
+    pl[i] = pack2(l0, l1);
+  }
+  if (to_tmem) {
+    tmem_st16(tmem_lane + TM_AHI + c * 16, ph);
+    tmem_st16(tmem_lane + TM_ALO + c * 16, pl);
+  }
+  if (img_hi) {
+    const int r = m & 7;
+    const int base = (m >> 3) * 4096 + (c >> 1) * 1024 + r * 128;
+#pragma unroll
+    for (int i8 = 0; i8 < 4; ++i8) {
+      const int off = base + ((((c & 1) * 4 + i8) ^ r) << 4);
+      *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(ph[4 * i8], ph[4 * i8 + 1], ph[4 * i8 + 2], ph[4 * i8 + 3]);
+      *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(pl[4 * i8], pl[4 * i8 + 1], pl[4 * i8 + 2], pl[4 * i8 + 3]);
+    }
+  }
+}
+
+// MMAs of one 64-wide k chunk whose A operand is in TMEM (hi at TM_AHI, lo at TM_ALO):
+//   D += A_hi*B_hi + A_lo*B_hi   (B_hi image)    then   D += A_hi*B_lo   (B_lo image)
+__device__ __forceinline__ void mma_chunk_ts(Pipe& pp, uint32_t tmem, int kchunk, uint32_t idesc, bool& first) {
+  {
+    mbar_wait(&pp.full[pp.slot()], pp.parity());
+    tc_fence_after();
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t bd = make_desc(sb + ks * 32, 16, 1024);
+      mma_ts(tmem + TM_D, tmem + TM_AHI + kchunk * 32 + ks * 8, bd, idesc, first ? 0u : 1u);
+      first = false;
+      mma_ts(tmem + TM_D, tmem + TM_ALO + kchunk * 32 + ks * 8, bd, idesc, 1u);
+    }
+    mma_commit(&pp.empty[pp.slot()]);
+    ++pp.it;
+  }
+  {
+    mbar_wait(&pp.full[pp.slot()], pp.parity());
+    tc_fence_after();
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t bd = make_desc(sb + ks * 32, 16, 1024);
+      mma_ts(tmem + TM_D, tmem + TM_AHI + kchunk * 32 + ks * 8, bd, idesc, 1u);
+    }
+    mma_commit(&pp.empty[pp.slot()]);
+    ++pp.it;
+  }
+}
+// same with the A operand in shared memory (64-wide K-major SW128 tile: hi image, lo image)
+__device__ __forceinline__ void mma_chunk_ss(Pipe& pp, uint32_t tmem, const char* a_hi, const char* a_lo,
+                                             uint32_t idesc, bool& first) {
+  const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
+  {
+    mbar_wait(&pp.full[pp.slot()], pp.parity());
+    tc_fence_after();
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t bd = make_desc(sb + ks * 32, 16, 1024);
+      mma_ss(tmem + TM_D, make_desc(ah + ks * 32, 16, 1024), bd, idesc, first ? 0u : 1u);
+      first = false;
+      mma_ss(tmem + TM_D, make_desc(al + ks * 32, 16, 1024), bd, idesc, 1u);
+    }
+    mma_commit(&pp.empty[pp.slot()]);
+    ++pp.it;
+  }
+  {
+    mbar_wait(&pp.full[pp.slot()], pp.parity());
+    tc_fence_after();
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      mma_ss(tmem + TM_D, make_desc(ah + ks * 32, 16, 1024), make_desc(sb + ks * 32, 16, 1024), idesc, 1u);
+    mma_commit(&pp.empty[pp.slot()]);
+    ++pp.it;
+  }
+}
+
+__device__ __forceinline__ void produce_items(Pipe& pp, const char* src, int n_items) {
+  for (int i = 0; i < n_items; ++i) {
+    mbar_wait(&pp.empty[pp.slot()], pp.parity() ^ 1);
+    mbar_expect_tx(&pp.full[pp.slot()], STAGE_BYTES);
+    bulk_g2s(pp.stage + pp.slot() * STAGE_BYTES, src + (int64_t)i * STAGE_BYTES, STAGE_BYTES, &pp.full[pp.slot()]);
+    ++pp.it;
+  }
+}
+
+// dynamic shared memory map (all kernels): [stages][aux tile 32 KB][const floats][barriers]
+constexpr int SMEM_STAGES = NSTAGE * STAGE_BYTES;            // 160 KB
+constexpr int SMEM_AUX = 2 * PE_IMG_BYTES;                   // 32 KB: 64-wide tile (hi, lo)
+constexpr int SMEM_CONST_FLOATS = 3072;                      // 12 KB
+constexpr int SMEM_BARS = 256;
+constexpr int TC_SMEM_BYTES = SMEM_STAGES + SMEM_AUX + SMEM_CONST_FLOATS * 4 + SMEM_BARS + 1024;
+
+struct SmemMap {
+  char* stage; char* aux; float* cst; uint64_t* full; uint64_t* empty; uint64_t* a_ready; uint64_t* d_ready;
+  uint64_t* misc; uint32_t* tmem_slot;
+  __device__ __forceinline__ void init(char* raw) {
+    char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    stage = p; p += SMEM_STAGES;
+    aux = p; p += SMEM_AUX;
+    cst = reinterpret_cast<float*>(p); p += SMEM_CONST_FLOATS * 4;
+    full = reinterpret_cast<uint64_t*>(p);
+    empty = full + NSTAGE;
+    a_ready = empty + NSTAGE;
+    d_ready = a_ready + 1;
+    misc = d_ready + 1;
+    tmem_slot = reinterpret_cast<uint32_t*>(misc + 2);
+  }
+};
+
+__device__ __forceinline__ uint32_t setup_cta(SmemMap& sm, int warp) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    mbar_init(sm.a_ready, TM);
+    mbar_init(sm.d_ready, 1);
+    mbar_init(&sm.misc[0], 1);
+    mbar_init(&sm.misc[1], TM);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(sm.tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *sm.tmem_slot;
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <bool ATLAS>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_constant__ FwdParams P) {
+  extern __shared__ char smem_raw[];
+  SmemMap sm; sm.init(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int L = ATLAS ? 8 : 6;
+  constexpr int FIRST_TC = ATLAS ? 0 : 1;
+  constexpr int LAST_TC = L - 2;
+  constexpr int OUT = ATLAS ? 3 : 2;
+  constexpr int KLAST = ATLAS ? 296 : 256;
+  // constants in shared memory: biases of layers 0..L-2 at [l*256], last-layer weights + bias, (mapping) W0
+  float* s_bias = sm.cst;
+  float* s_wlast = sm.cst + (L - 1) * 256;
+  float* s_blast = s_wlast + OUT * KLAST;
+  float* s_w0 = s_blast + 4;
+  for (int i = threadIdx.x; i < (L - 1) * 256; i += blockDim.x) s_bias[i] = P.params[P.b_off[i >> 8] + (i & 255)];
+  for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i];
+  if (threadIdx.x < OUT) s_blast[threadIdx.x] = P.params[P.b_off[L - 1] + threadIdx.x];
+  if (!ATLAS) for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[i] = P.params[P.w_off[0] + i];
+  const uint32_t tmem = setup_cta(sm, warp);
+  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid);
+  constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      for (int t = blockIdx.x; t < ti.total; t += gridDim.x)
+        for (int l = FIRST_TC; l <= LAST_TC; ++l)
+          produce_items(pp, P.img.w_fwd + P.img.w_fwd_layer[l], P.img.n_chunks_fwd[l] * 2);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      uint32_t a_par = 0;
+      for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
+        for (int l = FIRST_TC; l <= LAST_TC; ++l) {
+          mbar_wait(sm.a_ready, a_par); a_par ^= 1;
+          tc_fence_after();
+          bool first = true;
+          if (l > 0) for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC, first);
+          if (ATLAS && (l == 0 || l == 4 || l == 7)) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + PE_IMG_BYTES, IDESC, first);
+          mma_commit(sm.d_ready);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (128 threads)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                       // row inside the tile == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t d_par = 0;
+    const float inv_scale = 1.0f / (S_ACT * S_W);
+    for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
+      const int gt = ti.global_tile(t);
+      const int64_t row = (int64_t)gt * TM + m;
+      // ---------------- prologue: layer-0 input
+      float pe_cache = 0.f; (void)pe_cache;
+      if (ATLAS) {
+        // positional encoding of in = uv*0.5+0.5 (implicit_neural_networks.py:9-13) into the aux tile
+        const float2 uv = *reinterpret_cast<const float2*>(P.x + row * 2);
+        const float in[2] = {uv.x * 0.5f + 0.5f, uv.y * 0.5f + 0.5f};
+        char* a_hi = sm.aux + 0;
+        char* a_lo = sm.aux + PE_IMG_BYTES;
+        char* g_hi = P.img.pe + (int64_t)gt * PE_IMG_BYTES;
+        char* g_lo = g_hi + P.img.pe_term_stride;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {               // 8 chunks of 8 columns; column = k*4 + {s0,s1,c0,c1}
+          __half h[8], lo[8];
+#pragma unroll
+          for (int half_k = 0; half_k < 2; ++half_k) {
+            const int k = c8 * 2 + half_k;
+            float vals[4] = {0.f, 0.f, 0.f, 0.f};
+            if (k < 10) {
+              const float bk = pe_freq(k);
+              const float a0 = in[0] * bk, a1 = in[1] * bk;
+              vals[0] = sinf(a0); vals[1] = sinf(a1); vals[2] = cosf(a0); vals[3] = cosf(a1);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_f16(vals[e] * S_ACT, h[half_k * 4 + e], lo[half_k * 4 + e]);
+          }
+          const int off = img64_off(m, c8 * 8);
+          const uint4 vh = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+          const uint4 vl = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+          *reinterpret_cast<uint4*>(a_hi + off) = vh;
+          *reinterpret_cast<uint4*>(a_lo + off) = vl;
+          *reinterpret_cast<uint4*>(g_hi + off) = vh;
+          *reinterpret_cast<uint4*>(g_lo + off) = vl;
+        }
+        fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the MMA
+        tc_fence_before();
+        mbar_arrive(sm.a_ready);
+      } else {
+        // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0)
+        const float4 xv = *reinterpret_cast<const float4*>(P.x + row * 4);
+        char* ih = P.img.act + 0 * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
+        char* il = ih + P.img.term_stride;
+        uint32_t bits[8];
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[32];
+          uint32_t bw = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int n = c * 32 + i;
+            float z = s_bias[n];
+            z = fmaf(xv.x, s_w0[n * 3 + 0], z);
+            z = fmaf(xv.y, s_w0[n * 3 + 1], z);
+            z = fmaf(xv.z, s_w0[n * 3 + 2], z);
+            bw |= (z > 0.f ? 1u : 0u) << i;
+            v[i] = fmaxf(z, 0.f);
+          }
+          bits[c] = bw;
+          emit_chunk(v, S_ACT, c, m, tlane, true, ih, il);
+        }
+        uint4* bdst = reinterpret_cast<uint4*>(P.img.bits + ((int64_t)0 * P.img.rows + row) * 8);
+        bdst[0] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+        bdst[1] = make_uint4(bits[4], bits[5], bits[6], bits[7]);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(sm.a_ready);
+      }
+      // ---------------- tensor-core layers
+      float outacc[OUT];
+#pragma unroll
+      for (int j = 0; j < OUT; ++j) outacc[j] = 0.f;
+#pragma unroll 1
+      for (int l = FIRST_TC; l <= LAST_TC; ++l) {
+        mbar_wait(sm.d_ready, d_par); d_par ^= 1;
+        tc_fence_after();
+        const bool last = (l == LAST_TC);
+        char* ih = P.img.act + (int64_t)l * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
+        char* il = ih + P.img.term_stride;
+        const float* bias = s_bias + l * 256;
+        uint32_t bits[8];
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tlane + TM_D + c * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+          uint32_t bw = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float z = fmaf(__uint_as_float(raw[i]), inv_scale, bias[c * 32 + i]);
+            bw |= (z > 0.f ? 1u : 0u) << i;
+            v[i] = fmaxf(z, 0.f);
+          }
+          bits[c] = bw;
+          if (last) {
+#pragma unroll
+            for (int j = 0; j < OUT; ++j) {
+              float a = outacc[j];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) a = fmaf(v[i], s_wlast[j * KLAST + c * 32 + i], a);
+              outacc[j] = a;
+            }
+          }
+          emit_chunk(v, S_ACT, c, m, tlane, !last, ih, il);
+        }
+        uint4* bdst = reinterpret_cast<uint4*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8);
+        bdst[0] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+        bdst[1] = make_uint4(bits[4], bits[5], bits[6], bits[7]);
+        if (!last) {
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(sm.a_ready);
+        }
+      }
+      // ---------------- output layer (+ skip part for the atlas) and tanh
+      if (ATLAS) {
+        const char* a_hi = sm.aux;
+        const char* a_lo = sm.aux + PE_IMG_BYTES;
+#pragma unroll 1
+        for (int k = 0; k < PE_COLS; ++k) {
+          const int off = img64_off(m, k);
+          const float pv = (__half2float(*reinterpret_cast<const __half*>(a_hi + off)) +
+                            __half2float(*reinterpret_cast<const __half*>(a_lo + off))) * (1.0f / S_ACT);
+#pragma unroll
+          for (int j = 0; j < OUT; ++j) outacc[j] = fmaf(pv, s_wlast[j * KLAST + 256 + k], outacc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < OUT; ++j) P.y[row * OUT + j] = tanhf(outacc[j] + s_blast[j]);
+      // all epilogue threads are done with the aux tile / D before the next tile's prologue overwrites them:
+      // the a_ready arrival of the next prologue is per-thread ordered after this point, and the MMA warp
+      // only reads aux after all 128 arrivals.  The aux tile itself is rewritten by the same thread rows.
+      if (ATLAS) {
+        // other threads may still be reading their own rows only (row-private), so no barrier is needed
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// =============================================================================================
+// backward (dgrad chain + last-layer / first-layer / bias gradients)
+// =============================================================================================
+struct BwdParams {
+  const float* dy;           // mapping: d_uv [rows][2];  atlas: d_y [rows][3]
+  const float* y;            // network output (tanh applied)
+  const float* x;            // mapping: x_map [rows][4]
+  float* d_in;               // atlas: d_uv [rows][2] (accumulated: += 0.5 * dPE/din)
+  const float* params;       // fp32 parameters of this network
+  float* grads;              // fp32 gradient block of this network
+  int64_t w_off[B200_MAX_LAYERS], b_off[B200_MAX_LAYERS];
+  NetImages img;
+  int cap, n_groups; const int* n_valid;
+  const int* gmax_bits;      // max |dL/dy| of this iteration as float bits
+};
+
+// column sums over the 32 rows of a warp: lane j ends with sum_rows v[j]
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float send = (lane & 16) ? v[i] : v[i + 16];
+    const float keep = (lane & 16) ? v[i + 16] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = (lane & 8) ? a[i] : a[i + 8];
+    const float keep = (lane & 8) ? a[i + 8] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = (lane & 4) ? b[i] : b[i + 4];
+    const float keep = (lane & 4) ? b[i + 4] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float d[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = (lane & 2) ? c[i] : c[i + 2];
+    const float keep = (lane & 2) ? c[i + 2] : c[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float send = (lane & 1) ? d[0] : d[1];
+  const float keep = (lane & 1) ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+__device__ __forceinline__ void grad_scales(const int* gmax_bits, float& s_g, float& inv_sg) {
+  const float mx = __int_as_float(*gmax_bits);
+  int e = 0;
+  if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);        // mx < 2^e
+  e = max(-60, min(60, e));
+  s_g = ldexpf(1.0f, 10 - e);                           // mx * s_g < 1024
+  inv_sg = ldexpf(1.0f, e - 10);
+}
+
+template <bool ATLAS>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ char smem_raw[];
+  SmemMap sm; sm.init(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int L = ATLAS ? 8 : 6;
+  constexpr int OUT = ATLAS ? 3 : 2;
+  constexpr int KLAST = ATLAS ? 296 : 256;
+  // dgrad layers run from L-2 down to LOW (atlas: additionally the 64-wide dPE product through layer 0)
+  constexpr int LOW = 1;
+  // shared constants: last-layer weights; bias-gradient accumulators for layers 0..L-2 at s_bacc[l*256];
+  // first-layer weight gradient accumulator (mapping: 256x3); last-layer weight gradient accumulator
+  float* s_wlast = sm.cst;                               // OUT*KLAST (<= 888)
+  float* s_bacc = sm.cst + 896;                          // (L-1)*256 (<= 1792)
+  float* s_w0acc = s_bacc + (L - 1) * 256;               // mapping: 768   (896+1280+768 = 2944 <= 3072)
+  for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i];
+  for (int i = threadIdx.x; i < (L - 1) * 256 + (ATLAS ? 0 : 768); i += blockDim.x) s_bacc[i] = 0.f;
+  const uint32_t tmem = setup_cta(sm, warp);
+  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid);
+  constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
+  constexpr uint32_t IDESC64 = make_idesc(128, 64, 0, 0);
+  float s_g, inv_sg;
+  grad_scales(P.gmax_bits, s_g, inv_sg);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      uint32_t h_par = 0;
+      for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
+        const int gt = ti.global_tile(t);
+        // stage 0..3 <- the input image of the last layer (h_{L-2}: hi 64 KB, lo 64 KB) for its weight
+        // gradient; the ring must be drained of this tile's predecessors first (empty waits do that)
+        const char* hsrc = P.img.act + (int64_t)(L - 2) * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
+        for (int i = 0; i < 4; ++i) {
+          mbar_wait(&pp.empty[pp.slot()], pp.parity() ^ 1);
+          mbar_expect_tx(&pp.full[pp.slot()], STAGE_BYTES);
+          const char* src = hsrc + (i >> 1) * P.img.term_stride + (i & 1) * STAGE_BYTES;
+          bulk_g2s(pp.stage + pp.slot() * STAGE_BYTES, src, STAGE_BYTES, &pp.full[pp.slot()]);
+          ++pp.it;
+        }
+        if (ATLAS) {
+          // aux tile <- positional-encoding image of this tile (hi, lo), completion on misc[0]
+          mbar_wait(&sm.misc[1], h_par ^ 1);             // previous tile's readers are done with aux
+          mbar_expect_tx(&sm.misc[0], 2 * PE_IMG_BYTES);
+          bulk_g2s(sm.aux, P.img.pe + (int64_t)gt * PE_IMG_BYTES, PE_IMG_BYTES, &sm.misc[0]);
+          bulk_g2s(sm.aux + PE_IMG_BYTES, P.img.pe + P.img.pe_term_stride + (int64_t)gt * PE_IMG_BYTES, PE_IMG_BYTES,
+                   &sm.misc[0]);
+          h_par ^= 1;
+        }
+        for (int l = L - 2; l >= LOW; --l) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[l], 8);
+        if (ATLAS) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[0], 8);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      uint32_t a_par = 0;
+      for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
+        // the four h stages are consumed by the epilogue warps; they are released through `empty` by
+        // this thread once the epilogue signalled (a_ready of the first dgrad layer)
+        const uint32_t it_h = pp.it;
+        pp.it += 4;
+        for (int l = L - 2; l >= LOW; --l) {
+          mbar_wait(sm.a_ready, a_par); a_par ^= 1;
+          tc_fence_after();
+          if (l == L - 2) {
+            // epilogue finished reading the h stages: hand them back to the producer
+            for (int i = 0; i < 4; ++i) mbar_arrive(&pp.empty[(it_h + i) % NSTAGE]);
+          }
+          bool first = true;
+          for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC, first);
+          mma_commit(sm.d_ready);
+        }
+        if (ATLAS) {
+          mbar_wait(sm.a_ready, a_par); a_par ^= 1;
+          tc_fence_after();
+          bool first = true;
+          for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC64, first);
+          mma_commit(sm.d_ready);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t d_par = 0, aux_par = 0;
+    uint32_t h_it = 0;                                    // mirrors the producer/MMA item counter
+    const float inv_dgrad = inv_sg * (1.0f / S_W);        // D = (S_g dZ)(S_w W)
+    for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
+      const int gt = ti.global_tile(t);
+      const int64_t row = (int64_t)gt * TM + m;
+      // ---------------- output layer: tanh', weight/bias gradient, dA_{L-1}
+      float dzl[OUT];
+#pragma unroll
+      for (int j = 0; j < OUT; ++j) {
+        const float yv = P.y[row * OUT + j];
+        dzl[j] = P.dy[row * OUT + j] * (1.0f - yv * yv);
+      }
+      // wait for the h image (4 stages) [and the PE tile]
+      const char* hst[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t it = h_it + i;
+        mbar_wait(&sm.full[it % NSTAGE], (it / NSTAGE) & 1);
+        hst[i] = sm.stage + (it % NSTAGE) * STAGE_BYTES;
+      }
+      if (ATLAS) { mbar_wait(&sm.misc[0], aux_par); }
+      // per-tile last-layer weight gradient: dW[j][k] = sum_m dz[m][j] * a[m][k].  Row m's dz is
+      // broadcast through shared memory (cst scratch after the accumulators is full, so use shuffles):
+      // thread (q, lane) owns columns k = q*64 + lane and q*64 + 32 + lane and loops over the 128 rows.
+      {
+        // stash dz of all 128 rows in the first bytes of the d_ready-free region: use s_w0acc tail? keep
+        // it simple: a small static shared array
+        __shared__ float s_dz[TM][4];
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) s_dz[m][j] = dzl[j];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float acc[2][OUT];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int j = 0; j < OUT; ++j) acc[u][j] = 0.f;
+        const int k0 = q * 64 + lane, k1 = k0 + 32;
+#pragma unroll 4
+        for (int r = 0; r < TM; ++r) {
+          const int o0 = img_off(r, k0), o1 = img_off(r, k1);
+          // image = [hi: stages 0,1 (64 KB)][lo: stages 2,3]; each stage holds 8 groups (32 KB)
+          const float a0 = (__half2float(*reinterpret_cast<const __half*>(hst[o0 >> 15] + (o0 & 32767))) +
+                            __half2float(*reinterpret_cast<const __half*>(hst[2 + (o0 >> 15)] + (o0 & 32767)))) *
+                           (1.0f / S_ACT);
+          const float a1 = (__half2float(*reinterpret_cast<const __half*>(hst[o1 >> 15] + (o1 & 32767))) +
+                            __half2float(*reinterpret_cast<const __half*>(hst[2 + (o1 >> 15)] + (o1 & 32767)))) *
+                           (1.0f / S_ACT);
+#pragma unroll
+          for (int j = 0; j < OUT; ++j) {
+            const float dzv = s_dz[r][j];
+            acc[0][j] = fmaf(dzv, a0, acc[0][j]);
+            acc[1][j] = fmaf(dzv, a1, acc[1][j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) {
+          atomicAdd(P.grads + P.w_off[L - 1] + j * KLAST + k0, acc[0][j]);
+          atomicAdd(P.grads + P.w_off[L - 1] + j * KLAST + k1, acc[1][j]);
+        }
+        if (ATLAS && m < PE_COLS) {
+          // skip part of the output layer: dW[j][256+k] = sum_m dz[m][j] * pe[m][k], thread m<40 owns k=m
+          float pacc[OUT];
+#pragma unroll
+          for (int j = 0; j < OUT; ++j) pacc[j] = 0.f;
+          for (int r = 0; r < TM; ++r) {
+            const int off = img64_off(r, m);
+            const float pv = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
+                              __half2float(*reinterpret_cast<const __half*>(sm.aux + PE_IMG_BYTES + off))) *
+                             (1.0f / S_ACT);
+#pragma unroll
+            for (int j = 0; j < OUT; ++j) pacc[j] = fmaf(s_dz[r][j], pv, pacc[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < OUT; ++j) atomicAdd(P.grads + P.w_off[L - 1] + j * KLAST + 256 + m, pacc[j]);
+        }
+        // bias gradient of the output layer
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) {
+          float sj = dzl[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, o);
+          if (lane == 0) atomicAdd(P.grads + P.b_off[L - 1] + j, sj);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");        // s_dz reuse by the next tile
+      }
+      h_it += 4 + (L - 2 - LOW + 1) * 8 + (ATLAS ? 8 : 0);
+      // dA_{L-1}[k] = sum_j dz[j] W_last[j][k], masked by relu'(h_{L-2}) -> dZ_{L-2}
+      {
+        const uint32_t* bsrc = P.img.bits + ((int64_t)(L - 2) * P.img.rows + row) * 8;
+        const uint4 b0 = *reinterpret_cast<const uint4*>(bsrc), b1 = *reinterpret_cast<const uint4*>(bsrc + 4);
+        const uint32_t bits[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        char* ih = P.img.dz + (int64_t)(L - 2) * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
+        char* il = ih + P.img.term_stride;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < OUT; ++j) a = fmaf(dzl[j], s_wlast[j * KLAST + c * 32 + i], a);
+            v[i] = ((bits[c] >> i) & 1u) ? a : 0.f;
+          }
+          const float cs = warp_colsum32(v, lane);
+          atomicAdd(&s_bacc[(L - 2) * 256 + c * 32 + lane], cs);
+          emit_chunk(v, s_g, c, m, tlane, true, ih, il);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(sm.a_ready);
+      }
+      // ---------------- hidden layers: dA_l = dZ_l W_l  ->  dZ_{l-1}
+#pragma unroll 1
+      for (int l = L - 2; l >= LOW; --l) {
+        mbar_wait(sm.d_ready, d_par); d_par ^= 1;
+        tc_fence_after();
+        const int slot = l - 1;                           // produces dZ_{l-1}
+        const uint32_t* bsrc = P.img.bits + ((int64_t)slot * P.img.rows + row) * 8;
+        const uint4 b0 = *reinterpret_cast<const uint4*>(bsrc), b1 = *reinterpret_cast<const uint4*>(bsrc + 4);
+        const uint32_t bits[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const bool need_img = ATLAS || slot >= 1;         // mapping dZ_0 feeds only the CUDA-core layer-0 gradient
+        const bool need_tmem = ATLAS ? true : (slot >= 1);
+        char* ih = P.img.dz + (int64_t)slot * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
+        char* il = ih + P.img.term_stride;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!ATLAS && slot == 0) xv = *reinterpret_cast<const float4*>(P.x + row * 4);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tlane + TM_D + c * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ((bits[c] >> i) & 1u) ? __uint_as_float(raw[i]) * inv_dgrad : 0.f;
+          const float cs = warp_colsum32(v, lane);
+          atomicAdd(&s_bacc[slot * 256 + c * 32 + lane], cs);
+          if (!ATLAS && slot == 0) {
+            // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.x;
+            atomicAdd(&s_w0acc[(c * 32 + lane) * 3 + 0], warp_colsum32(w, lane));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.y;
+            atomicAdd(&s_w0acc[(c * 32 + lane) * 3 + 1], warp_colsum32(w, lane));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.z;
+            atomicAdd(&s_w0acc[(c * 32 + lane) * 3 + 2], warp_colsum32(w, lane));
+          }
+          if (need_img || need_tmem) emit_chunk(v, s_g, c, m, tlane, need_tmem, need_img ? ih : nullptr, il);
+        }
+        if (need_tmem) {
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(sm.a_ready);
+        }
+      }
+      if (ATLAS) {
+        // ---------------- dPE = dZ_0 W_0 (64 columns, 40 real) -> d(in) -> d_uv += 0.5 * d(in)
+        mbar_wait(sm.d_ready, d_par); d_par ^= 1;
+        tc_fence_after();
+        float din[2] = {0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tlane + TM_D + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = c * 32 + i;
+            if (col < PE_COLS) {
+              const int k = col >> 2, e = col & 3;         // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
+              const float g = __uint_as_float(raw[i]) * inv_dgrad;
+              // partner value: d sin = cos * b,  d cos = -sin * b
+              const int pcol = (e < 2) ? col + 2 : col - 2;
+              const int off = img64_off(m, pcol);
+              const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
+                                     __half2float(*reinterpret_cast<const __half*>(sm.aux + PE_IMG_BYTES + off))) *
+                                    (1.0f / S_ACT);
+              const float bk = pe_freq(k);
+              din[e & 1] += (e < 2) ? g * partner * bk : -g * partner * bk;
+            }
+          }
+        }
+        float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
+        float2 cur = *dst;
+        cur.x += 0.5f * din[0];
+        cur.y += 0.5f * din[1];
+        *dst = cur;
+        mbar_arrive(&sm.misc[1]);                         // aux tile may be overwritten
+        aux_par ^= 1;
+      }
+    }
+    // flush the per-CTA accumulators
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < (L - 1) * 256; i += 128) {
+      const float v = s_bacc[i];
+      if (v != 0.f) atomicAdd(P.grads + P.b_off[i >> 8] + (i & 255), v);
+    }
+    if (!ATLAS)
+      for (int i = et; i < 768; i += 128) {
+        const float v = s_w0acc[i];
+        if (v != 0.f) atomicAdd(P.grads + P.w_off[0] + i, v);
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// =============================================================================================
+// weight gradients of the 256-wide layers:  dW[n][k] += sum_rows dZ[row][n] * H[row][k]
+// =============================================================================================
+struct WgradItem {
+  const char* a_img;      // dZ images (hi; lo at +a_term)   [tile][64 KB]
+  const char* b_img;      // input images (hi; lo at +b_term) [tile][64 KB] or [tile][16 KB] when b_cols == 64
+  int64_t a_term, b_term;
+  float* out; int ld_out; // fp32 dW block [256][ld_out], columns [0, n_cols)
+  int b_cols;             // 256 or 64
+  int n_cols;             // real columns to write (<= b_cols)
+  int cap, n_groups;      // row geometry of the network this item belongs to
+  int split, n_split;     // this CTA's share of the live tiles
+};
+constexpr int MAX_WGRAD_ITEMS = 320;
+struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; };
+
+constexpr int WG_STAGE = 65536;          // 32 rows: A hi 16K | A lo 16K | B hi 16K | B lo 16K
+constexpr int WG_NSTAGE = 3;
+constexpr int WG_SMEM = WG_NSTAGE * WG_STAGE + 1024 + 256;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_valid, const int* __restrict__ gmax_bits) {
+  extern __shared__ char smem_raw[];
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  char* stage = p;
+  uint64_t* full = reinterpret_cast<uint64_t*>(p + WG_NSTAGE * WG_STAGE);
+  uint64_t* empty = full + WG_NSTAGE;
+  uint64_t* d_ready = empty + WG_NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(d_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if ((int)blockIdx.x >= items->n) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem, TMEM_COLS); return; }
+  const WgradItem W = items->it[blockIdx.x];
+  TileIter ti; ti.init(W.cap, W.n_groups, n_valid);
+  const int t_begin = (int)((int64_t)ti.total * W.split / W.n_split);
+  const int t_end = (int)((int64_t)ti.total * (W.split + 1) / W.n_split);
+  const int b_tile_bytes = W.b_cols == 256 ? TILE_IMG_BYTES : PE_IMG_BYTES;
+  const int b_chunk = b_tile_bytes / 4;          // bytes of a 32-row chunk of one term
+  const uint32_t idesc = make_idesc(128, W.b_cols == 256 ? 256 : 64, 1, 1);
+  const int n_steps = (t_end - t_begin) * 4;     // 32-row steps
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < n_steps; ++s) {
+        const int slot = s % WG_NSTAGE;
+        const uint32_t par = (s / WG_NSTAGE) & 1;
+        mbar_wait(&empty[slot], par ^ 1);
+        const int gt = ti.global_tile(t_begin + (s >> 2));
+        const int ch = s & 3;
+        char* dst = stage + slot * WG_STAGE;
+        mbar_expect_tx(&full[slot], 2 * 16384 + 2 * b_chunk);
+        const char* a = W.a_img + (int64_t)gt * TILE_IMG_BYTES + ch * 16384;
+        bulk_g2s(dst, a, 16384, &full[slot]);
+        bulk_g2s(dst + 16384, a + W.a_term, 16384, &full[slot]);
+        const char* b = W.b_img + (int64_t)gt * b_tile_bytes + ch * b_chunk;
+        bulk_g2s(dst + 32768, b, b_chunk, &full[slot]);
+        bulk_g2s(dst + 49152, b + W.b_term, b_chunk, &full[slot]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t a_lbo = 1024, a_sbo = 4096;
+      const uint32_t b_lbo = 1024, b_sbo = W.b_cols == 256 ? 4096 : 1024;
+      const uint32_t b_kstep = W.b_cols == 256 ? 8192 : 2048;     // 16 rows = 2 groups
+      const uint32_t d_half = W.b_cols == 256 ? 256 : 64;         // TMEM columns per M-half
+      for (int s = 0; s < n_steps; ++s) {
+        const int slot = s % WG_NSTAGE;
+        mbar_wait(&full[slot], (s / WG_NSTAGE) & 1);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(stage + slot * WG_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+            const uint32_t acc = (s | ks) ? 1u : 0u;
+            const uint32_t d = tmem + mh * d_half;
+            const uint64_t a_hi = make_desc(sb + ks * 8192 + mh * 2048, a_lbo, a_sbo);
+            const uint64_t a_lo = make_desc(sb + 16384 + ks * 8192 + mh * 2048, a_lbo, a_sbo);
+            const uint64_t b_hi = make_desc(sb + 32768 + ks * b_kstep, b_lbo, b_sbo);
+            const uint64_t b_lo = make_desc(sb + 49152 + ks * b_kstep, b_lbo, b_sbo);
+            mma_ss(d, a_hi, b_hi, idesc, acc);
+            mma_ss(d, a_hi, b_lo, idesc, 1u);
+            mma_ss(d, a_lo, b_hi, idesc, 1u);
+          }
+        }
+        mma_commit(&empty[slot]);
+      }
+      mma_commit(d_ready);
+    }
+  } else if (n_steps > 0) {
+    float s_g, inv_sg;
+    grad_scales(gmax_bits, s_g, inv_sg);
+    const float inv = inv_sg * (1.0f / S_ACT);
+    const int q = warp & 3;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    mbar_wait(d_ready, 0);
+    tc_fence_after();
+    const uint32_t d_half = W.b_cols == 256 ? 256 : 64;
+    for (int mh = 0; mh < 2; ++mh) {
+      const int n = mh * 128 + q * 32 + lane;              // output row (layer output index)
+      float* orow = W.out + (int64_t)n * W.ld_out;
+      for (int c = 0; c < W.b_cols / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tlane + mh * d_half + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = c * 32 + i;
+          if (col < W.n_cols) atomicAdd(orow + col, __uint_as_float(raw[i]) * inv);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+static int ensure_attrs() {
+  static bool done = false;
+  if (done) return B200_OK;
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+  done = true;
+  return B200_OK;
+}
+
+// The job / item tables live at the start of the TC workspace region (device memory) and are rebuilt
+// by a tiny kernel-free cudaMemcpyAsync from a host staging copy kept alive per call site.  They depend
+// only on pointers, so they are uploaded once per (workspace, geometry) and reused inside graphs.
+struct HostTables {
+  const void* key_base = nullptr; int key_cap = 0, key_groups = 0; const void* key_params = nullptr;
+  const void* key_grads = nullptr; bool key_atlas = false;
+  PrepJobs* d_prep = nullptr; WgradItems* d_wg = nullptr;
+  int n_wg = 0, n_prep = 0;
+};
+constexpr int MAX_TABLES = 16;
+static HostTables g_tabs[MAX_TABLES];
+static int g_n_tabs = 0;
+
+static HostTables* find_tables(const TcStep& s) {
+  const bool atlas = s.y_atlas != nullptr;
+  for (int i = 0; i < g_n_tabs; ++i) {
+    HostTables& t = g_tabs[i];
+    if (t.key_base == s.plan->base && t.key_cap == s.cap && t.key_groups == s.n_groups && t.key_params == s.params &&
+        t.key_grads == s.grads && t.key_atlas == atlas)
+      return &t;
+  }
+  return nullptr;
+}
+
+static void add_prep(PrepJobs& pj, const float* W, int ldw, int n_rows, int k0, int k_cnt, int transpose, char* dst) {
+  PrepJob& j = pj.j[pj.n++];
+  j.W = W; j.ldw = ldw; j.n_rows = n_rows; j.k0 = k0; j.k_cnt = k_cnt; j.transpose = transpose;
+  j.hi = dst; j.lo = dst + STAGE_BYTES;
+}
+
+static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, HostTables** out) {
+  if (HostTables* t = find_tables(s)) { *out = t; return B200_OK; }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs == cudaStreamCaptureStatusActive) {
+    set_error("tensor-core tables must be built by one eager call before graph capture");
+    return B200_ERR_INVALID;
+  }
+  if (g_n_tabs == MAX_TABLES) g_n_tabs = 0;          // recycle (device buffers are reused)
+  HostTables& g_tab = g_tabs[g_n_tabs];
+  if (!g_tab.d_prep) {
+    B200_CHECK_CUDA(cudaMalloc(&g_tab.d_prep, sizeof(PrepJobs)));
+    B200_CHECK_CUDA(cudaMalloc(&g_tab.d_wg, sizeof(WgradItems)));
+  }
+  static PrepJobs pj; static WgradItems wi;
+  pj.n = 0; wi.n = 0;
+  const float* pm = s.params;
+  const float* pa = s.params + s.ms->total;
+  // ---- forward / dgrad weight images
+  for (int net = 0; net < 2; ++net) {
+    const MlpShape& sh = net ? *s.as : *s.ms;
+    const NetImages& im = net ? lay.atl : lay.map;
+    const float* pp = net ? pa : pm;
+    for (int l = 0; l < sh.L; ++l) {
+      char* dst = im.w_fwd + im.w_fwd_layer[l];
+      if (im.n_chunks_fwd[l] == 0) continue;
+      const float* W = pp + sh.w_off[l];
+      int item = 0;
+      if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+      if (net && (l == 0 || sh.skip[l]))
+        add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+    }
+    for (int l = 0; l < sh.L - 1; ++l) {
+      const bool used = net ? true : (l >= 1);
+      if (!used) continue;
+      char* dst = im.w_bwd + im.w_bwd_layer[l];
+      const float* W = pp + sh.w_off[l];
+      // image rows = input index k of layer l (256, or 40 for atlas layer 0), chunk over the output index n
+      const int rows = (net && l == 0) ? PE_COLS : 256;
+      for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], rows, kc * 64, 64, 1, dst + (int64_t)kc * 2 * STAGE_BYTES);
+    }
+  }
+  // ---- wgrad items
+  const int sms = sm_count();
+  const int map_layers = s.ms->L - 2;              // layers 1..L-2
+  const int atl_layers = s.as->L - 2;              // layers 1..L-2 main
+  // weights: mapping rows dominate; distribute ~sms CTAs proportionally to rows
+  const double rows_map = (double)s.n_groups, rows_atl = 3.0;
+  const double work = map_layers * rows_map + atl_layers * rows_atl + 2 * rows_atl * 0.3;
+  auto splits_for = [&](double rows) { int v = (int)(rows / work * sms + 0.5); return v < 1 ? 1 : v; };
+  float* gm = s.grads;
+  float* ga = s.grads + s.ms->total;
+  auto add_item = [&](const NetImages& im, int slot_a, const char* b_img, int64_t b_term, int b_cols, float* out,
+                      int ld_out, int n_cols, int cap, int groups, int n_split) {
+    for (int sp = 0; sp < n_split; ++sp) {
+      WgradItem& it = wi.it[wi.n++];
+      it.a_img = im.dz + (int64_t)slot_a * im.slot_stride; it.a_term = im.term_stride;
+      it.b_img = b_img; it.b_term = b_term; it.out = out; it.ld_out = ld_out; it.b_cols = b_cols; it.n_cols = n_cols;
+      it.cap = cap; it.n_groups = groups; it.split = sp; it.n_split = n_split;
+    }
+  };
+  {
+    const int sp_m = splits_for(rows_map), sp_a = splits_for(rows_atl), sp_x = splits_for(rows_atl * 0.3);
+    for (int l = 1; l <= s.ms->L - 2; ++l)
+      add_item(lay.map, l, lay.map.act + (int64_t)(l - 1) * lay.map.slot_stride, lay.map.term_stride, 256,
+               gm + s.ms->w_off[l], s.ms->K[l], 256, s.cap, s.n_groups, sp_m);
+    if (s.y_atlas != nullptr) {
+      for (int l = 1; l <= s.as->L - 2; ++l)
+        add_item(lay.atl, l, lay.atl.act + (int64_t)(l - 1) * lay.atl.slot_stride, lay.atl.term_stride, 256,
+                 ga + s.as->w_off[l], s.as->K[l], 256, s.cap, 3, sp_a);
+      // positional-encoding parts: layer 0 and the skip layer(s) below the output layer
+      add_item(lay.atl, 0, lay.atl.pe, lay.atl.pe_term_stride, 64, ga + s.as->w_off[0], s.as->K[0], PE_COLS, s.cap, 3, sp_x);
+      for (int l = 1; l <= s.as->L - 2; ++l)
+        if (s.as->skip[l])
+          add_item(lay.atl, l, lay.atl.pe, lay.atl.pe_term_stride, 64, ga + s.as->w_off[l] + 256, s.as->K[l], PE_COLS,
+                   s.cap, 3, sp_x);
+    }
+  }
+  if (pj.n > MAX_PREP_JOBS || wi.n > MAX_WGRAD_ITEMS) { set_error("table overflow"); return B200_ERR_INVALID; }
+  B200_CHECK_CUDA(cudaMemcpyAsync(g_tab.d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(g_tab.d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaStreamSynchronize(st));
+  g_tab.n_wg = wi.n; g_tab.n_prep = pj.n;
+  g_tab.key_base = s.plan->base; g_tab.key_cap = s.cap; g_tab.key_groups = s.n_groups; g_tab.key_params = s.params;
+  g_tab.key_grads = s.grads; g_tab.key_atlas = s.y_atlas != nullptr;
+  ++g_n_tabs;
+  *out = &g_tab;
+  return B200_OK;
+}
+
+static void fill_fwd(FwdParams& P, const MlpShape& sh, const NetImages& im, const float* x, float* y,
+                     const float* params, int cap, int groups, const int* n_valid) {
+  P.x = x; P.y = y; P.params = params; P.img = im; P.cap = cap; P.n_groups = groups; P.n_valid = n_valid;
+  for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
+}
+
+static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
+  B200_PROPAGATE(ensure_attrs());
+  const TcLayout lay = layout_of(s);
+  HostTables* tab = nullptr;
+  B200_PROPAGATE(build_tables(s, lay, st, &tab));
+  // weight images of both networks — every step, since Adam changed the parameters
+  tc_prep_kernel<<<tab->n_prep, 256, 0, st>>>(tab->d_prep);
+  B200_CHECK_LAUNCH();
+  const int tiles_map = s.n_groups * (s.cap / TM);
+  FwdParams pm{};
+  fill_fwd(pm, *s.ms, lay.map, s.x_map, s.uv, s.params, s.cap, s.n_groups, s.counters);
+  timer_begin(TAG_MAP_FWD, st);
+  tc_fwd_kernel<false><<<min(sm_count(), tiles_map), TC_THREADS, TC_SMEM_BYTES, st>>>(pm);
+  timer_end(TAG_MAP_FWD, st);
+  B200_CHECK_LAUNCH();
+  if (with_atlas) {
+    FwdParams pa{};
+    fill_fwd(pa, *s.as, lay.atl, s.uv, s.y_atlas, s.params + s.ms->total, s.cap, 3, s.counters);
+    timer_begin(TAG_ATLAS_FWD, st);
+    tc_fwd_kernel<true><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pa);
+    timer_end(TAG_ATLAS_FWD, st);
+    B200_CHECK_LAUNCH();
+  }
+  return B200_OK;
+}
+
+static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
+  const TcLayout lay = layout_of(s);
+  HostTables* tab = find_tables(s);
+  if (!tab) { set_error("tensor-core backward called before forward"); return B200_ERR_INVALID; }
+  const int* gmax = s.counters + 3;
+  auto fill = [&](BwdParams& P, const MlpShape& sh, const NetImages& im, const float* dy, const float* y,
+                  const float* x, float* d_in, const float* params, float* grads, int groups) {
+    P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = im;
+    P.cap = s.cap; P.n_groups = groups; P.n_valid = s.counters; P.gmax_bits = gmax;
+    for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
+  };
+  if (with_atlas) {
+    BwdParams pa{};
+    fill(pa, *s.as, lay.atl, s.d_y, s.y_atlas, nullptr, const_cast<float*>(s.d_uv), s.params + s.ms->total,
+         s.grads + s.ms->total, 3);
+    timer_begin(TAG_ATLAS_BWD, st);
+    tc_bwd_kernel<true><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pa);
+    timer_end(TAG_ATLAS_BWD, st);
+    B200_CHECK_LAUNCH();
+  }
+  BwdParams pm{};
+  fill(pm, *s.ms, lay.map, s.d_uv, s.uv, s.x_map, nullptr, s.params, s.grads, s.n_groups);
+  timer_begin(TAG_MAP_BWD, st);
+  tc_bwd_kernel<false><<<min(sm_count(), s.n_groups * (s.cap / TM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pm);
+  timer_end(TAG_MAP_BWD, st);
+  B200_CHECK_LAUNCH();
+  timer_begin(TAG_WGRAD, st);
+  tc_wgrad_kernel<<<tab->n_wg, TC_THREADS, WG_SMEM, st>>>(tab->d_wg, s.counters, gmax);
+  timer_end(TAG_WGRAD, st);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int tc_atlas_forward(const TcStep& s, cudaStream_t st) { return run_forward(s, true, st); }
+int tc_atlas_backward(const TcStep& s, cudaStream_t st) { return run_backward(s, true, st); }
+int tc_mapping_forward(const TcStep& s, cudaStream_t st) { return run_forward(s, false, st); }
+int tc_mapping_backward(const TcStep& s, cudaStream_t st) { return run_backward(s, false, st); }
+
 }  // namespace b200

@@ -165,11 +165,12 @@ int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int3
 /* ------------------------------------------------------------------------------------------
  * Optimiser — replaces torch.optim.Adam.step() (src/stage1_neural_atlas.py:132-134,231) on a
  * flat buffer.  `step` is a device int64 counter (steps already taken); it is incremented by
- * the kernel so the call can sit inside a replayed CUDA graph.  grad_scale multiplies the
+ * the kernel so the call can sit inside a replayed CUDA graph.  lr/betas/eps are doubles because
+ * torch derives 1-beta and the bias corrections from Python floats.  grad_scale multiplies the
  * gradient first (1/world for an averaged all-reduce; 1.0 otherwise).
  * ------------------------------------------------------------------------------------------ */
 int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                   int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale,
+                   int64_t n, double lr, double beta1, double beta2, double eps, float grad_scale,
                    int64_t* step, void* stream);
 
 /* ------------------------------------------------------------------------------------------
