@@ -155,7 +155,7 @@ def main():
     lib = N.lib()
     prec = args.precision
     if prec == "auto":
-        prec = "tc" if (lib.b200_device_supports_tc() and os.environ.get("B200_TC_READY", "0") == "1") else "fp32"
+        prec = "tc" if lib.b200_device_supports_tc() else "fp32"
     precision = N.PREC_TC if prec == "tc" else N.PREC_FP32
 
     data = synth.throughput_set(H, W, T, seed=0)

@@ -78,7 +78,7 @@ def pe_frequencies(spec: MlpSpec) -> torch.Tensor:
 def positional_encoding(x: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """implicit_neural_networks.py:9-13.  Row layout: for each frequency k the block
     [sin(x_0 b_k) .. sin(x_{d-1} b_k), cos(x_0 b_k) .. cos(x_{d-1} b_k)]."""
-    proj = x[:, :, None] * b.to(x.dtype)[None, None, :]          # (rows, d, F); one fp mult each
+    proj = x[:, :, None] * b.to(x.dtype)[None, None, :]          # (rows, d, F); one fp mult each (b is fp32-valued)
     sc = torch.cat((torch.sin(proj), torch.cos(proj)), dim=1)     # (rows, 2d, F)
     return sc.transpose(2, 1).reshape(x.shape[0], -1)             # (rows, F*2d)
 
@@ -98,7 +98,9 @@ def init_mlp(spec: MlpSpec, generator: Optional[torch.Generator] = None) -> List
 
 
 def mlp_forward(spec: MlpSpec, params: Sequence[torch.Tensor], x: torch.Tensor) -> torch.Tensor:
-    """implicit_neural_networks.py:62-81."""
+    """implicit_neural_networks.py:62-81.  (Inputs are cast to the parameter dtype: a no-op for the
+    fp32 reference arithmetic, and what lets the tests build a float64 "truth" with float64 params.)"""
+    x = x.to(params[0].dtype)
     if spec.use_positional:
         x = positional_encoding(x, pe_frequencies(spec).to(x.device))
     skip_in = x.detach().clone()                                   # :69 — detached skip input

@@ -1,0 +1,138 @@
+"""tcgen05 path (B200_PREC_TC: 2-term fp16 split, 3 MMAs per product, fp32 accumulation in TMEM)
+against the oracle.  Needs a compute-capability-10 GPU.
+
+Tolerances
+  forward       |uv err| <= 2e-6, |atlas output err| <= 5e-5 (PE frequencies up to 2^9*pi amplify the
+                uv rounding), against the fp32 oracle
+  gradients     measured against a FLOAT64 evaluation of the oracle: the tensor-core path must be as
+                accurate as the fp32 CUDA-core path — err_tc <= max(4 * err_fp32path, 2e-5 * max|grad|)
+                per tensor (the sums over ~10^5 rows cancel heavily, so fp32-vs-fp32 comparisons
+                only measure summation order)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from b200 import _native as N
+from b200 import atlas as A
+from b200 import synth
+from oracle import atlas_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _need_tc():
+    if not N.lib().b200_device_supports_tc():
+        pytest.skip("no sm_100 device")
+
+
+def _params(golden_dir):
+    z = np.load(os.path.join(golden_dir, "params_seed1234.npz"))
+    return ([torch.from_numpy(z[f"map{i}"]) for i in range(12)], [torch.from_numpy(z[f"atl{i}"]) for i in range(16)])
+
+
+def _tc_outputs(tr, B):
+    cap = (B + 127) // 128 * 128
+    ws = tr._workspace()
+    r256 = lambda n: (n + 255) // 256 * 256
+    off = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr() + 256
+    off += r256(cap * 4)
+    off_x = off; off += r256(9 * cap * 16)
+    off += r256(cap * 48) + r256(9 * cap * 8) + r256(3 * cap * 12) + r256(3 * cap * 160)
+    x = ws[off_x:off_x + 9 * cap * 16].view(torch.float32).view(9 * cap, 4)
+    uv = ws[off:off + 9 * cap * 8].view(torch.float32).view(9 * cap, 2); off += r256(9 * cap * 8)
+    y = ws[off:off + 3 * cap * 12].view(torch.float32).view(3 * cap, 3)
+    return cap, x, uv, y
+
+
+@pytest.mark.parametrize("B,shape", [(64, (24, 40, 6)), (3000, (60, 100, 9))])
+def test_tc_forward_and_gradients(golden_dir, B, shape):
+    _need_tc()
+    H, W, T = shape
+    data = synth.throughput_set(H, W, T, seed=3)
+    inds = torch.randint(H * W * T, (B, 1), generator=torch.Generator().manual_seed(2))
+    mp, ap = _params(golden_dir)
+    vid = A.DeviceVideo.from_reference_layout(data, DEV)
+    grads = {}
+    for name, prec in (("fp32", N.PREC_FP32), ("tc", N.PREC_TC)):
+        tr = A.AtlasTrainer(vid, {"samples_batch": B}, precision=prec, device=DEV)
+        tr.load_state(O.state_dict_of(mp), O.state_dict_of(ap))
+        tr.indices.copy_(inds.reshape(-1))
+        tr.loss_grad(True)
+        torch.cuda.synchronize()
+        grads[name] = tr.grads.clone()
+        if prec == N.PREC_TC:
+            cap, x, uv, y = _tc_outputs(tr, B)
+            with torch.no_grad():
+                uv_ref = O.mlp_forward(O.MAPPING_SPEC, mp, x.cpu()[:, :3])
+                y_ref = O.mlp_forward(O.ATLAS_SPEC, ap, uv_ref[:3 * cap] * 0.5 + 0.5)
+            live = torch.zeros(9 * cap, dtype=torch.bool)
+            for g in range(9):
+                live[g * cap:g * cap + B] = True
+            assert (uv.cpu() - uv_ref)[live].abs().max() <= 2e-6
+            assert (y.cpu() - y_ref)[live[:3 * cap]].abs().max() <= 5e-5
+            losses_tc = tr.losses.cpu().numpy().copy()
+        else:
+            losses_32 = tr.losses.cpu().numpy().copy()
+    np.testing.assert_allclose(losses_tc[:6], losses_32[:6], rtol=2e-5)
+    # float64 truth
+    video64 = O.Video(**{k: v.double() if v.dtype == torch.float32 else v for k, v in data.items()})
+    mp64 = [p.double().requires_grad_(True) for p in mp]
+    ap64 = [p.double().requires_grad_(True) for p in ap]
+    terms = O.iteration_losses(video64, mp64, ap64, inds, 0)
+    terms["total"].backward()
+    np.testing.assert_allclose(losses_tc[0], float(terms["total"].detach()), rtol=1e-4)
+    probe = A.AtlasTrainer(vid, {"samples_batch": B}, precision=N.PREC_FP32, device=DEV)
+    truth = [p.grad.float() for p in mp64 + ap64]
+    i = 0
+    for which in ("mapping", "atlas"):
+        g32 = probe._views(grads["fp32"], which)
+        gtc = probe._views(grads["tc"], which)
+        for k in g32:
+            ref = truth[i].to(DEV); i += 1
+            e32 = (g32[k] - ref).abs().max().item()
+            etc = (gtc[k] - ref).abs().max().item()
+            assert etc <= max(4 * e32, 2e-5 * ref.abs().max().item()) + 1e-9, (which, k, etc, e32)
+
+
+def test_tc_trajectory_and_pretrain(golden_dir):
+    _need_tc()
+    H, W, T, B = 24, 40, 6, 64
+    data = synth.throughput_set(H, W, T, seed=3)
+    video = O.Video(**data)
+    mp, ap = _params(golden_dir)
+    vid = A.DeviceVideo.from_reference_layout(data, DEV)
+    tr = A.AtlasTrainer(vid, {"samples_batch": B}, precision=N.PREC_TC, device=DEV)
+    tr.load_state(O.state_dict_of(mp), O.state_dict_of(ap))
+    mp = [p.clone().requires_grad_(True) for p in mp]
+    ap = [p.clone().requires_grad_(True) for p in ap]
+    opt = O.make_optimizer(mp, ap)
+    gi = torch.Generator().manual_seed(21)
+    for it in (0, 1, 6000, 6001, 2):                      # both graph variants, interleaved
+        inds = torch.randint(H * W * T, (B, 1), generator=gi)
+        ref = O.train_iteration(video, mp, ap, opt, inds, it)
+        got = tr.step_host(inds, it, use_graph=True)
+        np.testing.assert_allclose(got[0], ref["total"], rtol=1e-3)
+    for which, ref_p in (("mapping", mp), ("atlas", ap)):
+        for (k, v), r in zip(tr.param_views(which).items(), ref_p):
+            assert (v.cpu() - r.detach()).abs().max() <= 1.5e-5, (which, k)
+    # pre-training on the tensor-core path
+    tr2 = A.AtlasTrainer(vid, {"samples_batch": 10000}, precision=N.PREC_TC, device=DEV)
+    mp0, ap0 = _params(golden_dir)
+    tr2.load_state(O.state_dict_of(mp0), O.state_dict_of(ap0))
+    mpp = [p.clone().requires_grad_(True) for p in mp0]
+    torch.manual_seed(5)
+    popt = torch.optim.Adam(mpp, lr=1e-4)
+    for f in range(2):
+        ys = torch.randint(20, (10000, 1)); xs = torch.randint(36, (10000, 1))
+        loss = O.pretrain_losses(mpp, f, ys, xs, 2, 36, 0.8)
+        popt.zero_grad(); loss.backward(); popt.step()
+    torch.manual_seed(5)
+    last = tr2.pretrain(2, 20, 36, 1)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(float(last[0]), float(loss.detach()), rtol=1e-4)
+    for (k, v), r in zip(tr2.param_views("mapping").items(), mpp):
+        assert (v.cpu() - r.detach()).abs().max() <= 1e-5, k
