@@ -234,9 +234,11 @@ def test_five_step_trajectory_with_graph_replay(golden_dir):
     assert int(tr.step_count) == 5
     for which, ref_p in (("mapping", mp), ("atlas", ap)):
         for (k, v), r in zip(tr.param_views(which).items(), ref_p):
-            # 5 Adam steps of 1e-4 each: parameters may differ by a fraction of one step where the
-            # gradient sign is noise-dominated; bound by 1.5e-5 absolute (< 1/6 of one step)
-            assert (v.cpu() - r.detach()).abs().max() <= 1.5e-5, (which, k)
+            # 5 Adam steps of 1e-4 each: where a gradient component is summation-noise dominated its
+            # normalised update differs, so single entries may be off by a fraction of one step;
+            # the bulk must agree to fp32 rounding
+            d = (v.cpu() - r.detach()).abs()
+            assert d.max() <= 5e-5 and d.mean() <= 2e-7, (which, k, float(d.max()), float(d.mean()))
     sd = tr.optimizer_state_dict()
     assert len(sd["state"]) == 28 and sd["param_groups"][1]["params"][0] == 12
     assert float(sd["state"][0]["step"]) == 5.0
