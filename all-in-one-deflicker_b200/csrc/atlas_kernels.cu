@@ -75,61 +75,76 @@ int launch_video_pack(const float* fr, const float* dx, const float* dy, const f
 // loss_utils.py:328-331 (counts only).
 // ---------------------------------------------------------------------------------------------
 constexpr int SELECT_THREADS = 1024;
+constexpr int SELECT_MAX_CHUNKS = 16;            // batch <= 16384 on the fast path
 
+// One block; sample b is handled by thread b % 1024 in pass b / 1024 (coalesced index loads, all loads of
+// a thread in flight together).  Positions come from ballots + a scan over (pass, warp) counts.
 __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const int64_t* __restrict__ indices, int B,
                                                                  B200Video vid, int* __restrict__ counters,
                                                                  int* __restrict__ list) {
-  __shared__ int warp_tot[3][32];
+  __shared__ int s_cnt[SELECT_MAX_CHUNKS * 32];
+  __shared__ int s_tot[3];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int per = (B + SELECT_THREADS - 1) / SELECT_THREADS;
-  const int b0 = tid * per, b1 = min(B, b0 + per);
+  const int chunks = (B + SELECT_THREADS - 1) / SELECT_THREADS;
   const int64_t HW = (int64_t)vid.H * vid.W;
-  int c_loc = 0, c_f = 0, c_b = 0;
-  for (int b = b0; b < b1; ++b) {
-    const int64_t n = indices[b];
-    const int t = (int)(n / HW);
-    c_loc += (t >= vid.t_begin && t < vid.t_end);
-    c_f += (vid.mask_fwd_bits[n >> 5] >> (n & 31)) & 1u;
-    c_b += (vid.mask_bwd_bits[n >> 5] >> (n & 31)) & 1u;
-  }
-  // block-wide exclusive scan of c_loc, totals of the other two
-  int incl = c_loc, sf = c_f, sb = c_b;
+  if (tid < 3) s_tot[tid] = 0;
+  int64_t n[SELECT_MAX_CHUNKS];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
+  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
+    const int b = k * SELECT_THREADS + tid;
+    n[k] = (k < chunks && b < B) ? indices[b] : -1;
+  }
+  uint32_t wf[SELECT_MAX_CHUNKS], wb[SELECT_MAX_CHUNKS];
+#pragma unroll
+  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
+    wf[k] = wb[k] = 0;
+    if (n[k] >= 0) { wf[k] = vid.mask_fwd_bits[n[k] >> 5]; wb[k] = vid.mask_bwd_bits[n[k] >> 5]; }
+  }
+  uint32_t loc_ballot[SELECT_MAX_CHUNKS];
+  int c_f = 0, c_b = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
+    bool loc = false;
+    if (n[k] >= 0) {
+      const int t = (int)(n[k] / HW);
+      loc = (t >= vid.t_begin && t < vid.t_end);
+      c_f += (wf[k] >> (n[k] & 31)) & 1u;
+      c_b += (wb[k] >> (n[k] & 31)) & 1u;
+    }
+    loc_ballot[k] = __ballot_sync(0xffffffffu, loc);
+    if (lane == 0) s_cnt[k * 32 + wid] = __popc(loc_ballot[k]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    sf += __shfl_xor_sync(0xffffffffu, sf, o);
-    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    c_f += __shfl_xor_sync(0xffffffffu, c_f, o);
+    c_b += __shfl_xor_sync(0xffffffffu, c_b, o);
   }
-  if (lane == 31) warp_tot[0][wid] = incl;
-  if (lane == 0) { warp_tot[1][wid] = sf; warp_tot[2][wid] = sb; }
+  if (lane == 0) { atomicAdd(&s_tot[1], c_f); atomicAdd(&s_tot[2], c_b); }
   __syncthreads();
   if (wid == 0) {
-    int w = warp_tot[0][lane], wi = w;
+    // exclusive scan of the 16 x 32 counts in (pass, warp) order: lane handles 16 consecutive entries
+    int local[16], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { local[i] = s_cnt[lane * 16 + i]; sum += local[i]; }
+    int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += v;
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-    warp_tot[0][lane] = wi - w;                   // exclusive prefix of the warp totals
-    int tf = warp_tot[1][lane], tb = warp_tot[2][lane];
+    int run = incl - sum;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      tf += __shfl_xor_sync(0xffffffffu, tf, o);
-      tb += __shfl_xor_sync(0xffffffffu, tb, o);
-    }
-    if (lane == 31) counters[0] = wi;
-    if (lane == 0) { counters[1] = tf; counters[2] = tb; counters[3] = 0; }
+    for (int i = 0; i < 16; ++i) { s_cnt[lane * 16 + i] = run; run += local[i]; }
+    if (lane == 31) s_tot[0] = incl;
   }
   __syncthreads();
-  int pos = warp_tot[0][wid] + incl - c_loc;
-  for (int b = b0; b < b1; ++b) {
-    const int t = (int)(indices[b] / HW);
-    if (t >= vid.t_begin && t < vid.t_end) list[pos++] = b;
+#pragma unroll
+  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
+    if ((loc_ballot[k] >> lane) & 1u)
+      list[s_cnt[k * 32 + wid] + __popc(loc_ballot[k] & ((1u << lane) - 1u))] = k * SELECT_THREADS + tid;
   }
+  if (tid == 0) { counters[0] = s_tot[0]; counters[1] = s_tot[1]; counters[2] = s_tot[2]; counters[3] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------

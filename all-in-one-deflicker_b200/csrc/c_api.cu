@@ -104,7 +104,7 @@ struct AtlasPlan {
 };
 
 static int plan_atlas(const B200AtlasConfig* cfg, char* base, AtlasPlan* pl) {
-  B200_REQUIRE(cfg && cfg->batch > 0 && cfg->batch <= (1 << 22), "invalid batch");
+  B200_REQUIRE(cfg && cfg->batch > 0 && cfg->batch <= 16384, "samples_batch must be in [1, 16384]");
   B200_PROPAGATE(resolve_mlp(&mapping_desc(), &pl->ms));
   B200_PROPAGATE(resolve_mlp(&atlas_desc(), &pl->as));
   pl->cap = (int)round_up(cfg->batch, kTileRows);

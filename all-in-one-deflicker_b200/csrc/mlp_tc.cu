@@ -12,14 +12,15 @@
 //                    layout a UMMA descriptor reads), W for the forward and W^T for the dgrad
 //   tc_fwd_kernel    persistent; one 128-row tile walks through ALL layers on chip: activations live
 //                    in TMEM (A operand, TS-mode MMA), weights stream L2->smem through the TMA engine
-//                    (cp.async.bulk + mbarrier ring), epilogue = bias + ReLU + split + TMEM store;
-//                    first/last (K=3 / N=2,3) layers and the positional encoding run on CUDA cores
-//                    inside the same kernel
-//   tc_bwd_kernel    same structure for dL/dz: tanh', last layer and its weight gradient on CUDA
-//                    cores, hidden layers as dZ * W (B = W^T images), ReLU mask from 1-bit flags,
-//                    bias gradients by an in-register butterfly column sum
+//                    (cp.async.bulk + mbarrier ring), epilogue (8 warps) = bias + ReLU + split ->
+//                    TMEM store (next layer's A) and, via a swizzled smem staging tile + bulk store,
+//                    the activation image the weight-gradient kernel consumes; first/last (K=3 / N=2,3)
+//                    layers and the positional encoding run on CUDA cores inside the same kernel
+//   tc_bwd_kernel    same structure for dL/dz: tanh', last layer on CUDA cores, hidden layers as
+//                    dZ * W (B = W^T images), ReLU mask from 1-bit flags, bias gradients by an
+//                    in-register butterfly column sum
 //   tc_wgrad_kernel  dW = dZ^T * H as UMMA with both operands MN-major straight from the images
-//                    the two kernels above left in HBM; split over rows, fp32 reductions (red.v4)
+//                    the two kernels above left in HBM; split over rows, fp32 vector reductions
 //
 // Restates nn.Linear/ReLU/tanh/skip-concat forward+autograd of
 //   src/models/stage_1/implicit_neural_networks.py:62-81 for the two networks of
@@ -34,25 +35,22 @@ using namespace ptx;
 constexpr int TM = 128;                 // rows per tile (UMMA M)
 constexpr int HID = 256;
 constexpr int STAGE_BYTES = 32768;      // one weight image: 256 rows x 64 k (fp16), 128B swizzle
-constexpr int NSTAGE = 5;
 constexpr float S_ACT = 16.0f;          // activation scale before the fp16 split
 constexpr float S_W = 256.0f;           // weight scale
-constexpr int TILE_IMG_BYTES = TM * HID * 2;     // one term of one activation tile image: 64 KB
-constexpr int PE_IMG_BYTES = TM * 64 * 2;        // one term of one 64-wide tile image: 16 KB
+constexpr int ATOM_BYTES = TM * 128;    // one 64-column block of a tile image, one term: 16 KB
+constexpr int TILE_IMG_BYTES = 4 * ATOM_BYTES;   // one term of one [128 x 256] activation tile image: 64 KB
 constexpr int PE_COLS = 40;
 
-constexpr int TC_THREADS = 192;         // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + EPI_THREADS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_D = 0, TM_AHI = 256, TM_ALO = 384;
 
-// byte offset of element (row m, column n) inside one term of a [128 x 256] tile image:
-// [16 groups of 8 rows][4 atoms of 64 columns][8 rows x 128 B, 16-byte chunks XOR row]
-__host__ __device__ __forceinline__ int img_off(int m, int n) {
-  const int r = m & 7;
-  return (m >> 3) * 4096 + (n >> 6) * 1024 + r * 128 + ((((n & 63) >> 3) ^ r) << 4) + ((n & 7) << 1);
-}
-// same for a [rows x 64] image (one atom per group): also the K-major SW128 layout of a weight image
-__host__ __device__ __forceinline__ int img64_off(int m, int k) {
+// Tile image = 4 atom blocks (64 columns each); an atom block is [16 groups of 8 rows][8 rows x 128 B]
+// with the 16-byte chunks of a row XOR-swizzled by (row & 7).  The same bytes are a K-major SW128 UMMA
+// operand (M/N = rows, K = the 64 columns) and an MN-major SW128 operand (MN = columns, K = rows).
+__host__ __device__ __forceinline__ int atom_off(int m, int k) {          // k in [0, 64)
   const int r = m & 7;
   return (m >> 3) * 1024 + r * 128 + (((k >> 3) ^ r) << 4) + ((k & 7) << 1);
 }
@@ -65,19 +63,16 @@ struct NetImages {
   char* w_fwd; int64_t w_fwd_layer[B200_MAX_LAYERS]; int n_chunks_fwd[B200_MAX_LAYERS];
   // dgrad weight images (W^T): per layer, per 64-wide chunk of the reduction (out) index: hi, lo
   char* w_bwd; int64_t w_bwd_layer[B200_MAX_LAYERS];
-  // activation images h_0..h_{L-2}: [slot][term][tile][64 KB]; dZ images for layers 1..L-2 (mapping),
-  // 0..L-2 (atlas): same shape
+  // activation images h_0..h_{L-2} and dZ images: [slot][term][tile][4 atoms][16 KB]
   char* act; char* dz;
   int64_t slot_stride, term_stride;       // bytes
-  char* pe; int64_t pe_term_stride;       // atlas: [term][tile][16 KB]
-  uint32_t* bits;                         // [slot][rows][8]
+  // 64-wide images: [term][tile][16 KB]: positional encoding (atlas) and the output-layer dZ
+  char* pe; char* dzl; int64_t w64_term_stride;
+  uint32_t* bits;                         // ReLU flags [slot][rows][8]
   int64_t rows;
 };
 
-struct TcLayout {
-  NetImages map, atl;
-  int64_t bytes;
-};
+struct TcLayout { NetImages map, atl; };
 
 static char* carve_tc(char*& p, int64_t bytes) { char* r = p; p += round_up(bytes, 1024); return r; }
 
@@ -97,16 +92,17 @@ static void plan_net(const MlpShape& s, int64_t rows, bool is_atlas, char*& p, N
   off = 0;
   for (int l = 0; l < s.L; ++l) {
     n->w_bwd_layer[l] = off;
-    const bool dgrad_layer = is_atlas ? (l <= s.L - 2) : (l >= 2 && l <= s.L - 2);
-    if (dgrad_layer || (!is_atlas && l == 1)) off += (int64_t)(HID / 64) * 2 * STAGE_BYTES;
+    const bool used = l <= s.L - 2 && (is_atlas || l >= 1);
+    if (used) off += (int64_t)(HID / 64) * 2 * STAGE_BYTES;
   }
   n->w_bwd = carve_tc(p, off);
   n->term_stride = tiles * TILE_IMG_BYTES;
   n->slot_stride = 2 * n->term_stride;
   n->act = carve_tc(p, (int64_t)(s.L - 1) * n->slot_stride);
   n->dz = carve_tc(p, (int64_t)(s.L - 1) * n->slot_stride);
-  n->pe = nullptr; n->pe_term_stride = 0;
-  if (is_atlas) { n->pe_term_stride = tiles * PE_IMG_BYTES; n->pe = carve_tc(p, 2 * n->pe_term_stride); }
+  n->w64_term_stride = tiles * ATOM_BYTES;
+  n->pe = is_atlas ? carve_tc(p, 2 * n->w64_term_stride) : nullptr;
+  n->dzl = carve_tc(p, 2 * n->w64_term_stride);
   n->bits = reinterpret_cast<uint32_t*>(carve_tc(p, (int64_t)(s.L - 1) * rows * 32));
 }
 
@@ -116,9 +112,7 @@ int64_t tc_plan(const MlpShape& ms, const MlpShape& as, int64_t rows_map, int64_
   TcLayout lay{};
   plan_net(ms, rows_map, false, p, &lay.map);
   plan_net(as, rows_atlas, true, p, &lay.atl);
-  if (out) {
-    out->base = base; out->bytes = p - base; out->rows_map = rows_map; out->rows_atlas = rows_atlas;
-  }
+  if (out) { out->base = base; out->bytes = p - base; out->rows_map = rows_map; out->rows_atlas = rows_atlas; }
   return p - base;
 }
 
@@ -135,7 +129,7 @@ static TcLayout layout_of(const TcStep& s) {
 // ---------------------------------------------------------------------------------------------
 struct PrepJob {
   const float* W; int ldw;          // fp32 weight [N][ldw]
-  int n_rows, k0, k_cnt;            // image rows (N index range 0..n_rows) and the K window [k0, k0+k_cnt)
+  int n_rows, k0, k_cnt;            // valid image rows and the window [k0, k0+k_cnt) of the other index
   int transpose;                    // 0: image(row=n, col=k-k0) = W[n][k];  1: image(row=k, col=n-k0) = W[n][k]
   char* hi; char* lo;               // destination images (32 KB each, zero padded)
 };
@@ -143,37 +137,36 @@ constexpr int MAX_PREP_JOBS = 96;
 struct PrepJobs { PrepJob j[MAX_PREP_JOBS]; int n; };
 
 __global__ void tc_prep_kernel(const PrepJobs* __restrict__ jobs_ptr) {
-  const PrepJob jb = jobs_ptr->j[blockIdx.x];
-  // one image = 256 rows x 64 cols; thread handles 8 consecutive columns (one 16-byte chunk)
-  for (int e = threadIdx.x; e < 256 * 8; e += blockDim.x) {
-    const int row = e >> 3, c8 = (e & 7) * 8;
-    __half h[8], l[8];
+  const PrepJob jb = jobs_ptr->j[blockIdx.x >> 2];
+  // one image = 256 rows x 64 cols; this block does 64 rows; thread handles one 16-byte chunk at a time
+  for (int e = threadIdx.x; e < 64 * 8; e += blockDim.x) {
+    const int row = (blockIdx.x & 3) * 64 + (e >> 3), c8 = (e & 7) * 8;
+    float v[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int col = c8 + q;
-      float v = 0.f;
-      if (!jb.transpose) {
-        if (row < jb.n_rows && col < jb.k_cnt) v = jb.W[(int64_t)row * jb.ldw + jb.k0 + col];
-      } else {
-        // row = k index of W (output column of the dgrad), col = n - k0
-        if (row < jb.n_rows && col < jb.k_cnt) v = jb.W[(int64_t)(jb.k0 + col) * jb.ldw + row];
-      }
-      split_f16(v * S_W, h[q], l[q]);
+      v[q] = 0.f;
+      if (row < jb.n_rows && col < jb.k_cnt)
+        v[q] = jb.transpose ? jb.W[(int64_t)(jb.k0 + col) * jb.ldw + row] : jb.W[(int64_t)row * jb.ldw + jb.k0 + col];
     }
-    const int off = img64_off(row, c8);
-    *reinterpret_cast<uint4*>(jb.hi + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-    *reinterpret_cast<uint4*>(jb.lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split2_f16(v[2 * q] * S_W, v[2 * q + 1] * S_W, h[q], l[q]);
+    const int off = atom_off(row, c8);
+    *reinterpret_cast<uint4*>(jb.hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(jb.lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // shared pieces of the fused kernels
 // ---------------------------------------------------------------------------------------------
+template <int NST>
 struct Pipe {                        // weight-image ring shared by producer and MMA warp
   uint64_t* full; uint64_t* empty; char* stage;
-  uint32_t it;                       // running item counter (stage = it % NSTAGE, parity from it / NSTAGE)
-  __device__ __forceinline__ int slot() const { return it % NSTAGE; }
-  __device__ __forceinline__ uint32_t parity() const { return (it / NSTAGE) & 1; }
+  uint32_t it;                       // running item counter
+  __device__ __forceinline__ int slot() const { return it % NST; }
+  __device__ __forceinline__ uint32_t parity() const { return (it / NST) & 1; }
 };
 
 struct TileIter {                    // static round-robin over the live tiles of a group-major batch
@@ -186,47 +179,10 @@ struct TileIter {                    // static round-robin over the live tiles o
   __device__ __forceinline__ int global_tile(int t) const { return (t / ntg) * cap_tiles + (t % ntg); }
 };
 
-struct FwdParams {
-  const float* x;            // mapping: [rows][4] (x, y, t, 0);  atlas: uv [rows][2]
-  float* y;                  // mapping: uv [rows][2];  atlas: y [rows][3]
-  const float* params;       // fp32 parameters of this network
-  int64_t w_off[B200_MAX_LAYERS], b_off[B200_MAX_LAYERS];
-  NetImages img;
-  int cap, n_groups; const int* n_valid;
-};
-
-// One 32-column chunk of a layer output (already activated, fp32): split, pack, optionally store
-// as the next layer's A operand in TMEM and into the tile image in HBM.
-__device__ __forceinline__ void emit_chunk(const float (&v)[32], float scale, int c, int m, uint32_t tmem_lane,
-                                           bool to_tmem, char* img_hi, char* img_lo) {
-  uint32_t ph[16], pl[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    __half h0, l0, h1, l1;
-    split_f16(v[2 * i] * scale, h0, l0);
-    split_f16(v[2 * i + 1] * scale, h1, l1);
-    ph[i] = pack2(h0, h1);
-    pl[i] = pack2(l0, l1);
-  }
-  if (to_tmem) {
-    tmem_st16(tmem_lane + TM_AHI + c * 16, ph);
-    tmem_st16(tmem_lane + TM_ALO + c * 16, pl);
-  }
-  if (img_hi) {
-    const int r = m & 7;
-    const int base = (m >> 3) * 4096 + (c >> 1) * 1024 + r * 128;
-#pragma unroll
-    for (int i8 = 0; i8 < 4; ++i8) {
-      const int off = base + ((((c & 1) * 4 + i8) ^ r) << 4);
-      *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(ph[4 * i8], ph[4 * i8 + 1], ph[4 * i8 + 2], ph[4 * i8 + 3]);
-      *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(pl[4 * i8], pl[4 * i8 + 1], pl[4 * i8 + 2], pl[4 * i8 + 3]);
-    }
-  }
-}
-
 // MMAs of one 64-wide k chunk whose A operand is in TMEM (hi at TM_AHI, lo at TM_ALO):
 //   D += A_hi*B_hi + A_lo*B_hi   (B_hi image)    then   D += A_hi*B_lo   (B_lo image)
-__device__ __forceinline__ void mma_chunk_ts(Pipe& pp, uint32_t tmem, int kchunk, uint32_t idesc, bool& first) {
+template <int NST>
+__device__ __forceinline__ void mma_chunk_ts(Pipe<NST>& pp, uint32_t tmem, int kchunk, uint32_t idesc, bool& first) {
   {
     mbar_wait(&pp.full[pp.slot()], pp.parity());
     tc_fence_after();
@@ -246,16 +202,15 @@ __device__ __forceinline__ void mma_chunk_ts(Pipe& pp, uint32_t tmem, int kchunk
     tc_fence_after();
     const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t bd = make_desc(sb + ks * 32, 16, 1024);
-      mma_ts(tmem + TM_D, tmem + TM_AHI + kchunk * 32 + ks * 8, bd, idesc, 1u);
-    }
+    for (int ks = 0; ks < 4; ++ks)
+      mma_ts(tmem + TM_D, tmem + TM_AHI + kchunk * 32 + ks * 8, make_desc(sb + ks * 32, 16, 1024), idesc, 1u);
     mma_commit(&pp.empty[pp.slot()]);
     ++pp.it;
   }
 }
 // same with the A operand in shared memory (64-wide K-major SW128 tile: hi image, lo image)
-__device__ __forceinline__ void mma_chunk_ss(Pipe& pp, uint32_t tmem, const char* a_hi, const char* a_lo,
+template <int NST>
+__device__ __forceinline__ void mma_chunk_ss(Pipe<NST>& pp, uint32_t tmem, const char* a_hi, const char* a_lo,
                                              uint32_t idesc, bool& first) {
   const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
   {
@@ -284,7 +239,8 @@ __device__ __forceinline__ void mma_chunk_ss(Pipe& pp, uint32_t tmem, const char
   }
 }
 
-__device__ __forceinline__ void produce_items(Pipe& pp, const char* src, int n_items) {
+template <int NST>
+__device__ __forceinline__ void produce_items(Pipe<NST>& pp, const char* src, int n_items) {
   for (int i = 0; i < n_items; ++i) {
     mbar_wait(&pp.empty[pp.slot()], pp.parity() ^ 1);
     mbar_expect_tx(&pp.full[pp.slot()], STAGE_BYTES);
@@ -293,37 +249,44 @@ __device__ __forceinline__ void produce_items(Pipe& pp, const char* src, int n_i
   }
 }
 
-// dynamic shared memory map (all kernels): [stages][aux tile 32 KB][const floats][barriers]
-constexpr int SMEM_STAGES = NSTAGE * STAGE_BYTES;            // 160 KB
-constexpr int SMEM_AUX = 2 * PE_IMG_BYTES;                   // 32 KB: 64-wide tile (hi, lo)
-constexpr int SMEM_CONST_FLOATS = 3072;                      // 12 KB
+// dynamic shared memory map: [weight stages][staging 2 x (hi 16K | lo 16K)][aux tile 32 KB (atlas)][consts][barriers]
+constexpr int SMEM_STAGING = 2 * 2 * ATOM_BYTES;             // 64 KB
+constexpr int SMEM_AUX = 2 * ATOM_BYTES;                     // 32 KB
+constexpr int SMEM_CONST_FLOATS = 3584;                      // 14 KB
 constexpr int SMEM_BARS = 256;
-constexpr int TC_SMEM_BYTES = SMEM_STAGES + SMEM_AUX + SMEM_CONST_FLOATS * 4 + SMEM_BARS + 1024;
+template <bool ATLAS> struct KCfg {
+  static constexpr int NST = ATLAS ? 3 : 4;
+  static constexpr int SMEM = NST * STAGE_BYTES + SMEM_STAGING + (ATLAS ? SMEM_AUX : 0) + SMEM_CONST_FLOATS * 4 +
+                              SMEM_BARS + 1024;
+};
 
+template <int NST, bool ATLAS>
 struct SmemMap {
-  char* stage; char* aux; float* cst; uint64_t* full; uint64_t* empty; uint64_t* a_ready; uint64_t* d_ready;
-  uint64_t* misc; uint32_t* tmem_slot;
+  char* stage; char* staging; char* aux; float* cst;
+  uint64_t* full; uint64_t* empty; uint64_t* a_ready; uint64_t* d_ready; uint64_t* misc; uint32_t* tmem_slot;
   __device__ __forceinline__ void init(char* raw) {
     char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-    stage = p; p += SMEM_STAGES;
-    aux = p; p += SMEM_AUX;
+    stage = p; p += NST * STAGE_BYTES;
+    staging = p; p += SMEM_STAGING;
+    aux = p; if (ATLAS) p += SMEM_AUX;
     cst = reinterpret_cast<float*>(p); p += SMEM_CONST_FLOATS * 4;
     full = reinterpret_cast<uint64_t*>(p);
-    empty = full + NSTAGE;
-    a_ready = empty + NSTAGE;
+    empty = full + NST;
+    a_ready = empty + NST;
     d_ready = a_ready + 1;
     misc = d_ready + 1;
     tmem_slot = reinterpret_cast<uint32_t*>(misc + 2);
   }
 };
 
-__device__ __forceinline__ uint32_t setup_cta(SmemMap& sm, int warp) {
+template <int NST, bool ATLAS>
+__device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-    mbar_init(sm.a_ready, TM);
+    for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    mbar_init(sm.a_ready, EPI_THREADS);
     mbar_init(sm.d_ready, 1);
     mbar_init(&sm.misc[0], 1);
-    mbar_init(&sm.misc[1], TM);
+    mbar_init(&sm.misc[1], EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(sm.tmem_slot, TMEM_COLS);
@@ -333,28 +296,83 @@ __device__ __forceinline__ uint32_t setup_cta(SmemMap& sm, int warp) {
   return *sm.tmem_slot;
 }
 
+// Epilogue thread geometry: 8 warps; warp e handles TMEM lanes of quadrant (warp_id & 3) and the column
+// half hh = e / 4 (128 columns = 2 atom blocks = 4 chunks of 32 columns).
+struct EpiThread {
+  int e, q, hh, lane, m, tid;       // epilogue warp, TMEM quadrant, column half, lane, tile row, 0..255
+  uint32_t tlane;
+  __device__ __forceinline__ void init(uint32_t tmem) {
+    const int warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    e = warp - 2; q = warp & 3; hh = e >> 2;
+    m = q * 32 + lane;
+    tid = threadIdx.x - 64;
+    tlane = tmem + ((uint32_t)(q * 32) << 16);
+  }
+};
+
+// Pushes one finished 64-column atom block (held as packed hi/lo words of this thread's row) to the HBM
+// image through the staging buffer of this column half.  Called by all 128 threads of the half.
+//   ph/pl: 32 packed words each (64 columns).   bar_id: named barrier of this half.
+__device__ __forceinline__ void stage_and_store(const EpiThread& t, char* staging, const uint32_t (&ph)[32],
+                                                const uint32_t (&pl)[32], char* g_hi, char* g_lo, bool issuer,
+                                                int bar_id) {
+  char* sh = staging + t.hh * (2 * ATOM_BYTES);
+  char* sl = sh + ATOM_BYTES;
+  if (issuer) bulk_wait_read0();                       // previous block of this half has left the buffer
+  named_bar(bar_id, 128);
+  const int r = t.m & 7;
+  const int base = (t.m >> 3) * 1024 + r * 128;
+#pragma unroll
+  for (int c16 = 0; c16 < 8; ++c16) {
+    const int off = base + ((c16 ^ r) << 4);
+    *reinterpret_cast<uint4*>(sh + off) = make_uint4(ph[4 * c16], ph[4 * c16 + 1], ph[4 * c16 + 2], ph[4 * c16 + 3]);
+    *reinterpret_cast<uint4*>(sl + off) = make_uint4(pl[4 * c16], pl[4 * c16 + 1], pl[4 * c16 + 2], pl[4 * c16 + 3]);
+  }
+  fence_proxy_async_smem();
+  named_bar(bar_id, 128);
+  if (issuer) {
+    bulk_s2g(g_hi, sh, ATOM_BYTES);
+    bulk_s2g(g_lo, sl, ATOM_BYTES);
+    bulk_commit();
+  }
+}
+
+struct FwdParams {
+  const float* x;            // mapping: [rows][4] (x, y, t, 0);  atlas: uv [rows][2]
+  float* y;                  // mapping: uv [rows][2];  atlas: y [rows][3]
+  const float* params;       // fp32 parameters of this network
+  int64_t w_off[B200_MAX_LAYERS], b_off[B200_MAX_LAYERS];
+  NetImages img;
+  int cap, n_groups; const int* n_valid;
+};
+
 // =============================================================================================
 // forward
 // =============================================================================================
 template <bool ATLAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ char smem_raw[];
-  SmemMap sm; sm.init(smem_raw);
+  constexpr int NST = KCfg<ATLAS>::NST;
+  SmemMap<NST, ATLAS> sm; sm.init(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int L = ATLAS ? 8 : 6;
   constexpr int FIRST_TC = ATLAS ? 0 : 1;
   constexpr int LAST_TC = L - 2;
   constexpr int OUT = ATLAS ? 3 : 2;
   constexpr int KLAST = ATLAS ? 296 : 256;
-  // constants in shared memory: biases of layers 0..L-2 at [l*256], last-layer weights + bias, (mapping) W0
+  // constants in shared memory: biases of layers 0..L-2 (pre-multiplied by S_ACT) at [l*256], last-layer
+  // weights (pre-divided by S_ACT) + bias, (mapping) W0, and a small exchange area for the output layer
   float* s_bias = sm.cst;
   float* s_wlast = sm.cst + (L - 1) * 256;
   float* s_blast = s_wlast + OUT * KLAST;
-  float* s_w0 = s_blast + 4;
-  for (int i = threadIdx.x; i < (L - 1) * 256; i += blockDim.x) s_bias[i] = P.params[P.b_off[i >> 8] + (i & 255)];
-  for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i];
+  float* s_w0 = s_blast + 4;                              // mapping only: 768 floats
+  float* s_xch = sm.cst + SMEM_CONST_FLOATS - TM * 4;     // [128][4] partial outputs of column half 1
+  for (int i = threadIdx.x; i < (L - 1) * 256; i += blockDim.x)
+    s_bias[i] = P.params[P.b_off[i >> 8] + (i & 255)] * S_ACT;
+  for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i] * (1.0f / S_ACT);
   if (threadIdx.x < OUT) s_blast[threadIdx.x] = P.params[P.b_off[L - 1] + threadIdx.x];
-  if (!ATLAS) for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[i] = P.params[P.w_off[0] + i];
+  if (!ATLAS) for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[i] = P.params[P.w_off[0] + i] * S_ACT;
   const uint32_t tmem = setup_cta(sm, warp);
   TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid);
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
@@ -362,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x)
         for (int l = FIRST_TC; l <= LAST_TC; ++l)
           produce_items(pp, P.img.w_fwd + P.img.w_fwd_layer[l], P.img.n_chunks_fwd[l] * 2);
@@ -370,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
       uint32_t a_par = 0;
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
         for (int l = FIRST_TC; l <= LAST_TC; ++l) {
@@ -378,49 +396,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           tc_fence_after();
           bool first = true;
           if (l > 0) for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC, first);
-          if (ATLAS && (l == 0 || l == 4 || l == 7)) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + PE_IMG_BYTES, IDESC, first);
+          if (ATLAS && (l == 0 || l == 4)) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + ATOM_BYTES, IDESC, first);
           mma_commit(sm.d_ready);
         }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (128 threads)
-    const int q = warp & 3;
-    const int m = q * 32 + lane;                       // row inside the tile == TMEM lane
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    // ------------------------------------------------------------------ epilogue warps (256 threads)
+    EpiThread et; et.init(tmem);
+    const int m = et.m, hh = et.hh;
+    const bool issuer = (et.q == 0 && lane == 0);       // one bulk-store issuer per column half
+    const int bar_id = 1 + hh;
     uint32_t d_par = 0;
-    const float inv_scale = 1.0f / (S_ACT * S_W);
+    const float inv_scale = 1.0f / S_W;                 // D / (S_a S_w) * S_a : activations stay scaled by S_ACT
     for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
       const int gt = ti.global_tile(t);
       const int64_t row = (int64_t)gt * TM + m;
       // ---------------- prologue: layer-0 input
-      float pe_cache = 0.f; (void)pe_cache;
       if (ATLAS) {
         // positional encoding of in = uv*0.5+0.5 (implicit_neural_networks.py:9-13) into the aux tile
+        // (K-major SW128, columns k*4 + {sin x0, sin x1, cos x0, cos x1}); half 0 does k = 0..5, half 1 the rest
         const float2 uv = *reinterpret_cast<const float2*>(P.x + row * 2);
         const float in[2] = {uv.x * 0.5f + 0.5f, uv.y * 0.5f + 0.5f};
-        char* a_hi = sm.aux + 0;
-        char* a_lo = sm.aux + PE_IMG_BYTES;
-        char* g_hi = P.img.pe + (int64_t)gt * PE_IMG_BYTES;
-        char* g_lo = g_hi + P.img.pe_term_stride;
-#pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {               // 8 chunks of 8 columns; column = k*4 + {s0,s1,c0,c1}
-          __half h[8], lo[8];
+        char* a_hi = sm.aux;
+        char* a_lo = sm.aux + ATOM_BYTES;
+        char* g_hi = P.img.pe + (int64_t)gt * ATOM_BYTES;
+        char* g_lo = g_hi + P.img.w64_term_stride;
+        const int c_begin = hh ? 3 : 0, c_end = hh ? 8 : 3;
+        for (int c8 = c_begin; c8 < c_end; ++c8) {     // chunks of 8 columns = 2 frequencies
+          float vals[8];
 #pragma unroll
           for (int half_k = 0; half_k < 2; ++half_k) {
             const int k = c8 * 2 + half_k;
-            float vals[4] = {0.f, 0.f, 0.f, 0.f};
+            float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
             if (k < 10) {
               const float bk = pe_freq(k);
               const float a0 = in[0] * bk, a1 = in[1] * bk;
-              vals[0] = sinf(a0); vals[1] = sinf(a1); vals[2] = cosf(a0); vals[3] = cosf(a1);
+              s0 = sinf(a0); s1 = sinf(a1); c0 = cosf(a0); c1 = cosf(a1);
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split_f16(vals[e] * S_ACT, h[half_k * 4 + e], lo[half_k * 4 + e]);
+            vals[half_k * 4 + 0] = s0 * S_ACT; vals[half_k * 4 + 1] = s1 * S_ACT;
+            vals[half_k * 4 + 2] = c0 * S_ACT; vals[half_k * 4 + 3] = c1 * S_ACT;
           }
-          const int off = img64_off(m, c8 * 8);
-          const uint4 vh = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-          const uint4 vl = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+          uint32_t h[4], lo[4];
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) split2_f16(vals[2 * q2], vals[2 * q2 + 1], h[q2], lo[q2]);
+          const int off = atom_off(m, c8 * 8);
+          const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(a_hi + off) = vh;
           *reinterpret_cast<uint4*>(a_lo + off) = vl;
           *reinterpret_cast<uint4*>(g_hi + off) = vh;
@@ -430,31 +451,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         tc_fence_before();
         mbar_arrive(sm.a_ready);
       } else {
-        // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0)
+        // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0), this thread's 128 columns
         const float4 xv = *reinterpret_cast<const float4*>(P.x + row * 4);
-        char* ih = P.img.act + 0 * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
-        char* il = ih + P.img.term_stride;
-        uint32_t bits[8];
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float v[32];
-          uint32_t bw = 0;
+        char* img = P.img.act + (int64_t)gt * TILE_IMG_BYTES;
+        uint32_t bits[4];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int n = c * 32 + i;
-            float z = s_bias[n];
-            z = fmaf(xv.x, s_w0[n * 3 + 0], z);
-            z = fmaf(xv.y, s_w0[n * 3 + 1], z);
-            z = fmaf(xv.z, s_w0[n * 3 + 2], z);
-            bw |= (z > 0.f ? 1u : 0u) << i;
-            v[i] = fmaxf(z, 0.f);
+        for (int ab = 0; ab < 2; ++ab) {               // two atom blocks of this half
+          uint32_t ph[32], pl[32];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = ab * 2 + cc;                 // chunk inside the half
+            uint32_t bw = 0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float z[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int n = hh * 128 + c * 32 + i + u;
+                float a = s_bias[n];
+                a = fmaf(xv.x, s_w0[n * 3 + 0], a);
+                a = fmaf(xv.y, s_w0[n * 3 + 1], a);
+                a = fmaf(xv.z, s_w0[n * 3 + 2], a);
+                bw |= (a > 0.f ? 1u : 0u) << (i + u);
+                z[u] = fmaxf(a, 0.f);
+              }
+              split2_f16(z[0], z[1], ph[cc * 16 + i / 2], pl[cc * 16 + i / 2]);
+            }
+            bits[c] = bw;
+            uint32_t th[16], tl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { th[i] = ph[cc * 16 + i]; tl[i] = pl[cc * 16 + i]; }
+            tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
+            tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
           }
-          bits[c] = bw;
-          emit_chunk(v, S_ACT, c, m, tlane, true, ih, il);
+          char* g = img + (hh * 2 + ab) * ATOM_BYTES;
+          stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
         }
-        uint4* bdst = reinterpret_cast<uint4*>(P.img.bits + ((int64_t)0 * P.img.rows + row) * 8);
-        bdst[0] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
-        bdst[1] = make_uint4(bits[4], bits[5], bits[6], bits[7]);
+        *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)0 * P.img.rows + row) * 8 + hh * 4) =
+            make_uint4(bits[0], bits[1], bits[2], bits[3]);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(sm.a_ready);
@@ -468,66 +502,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
         const bool last = (l == LAST_TC);
-        char* ih = P.img.act + (int64_t)l * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
-        char* il = ih + P.img.term_stride;
-        const float* bias = s_bias + l * 256;
-        uint32_t bits[8];
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tlane + TM_D + c * 32, raw);
-          tmem_ld_wait();
-          float v[32];
-          uint32_t bw = 0;
+        char* img = P.img.act + (int64_t)l * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
+        const float* bias = s_bias + l * 256 + hh * 128;
+        uint32_t bits[4];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float z = fmaf(__uint_as_float(raw[i]), inv_scale, bias[c * 32 + i]);
-            bw |= (z > 0.f ? 1u : 0u) << i;
-            v[i] = fmaxf(z, 0.f);
-          }
-          bits[c] = bw;
-          if (last) {
+        for (int ab = 0; ab < 2; ++ab) {
+          uint32_t ph[32], pl[32];
 #pragma unroll
-            for (int j = 0; j < OUT; ++j) {
-              float a = outacc[j];
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = ab * 2 + cc;
+            uint32_t raw[32];
+            tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw);
+            tmem_ld_wait();
+            uint32_t bw = 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) a = fmaf(v[i], s_wlast[j * KLAST + c * 32 + i], a);
-              outacc[j] = a;
+            for (int i = 0; i < 32; i += 2) {
+              const float z0 = fmaf(__uint_as_float(raw[i]), inv_scale, bias[c * 32 + i]);
+              const float z1 = fmaf(__uint_as_float(raw[i + 1]), inv_scale, bias[c * 32 + i + 1]);
+              bw |= (z0 > 0.f ? 1u : 0u) << i;
+              bw |= (z1 > 0.f ? 1u : 0u) << (i + 1);
+              const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
+              if (last) {
+#pragma unroll
+                for (int j = 0; j < OUT; ++j) {
+                  outacc[j] = fmaf(v0, s_wlast[j * KLAST + hh * 128 + c * 32 + i], outacc[j]);
+                  outacc[j] = fmaf(v1, s_wlast[j * KLAST + hh * 128 + c * 32 + i + 1], outacc[j]);
+                }
+              }
+              split2_f16(v0, v1, ph[cc * 16 + i / 2], pl[cc * 16 + i / 2]);
+            }
+            bits[c] = bw;
+            if (!last) {
+              uint32_t th[16], tl[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { th[i] = ph[cc * 16 + i]; tl[i] = pl[cc * 16 + i]; }
+              tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
+              tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
             }
           }
-          emit_chunk(v, S_ACT, c, m, tlane, !last, ih, il);
+          char* g = img + (hh * 2 + ab) * ATOM_BYTES;
+          stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
         }
-        uint4* bdst = reinterpret_cast<uint4*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8);
-        bdst[0] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
-        bdst[1] = make_uint4(bits[4], bits[5], bits[6], bits[7]);
+        *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8 + hh * 4) =
+            make_uint4(bits[0], bits[1], bits[2], bits[3]);
         if (!last) {
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(sm.a_ready);
         }
       }
-      // ---------------- output layer (+ skip part for the atlas) and tanh
+      // ---------------- output layer (+ skip part for the atlas) and tanh; the two column halves of a row
+      // combine through shared memory
       if (ATLAS) {
         const char* a_hi = sm.aux;
-        const char* a_lo = sm.aux + PE_IMG_BYTES;
-#pragma unroll 1
-        for (int k = 0; k < PE_COLS; ++k) {
-          const int off = img64_off(m, k);
-          const float pv = (__half2float(*reinterpret_cast<const __half*>(a_hi + off)) +
-                            __half2float(*reinterpret_cast<const __half*>(a_lo + off))) * (1.0f / S_ACT);
+        const char* a_lo = sm.aux + ATOM_BYTES;
+        for (int k = hh * 20; k < hh * 20 + 20; ++k) {
+          const int off = atom_off(m, k);
+          const float pv = __half2float(*reinterpret_cast<const __half*>(a_hi + off)) +
+                           __half2float(*reinterpret_cast<const __half*>(a_lo + off));     // S_ACT * pe
 #pragma unroll
           for (int j = 0; j < OUT; ++j) outacc[j] = fmaf(pv, s_wlast[j * KLAST + 256 + k], outacc[j]);
         }
       }
+      if (hh == 1) {
 #pragma unroll
-      for (int j = 0; j < OUT; ++j) P.y[row * OUT + j] = tanhf(outacc[j] + s_blast[j]);
-      // all epilogue threads are done with the aux tile / D before the next tile's prologue overwrites them:
-      // the a_ready arrival of the next prologue is per-thread ordered after this point, and the MMA warp
-      // only reads aux after all 128 arrivals.  The aux tile itself is rewritten by the same thread rows.
-      if (ATLAS) {
-        // other threads may still be reading their own rows only (row-private), so no barrier is needed
+        for (int j = 0; j < OUT; ++j) s_xch[m * 4 + j] = outacc[j];
       }
+      named_bar(3, EPI_THREADS);
+      if (hh == 0) {
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) P.y[row * OUT + j] = tanhf(outacc[j] + s_xch[m * 4 + j] + s_blast[j]);
+      }
+      named_bar(3, EPI_THREADS);                         // s_xch / aux tile reuse by the next tile
     }
+    if (issuer) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -535,7 +583,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
 }
 
 // =============================================================================================
-// backward (dgrad chain + last-layer / first-layer / bias gradients)
+// backward (dgrad chain + first-layer / bias gradients; the 64-wide output-layer dZ image)
 // =============================================================================================
 struct BwdParams {
   const float* dy;           // mapping: d_uv [rows][2];  atlas: d_y [rows][3]
@@ -597,15 +645,15 @@ __device__ __forceinline__ void grad_scales(const int* gmax_bits, float& s_g, fl
 template <bool ATLAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ char smem_raw[];
-  SmemMap sm; sm.init(smem_raw);
+  constexpr int NST = KCfg<ATLAS>::NST;
+  SmemMap<NST, ATLAS> sm; sm.init(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int L = ATLAS ? 8 : 6;
   constexpr int OUT = ATLAS ? 3 : 2;
   constexpr int KLAST = ATLAS ? 296 : 256;
-  // dgrad layers run from L-2 down to LOW (atlas: additionally the 64-wide dPE product through layer 0)
-  constexpr int LOW = 1;
-  // shared constants: last-layer weights; bias-gradient accumulators for layers 0..L-2 at s_bacc[l*256];
-  // first-layer weight gradient accumulator (mapping: 256x3); last-layer weight gradient accumulator
+  constexpr int LOW = 1;                                  // dgrad layers L-2 .. 1 (atlas: + the dPE product)
+  constexpr int N_DGRAD = L - 2 - LOW + 1;
+  // shared constants: last-layer weights; bias-gradient accumulators for layers 0..L-2; (mapping) dW0
   float* s_wlast = sm.cst;                               // OUT*KLAST (<= 888)
   float* s_bacc = sm.cst + 896;                          // (L-1)*256 (<= 1792)
   float* s_w0acc = s_bacc + (L - 1) * 256;               // mapping: 768   (896+1280+768 = 2944 <= 3072)
@@ -620,26 +668,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
       uint32_t h_par = 0;
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
         const int gt = ti.global_tile(t);
-        // stage 0..3 <- the input image of the last layer (h_{L-2}: hi 64 KB, lo 64 KB) for its weight
-        // gradient; the ring must be drained of this tile's predecessors first (empty waits do that)
-        const char* hsrc = P.img.act + (int64_t)(L - 2) * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
-        for (int i = 0; i < 4; ++i) {
-          mbar_wait(&pp.empty[pp.slot()], pp.parity() ^ 1);
-          mbar_expect_tx(&pp.full[pp.slot()], STAGE_BYTES);
-          const char* src = hsrc + (i >> 1) * P.img.term_stride + (i & 1) * STAGE_BYTES;
-          bulk_g2s(pp.stage + pp.slot() * STAGE_BYTES, src, STAGE_BYTES, &pp.full[pp.slot()]);
-          ++pp.it;
-        }
         if (ATLAS) {
           // aux tile <- positional-encoding image of this tile (hi, lo), completion on misc[0]
           mbar_wait(&sm.misc[1], h_par ^ 1);             // previous tile's readers are done with aux
-          mbar_expect_tx(&sm.misc[0], 2 * PE_IMG_BYTES);
-          bulk_g2s(sm.aux, P.img.pe + (int64_t)gt * PE_IMG_BYTES, PE_IMG_BYTES, &sm.misc[0]);
-          bulk_g2s(sm.aux + PE_IMG_BYTES, P.img.pe + P.img.pe_term_stride + (int64_t)gt * PE_IMG_BYTES, PE_IMG_BYTES,
+          mbar_expect_tx(&sm.misc[0], 2 * ATOM_BYTES);
+          bulk_g2s(sm.aux, P.img.pe + (int64_t)gt * ATOM_BYTES, ATOM_BYTES, &sm.misc[0]);
+          bulk_g2s(sm.aux + ATOM_BYTES, P.img.pe + P.img.w64_term_stride + (int64_t)gt * ATOM_BYTES, ATOM_BYTES,
                    &sm.misc[0]);
           h_par ^= 1;
         }
@@ -649,144 +687,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      Pipe pp{sm.full, sm.empty, sm.stage, 0};
+      Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
       uint32_t a_par = 0;
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
-        // the four h stages are consumed by the epilogue warps; they are released through `empty` by
-        // this thread once the epilogue signalled (a_ready of the first dgrad layer)
-        const uint32_t it_h = pp.it;
-        pp.it += 4;
-        for (int l = L - 2; l >= LOW; --l) {
-          mbar_wait(sm.a_ready, a_par); a_par ^= 1;
-          tc_fence_after();
-          if (l == L - 2) {
-            // epilogue finished reading the h stages: hand them back to the producer
-            for (int i = 0; i < 4; ++i) mbar_arrive(&pp.empty[(it_h + i) % NSTAGE]);
-          }
-          bool first = true;
-          for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC, first);
-          mma_commit(sm.d_ready);
-        }
-        if (ATLAS) {
+        for (int l = 0; l < N_DGRAD + (ATLAS ? 1 : 0); ++l) {
           mbar_wait(sm.a_ready, a_par); a_par ^= 1;
           tc_fence_after();
           bool first = true;
-          for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC64, first);
+          const uint32_t idesc = (ATLAS && l == N_DGRAD) ? IDESC64 : IDESC;
+          for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, idesc, first);
           mma_commit(sm.d_ready);
         }
       }
     }
   } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    EpiThread et; et.init(tmem);
+    const int m = et.m, hh = et.hh;
+    const bool issuer = (et.q == 0 && lane == 0);
+    const int bar_id = 1 + hh;
     uint32_t d_par = 0, aux_par = 0;
-    uint32_t h_it = 0;                                    // mirrors the producer/MMA item counter
     const float inv_dgrad = inv_sg * (1.0f / S_W);        // D = (S_g dZ)(S_w W)
     for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
       const int gt = ti.global_tile(t);
       const int64_t row = (int64_t)gt * TM + m;
-      // ---------------- output layer: tanh', weight/bias gradient, dA_{L-1}
+      // ---------------- output layer: tanh', bias gradient, the 64-wide dZ_L image, dA_{L-1}
       float dzl[OUT];
 #pragma unroll
       for (int j = 0; j < OUT; ++j) {
         const float yv = P.y[row * OUT + j];
         dzl[j] = P.dy[row * OUT + j] * (1.0f - yv * yv);
       }
-      // wait for the h image (4 stages) [and the PE tile]
-      const char* hst[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t it = h_it + i;
-        mbar_wait(&sm.full[it % NSTAGE], (it / NSTAGE) & 1);
-        hst[i] = sm.stage + (it % NSTAGE) * STAGE_BYTES;
-      }
-      if (ATLAS) { mbar_wait(&sm.misc[0], aux_par); }
-      // per-tile last-layer weight gradient: dW[j][k] = sum_m dz[m][j] * a[m][k].  Row m's dz is
-      // broadcast through shared memory (cst scratch after the accumulators is full, so use shuffles):
-      // thread (q, lane) owns columns k = q*64 + lane and q*64 + 32 + lane and loops over the 128 rows.
-      {
-        // stash dz of all 128 rows in the first bytes of the d_ready-free region: use s_w0acc tail? keep
-        // it simple: a small static shared array
-        __shared__ float s_dz[TM][4];
-#pragma unroll
-        for (int j = 0; j < OUT; ++j) s_dz[m][j] = dzl[j];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        float acc[2][OUT];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int j = 0; j < OUT; ++j) acc[u][j] = 0.f;
-        const int k0 = q * 64 + lane, k1 = k0 + 32;
-#pragma unroll 4
-        for (int r = 0; r < TM; ++r) {
-          const int o0 = img_off(r, k0), o1 = img_off(r, k1);
-          // image = [hi: stages 0,1 (64 KB)][lo: stages 2,3]; each stage holds 8 groups (32 KB)
-          const float a0 = (__half2float(*reinterpret_cast<const __half*>(hst[o0 >> 15] + (o0 & 32767))) +
-                            __half2float(*reinterpret_cast<const __half*>(hst[2 + (o0 >> 15)] + (o0 & 32767)))) *
-                           (1.0f / S_ACT);
-          const float a1 = (__half2float(*reinterpret_cast<const __half*>(hst[o1 >> 15] + (o1 & 32767))) +
-                            __half2float(*reinterpret_cast<const __half*>(hst[2 + (o1 >> 15)] + (o1 & 32767)))) *
-                           (1.0f / S_ACT);
-#pragma unroll
-          for (int j = 0; j < OUT; ++j) {
-            const float dzv = s_dz[r][j];
-            acc[0][j] = fmaf(dzv, a0, acc[0][j]);
-            acc[1][j] = fmaf(dzv, a1, acc[1][j]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < OUT; ++j) {
-          atomicAdd(P.grads + P.w_off[L - 1] + j * KLAST + k0, acc[0][j]);
-          atomicAdd(P.grads + P.w_off[L - 1] + j * KLAST + k1, acc[1][j]);
-        }
-        if (ATLAS && m < PE_COLS) {
-          // skip part of the output layer: dW[j][256+k] = sum_m dz[m][j] * pe[m][k], thread m<40 owns k=m
-          float pacc[OUT];
-#pragma unroll
-          for (int j = 0; j < OUT; ++j) pacc[j] = 0.f;
-          for (int r = 0; r < TM; ++r) {
-            const int off = img64_off(r, m);
-            const float pv = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
-                              __half2float(*reinterpret_cast<const __half*>(sm.aux + PE_IMG_BYTES + off))) *
-                             (1.0f / S_ACT);
-#pragma unroll
-            for (int j = 0; j < OUT; ++j) pacc[j] = fmaf(s_dz[r][j], pv, pacc[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < OUT; ++j) atomicAdd(P.grads + P.w_off[L - 1] + j * KLAST + 256 + m, pacc[j]);
-        }
-        // bias gradient of the output layer
+      if (hh == 0) {
 #pragma unroll
         for (int j = 0; j < OUT; ++j) {
           float sj = dzl[j];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, o);
-          if (lane == 0) atomicAdd(P.grads + P.b_off[L - 1] + j, sj);
+          if (lane == 0 && sj != 0.f) atomicAdd(P.grads + P.b_off[L - 1] + j, sj);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");        // s_dz reuse by the next tile
+        // image row: columns 0..OUT-1 = S_g * dz, rest zero
+        uint32_t h0, l0, h1 = 0, l1 = 0;
+        split2_f16(dzl[0] * s_g, dzl[1] * s_g, h0, l0);
+        if (OUT == 3) split2_f16(dzl[OUT - 1] * s_g, 0.f, h1, l1);
+        char* g_hi = P.img.dzl + (int64_t)gt * ATOM_BYTES;
+        char* g_lo = g_hi + P.img.w64_term_stride;
+        const int r = m & 7;
+        const int base = (m >> 3) * 1024 + r * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const int off = base + ((c16 ^ r) << 4);
+          *reinterpret_cast<uint4*>(g_hi + off) = c16 == 0 ? make_uint4(h0, h1, 0, 0) : make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(g_lo + off) = c16 == 0 ? make_uint4(l0, l1, 0, 0) : make_uint4(0, 0, 0, 0);
+        }
       }
-      h_it += 4 + (L - 2 - LOW + 1) * 8 + (ATLAS ? 8 : 0);
       // dA_{L-1}[k] = sum_j dz[j] W_last[j][k], masked by relu'(h_{L-2}) -> dZ_{L-2}
       {
-        const uint32_t* bsrc = P.img.bits + ((int64_t)(L - 2) * P.img.rows + row) * 8;
-        const uint4 b0 = *reinterpret_cast<const uint4*>(bsrc), b1 = *reinterpret_cast<const uint4*>(bsrc + 4);
-        const uint32_t bits[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        char* ih = P.img.dz + (int64_t)(L - 2) * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
-        char* il = ih + P.img.term_stride;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          float v[32];
+        const uint4 bb = *reinterpret_cast<const uint4*>(P.img.bits + ((int64_t)(L - 2) * P.img.rows + row) * 8 + hh * 4);
+        const uint32_t bits[4] = {bb.x, bb.y, bb.z, bb.w};
+        char* img = P.img.dz + (int64_t)(L - 2) * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = 0.f;
+        for (int ab = 0; ab < 2; ++ab) {
+          uint32_t ph[32], pl[32];
 #pragma unroll
-            for (int j = 0; j < OUT; ++j) a = fmaf(dzl[j], s_wlast[j * KLAST + c * 32 + i], a);
-            v[i] = ((bits[c] >> i) & 1u) ? a : 0.f;
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = ab * 2 + cc;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float a = 0.f;
+#pragma unroll
+              for (int j = 0; j < OUT; ++j) a = fmaf(dzl[j], s_wlast[j * KLAST + hh * 128 + c * 32 + i], a);
+              v[i] = ((bits[c] >> i) & 1u) ? a : 0.f;
+            }
+            atomicAdd(&s_bacc[(L - 2) * 256 + hh * 128 + c * 32 + lane], warp_colsum32(v, lane));
+            uint32_t th[16], tl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, th[i], tl[i]);
+              ph[cc * 16 + i] = th[i]; pl[cc * 16 + i] = tl[i];
+            }
+            tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
+            tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
           }
-          const float cs = warp_colsum32(v, lane);
-          atomicAdd(&s_bacc[(L - 2) * 256 + c * 32 + lane], cs);
-          emit_chunk(v, s_g, c, m, tlane, true, ih, il);
+          char* g = img + (hh * 2 + ab) * ATOM_BYTES;
+          stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -798,39 +782,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
         const int slot = l - 1;                           // produces dZ_{l-1}
-        const uint32_t* bsrc = P.img.bits + ((int64_t)slot * P.img.rows + row) * 8;
-        const uint4 b0 = *reinterpret_cast<const uint4*>(bsrc), b1 = *reinterpret_cast<const uint4*>(bsrc + 4);
-        const uint32_t bits[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint4 bb = *reinterpret_cast<const uint4*>(P.img.bits + ((int64_t)slot * P.img.rows + row) * 8 + hh * 4);
+        const uint32_t bits[4] = {bb.x, bb.y, bb.z, bb.w};
         const bool need_img = ATLAS || slot >= 1;         // mapping dZ_0 feeds only the CUDA-core layer-0 gradient
         const bool need_tmem = ATLAS ? true : (slot >= 1);
-        char* ih = P.img.dz + (int64_t)slot * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
-        char* il = ih + P.img.term_stride;
+        char* img = P.img.dz + (int64_t)slot * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!ATLAS && slot == 0) xv = *reinterpret_cast<const float4*>(P.x + row * 4);
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tlane + TM_D + c * 32, raw);
-          tmem_ld_wait();
-          float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ((bits[c] >> i) & 1u) ? __uint_as_float(raw[i]) * inv_dgrad : 0.f;
-          const float cs = warp_colsum32(v, lane);
-          atomicAdd(&s_bacc[slot * 256 + c * 32 + lane], cs);
-          if (!ATLAS && slot == 0) {
-            // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
-            float w[32];
+        for (int ab = 0; ab < 2; ++ab) {
+          uint32_t ph[32], pl[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.x;
-            atomicAdd(&s_w0acc[(c * 32 + lane) * 3 + 0], warp_colsum32(w, lane));
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = ab * 2 + cc;
+            uint32_t raw[32];
+            tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.y;
-            atomicAdd(&s_w0acc[(c * 32 + lane) * 3 + 1], warp_colsum32(w, lane));
+            for (int i = 0; i < 32; ++i) v[i] = ((bits[c] >> i) & 1u) ? __uint_as_float(raw[i]) * inv_dgrad : 0.f;
+            atomicAdd(&s_bacc[slot * 256 + hh * 128 + c * 32 + lane], warp_colsum32(v, lane));
+            if (!ATLAS && slot == 0) {
+              // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
+              const int n = hh * 128 + c * 32 + lane;
+              float w[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.z;
-            atomicAdd(&s_w0acc[(c * 32 + lane) * 3 + 2], warp_colsum32(w, lane));
+              for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.x;
+              atomicAdd(&s_w0acc[n * 3 + 0], warp_colsum32(w, lane));
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.y;
+              atomicAdd(&s_w0acc[n * 3 + 1], warp_colsum32(w, lane));
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.z;
+              atomicAdd(&s_w0acc[n * 3 + 2], warp_colsum32(w, lane));
+            }
+            if (need_img || need_tmem) {
+              uint32_t th[16], tl[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, th[i], tl[i]);
+                ph[cc * 16 + i] = th[i]; pl[cc * 16 + i] = tl[i];
+              }
+              if (need_tmem) {
+                tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
+                tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
+              }
+            }
           }
-          if (need_img || need_tmem) emit_chunk(v, s_g, c, m, tlane, need_tmem, need_img ? ih : nullptr, il);
+          if (need_img) {
+            char* g = img + (hh * 2 + ab) * ATOM_BYTES;
+            stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+          }
         }
         if (need_tmem) {
           tmem_st_wait();
@@ -842,47 +844,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         // ---------------- dPE = dZ_0 W_0 (64 columns, 40 real) -> d(in) -> d_uv += 0.5 * d(in)
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
-        float din[2] = {0.f, 0.f};
+        mbar_wait(&sm.misc[0], aux_par);                  // PE tile of this row block
+        if (hh == 0) {
+          float din[2] = {0.f, 0.f};
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tlane + TM_D + c * 32, raw);
-          tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tmem_ld32(et.tlane + TM_D + c * 32, raw);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = c * 32 + i;
-            if (col < PE_COLS) {
-              const int k = col >> 2, e = col & 3;         // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
-              const float g = __uint_as_float(raw[i]) * inv_dgrad;
-              // partner value: d sin = cos * b,  d cos = -sin * b
-              const int pcol = (e < 2) ? col + 2 : col - 2;
-              const int off = img64_off(m, pcol);
-              const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
-                                     __half2float(*reinterpret_cast<const __half*>(sm.aux + PE_IMG_BYTES + off))) *
-                                    (1.0f / S_ACT);
-              const float bk = pe_freq(k);
-              din[e & 1] += (e < 2) ? g * partner * bk : -g * partner * bk;
+            for (int i = 0; i < 32; ++i) {
+              const int col = c * 32 + i;
+              if (col < PE_COLS) {
+                const int k = col >> 2, e = col & 3;       // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
+                const float g = __uint_as_float(raw[i]) * inv_dgrad;
+                const int pcol = (e < 2) ? col + 2 : col - 2;   // d sin = cos * b,  d cos = -sin * b
+                const int off = atom_off(m, pcol);
+                const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
+                                       __half2float(*reinterpret_cast<const __half*>(sm.aux + ATOM_BYTES + off))) *
+                                      (1.0f / S_ACT);
+                const float bk = pe_freq(k);
+                din[e & 1] += (e < 2) ? g * partner * bk : -g * partner * bk;
+              }
             }
           }
+          float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
+          float2 cur = *dst;
+          cur.x += 0.5f * din[0];
+          cur.y += 0.5f * din[1];
+          *dst = cur;
         }
-        float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
-        float2 cur = *dst;
-        cur.x += 0.5f * din[0];
-        cur.y += 0.5f * din[1];
-        *dst = cur;
+        tc_fence_before();
         mbar_arrive(&sm.misc[1]);                         // aux tile may be overwritten
         aux_par ^= 1;
+        named_bar(3, EPI_THREADS);                        // D of the dPE product fully read before the next tile
       }
     }
+    if (issuer) bulk_wait_all0();
     // flush the per-CTA accumulators
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int et = threadIdx.x - 64;
-    for (int i = et; i < (L - 1) * 256; i += 128) {
+    named_bar(3, EPI_THREADS);
+    for (int i = et.tid; i < (L - 1) * 256; i += EPI_THREADS) {
       const float v = s_bacc[i];
       if (v != 0.f) atomicAdd(P.grads + P.b_off[i >> 8] + (i & 255), v);
     }
     if (!ATLAS)
-      for (int i = et; i < 768; i += 128) {
+      for (int i = et.tid; i < 768; i += EPI_THREADS) {
         const float v = s_w0acc[i];
         if (v != 0.f) atomicAdd(P.grads + P.w_off[0] + i, v);
       }
@@ -893,26 +899,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
 }
 
 // =============================================================================================
-// weight gradients of the 256-wide layers:  dW[n][k] += sum_rows dZ[row][n] * H[row][k]
+// weight gradients:  dW[n][k] += sum_rows dZ[row][n] * H[row][k]
 // =============================================================================================
 struct WgradItem {
-  const char* a_img;      // dZ images (hi; lo at +a_term)   [tile][64 KB]
-  const char* b_img;      // input images (hi; lo at +b_term) [tile][64 KB] or [tile][16 KB] when b_cols == 64
+  const char* a_img;      // dZ image, hi (lo at +a_term): 256 wide [tile][4 atoms][16 KB] or 64 wide [tile][16 KB]
+  const char* b_img;      // input image, hi (lo at +b_term): same two shapes
   int64_t a_term, b_term;
-  float* out; int ld_out; // fp32 dW block [256][ld_out], columns [0, n_cols)
+  float* out; int ld_out; // fp32 dW block [a_cols rows][ld_out], columns [0, n_cols)
+  int a_cols;             // 256: two M=128 MMAs;  64: one M=64 MMA (output-layer gradient, n_rows real rows)
   int b_cols;             // 256 or 64
-  int n_cols;             // real columns to write (<= b_cols)
+  int n_rows, n_cols;     // real rows / columns to write
   int cap, n_groups;      // row geometry of the network this item belongs to
   int split, n_split;     // this CTA's share of the live tiles
 };
 constexpr int MAX_WGRAD_ITEMS = 320;
 struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; };
 
-constexpr int WG_STAGE = 65536;          // 32 rows: A hi 16K | A lo 16K | B hi 16K | B lo 16K
+constexpr int WG_STAGE = 65536;          // 32 rows: A hi 16K | A lo 16K | B hi 16K | B lo 16K, each [atom][4 groups][1 KB]
 constexpr int WG_NSTAGE = 3;
 constexpr int WG_SMEM = WG_NSTAGE * WG_STAGE + 1024 + 256;
+constexpr int WG_THREADS = 192;
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_valid, const int* __restrict__ gmax_bits) {
   extern __shared__ char smem_raw[];
   char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -932,55 +940,54 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if ((int)blockIdx.x >= items->n) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem, TMEM_COLS); return; }
   const WgradItem W = items->it[blockIdx.x];
   TileIter ti; ti.init(W.cap, W.n_groups, n_valid);
   const int t_begin = (int)((int64_t)ti.total * W.split / W.n_split);
   const int t_end = (int)((int64_t)ti.total * (W.split + 1) / W.n_split);
-  const int b_tile_bytes = W.b_cols == 256 ? TILE_IMG_BYTES : PE_IMG_BYTES;
-  const int b_chunk = b_tile_bytes / 4;          // bytes of a 32-row chunk of one term
-  const uint32_t idesc = make_idesc(128, W.b_cols == 256 ? 256 : 64, 1, 1);
+  const int a_atoms = W.a_cols / 64, b_atoms = W.b_cols / 64;
   const int n_steps = (t_end - t_begin) * 4;     // 32-row steps
 
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < n_steps; ++s) {
         const int slot = s % WG_NSTAGE;
-        const uint32_t par = (s / WG_NSTAGE) & 1;
-        mbar_wait(&empty[slot], par ^ 1);
+        mbar_wait(&empty[slot], ((s / WG_NSTAGE) & 1) ^ 1);
         const int gt = ti.global_tile(t_begin + (s >> 2));
-        const int ch = s & 3;
+        const int ch = s & 3;                      // 32-row chunk = groups 4ch .. 4ch+3 of every atom block
         char* dst = stage + slot * WG_STAGE;
-        mbar_expect_tx(&full[slot], 2 * 16384 + 2 * b_chunk);
-        const char* a = W.a_img + (int64_t)gt * TILE_IMG_BYTES + ch * 16384;
-        bulk_g2s(dst, a, 16384, &full[slot]);
-        bulk_g2s(dst + 16384, a + W.a_term, 16384, &full[slot]);
-        const char* b = W.b_img + (int64_t)gt * b_tile_bytes + ch * b_chunk;
-        bulk_g2s(dst + 32768, b, b_chunk, &full[slot]);
-        bulk_g2s(dst + 49152, b + W.b_term, b_chunk, &full[slot]);
+        mbar_expect_tx(&full[slot], 2 * 4096 * (a_atoms + b_atoms));
+        const char* a = W.a_img + (int64_t)gt * a_atoms * ATOM_BYTES + ch * 4096;
+        for (int j = 0; j < a_atoms; ++j) {
+          bulk_g2s(dst + j * 4096, a + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+          bulk_g2s(dst + 16384 + j * 4096, a + W.a_term + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+        }
+        const char* b = W.b_img + (int64_t)gt * b_atoms * ATOM_BYTES + ch * 4096;
+        for (int j = 0; j < b_atoms; ++j) {
+          bulk_g2s(dst + 32768 + j * 4096, b + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+          bulk_g2s(dst + 49152 + j * 4096, b + W.b_term + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t a_lbo = 1024, a_sbo = 4096;
-      const uint32_t b_lbo = 1024, b_sbo = W.b_cols == 256 ? 4096 : 1024;
-      const uint32_t b_kstep = W.b_cols == 256 ? 8192 : 2048;     // 16 rows = 2 groups
-      const uint32_t d_half = W.b_cols == 256 ? 256 : 64;         // TMEM columns per M-half
+      // smem operand: [atom][4 groups][1 KB] -> MN-major SW128: LBO (atom stride) 4096, SBO (8-row group) 1024
+      const int m_inst = W.a_cols == 256 ? 128 : 64;
+      const uint32_t idesc = make_idesc(m_inst, W.b_cols, 1, 1);
+      const int m_halves = W.a_cols == 256 ? 2 : 1;
       for (int s = 0; s < n_steps; ++s) {
         const int slot = s % WG_NSTAGE;
         mbar_wait(&full[slot], (s / WG_NSTAGE) & 1);
         tc_fence_after();
         const uint32_t sb = smem_u32(stage + slot * WG_STAGE);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-          for (int mh = 0; mh < 2; ++mh) {
+        for (int ks = 0; ks < 2; ++ks) {             // 16 rows = 2 groups per MMA
+          for (int mh = 0; mh < m_halves; ++mh) {
             const uint32_t acc = (s | ks) ? 1u : 0u;
-            const uint32_t d = tmem + mh * d_half;
-            const uint64_t a_hi = make_desc(sb + ks * 8192 + mh * 2048, a_lbo, a_sbo);
-            const uint64_t a_lo = make_desc(sb + 16384 + ks * 8192 + mh * 2048, a_lbo, a_sbo);
-            const uint64_t b_hi = make_desc(sb + 32768 + ks * b_kstep, b_lbo, b_sbo);
-            const uint64_t b_lo = make_desc(sb + 49152 + ks * b_kstep, b_lbo, b_sbo);
+            const uint32_t d = tmem + mh * W.b_cols;
+            const uint64_t a_hi = make_desc(sb + ks * 2048 + mh * 8192, 4096, 1024);
+            const uint64_t a_lo = make_desc(sb + 16384 + ks * 2048 + mh * 8192, 4096, 1024);
+            const uint64_t b_hi = make_desc(sb + 32768 + ks * 2048, 4096, 1024);
+            const uint64_t b_lo = make_desc(sb + 49152 + ks * 2048, 4096, 1024);
             mma_ss(d, a_hi, b_hi, idesc, acc);
             mma_ss(d, a_hi, b_lo, idesc, 1u);
             mma_ss(d, a_lo, b_hi, idesc, 1u);
@@ -998,18 +1005,27 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     mbar_wait(d_ready, 0);
     tc_fence_after();
-    const uint32_t d_half = W.b_cols == 256 ? 256 : 64;
-    for (int mh = 0; mh < 2; ++mh) {
-      const int n = mh * 128 + q * 32 + lane;              // output row (layer output index)
+    const int m_halves = W.a_cols == 256 ? 2 : 1;
+    for (int mh = 0; mh < m_halves; ++mh) {
+      // M=128: accumulator row i of half mh lives in TMEM lane i.  M=64: rows 0..15 in lanes 0..15 of quadrant 0.
+      const int n = mh * 128 + q * 32 + lane;              // layer output index of this thread's accumulator row
+      const bool live = W.a_cols == 256 ? true : (q == 0 && lane < W.n_rows);
       float* orow = W.out + (int64_t)n * W.ld_out;
       for (int c = 0; c < W.b_cols / 32; ++c) {
         uint32_t raw[32];
-        tmem_ld32(tlane + mh * d_half + c * 32, raw);
+        tmem_ld32(tlane + mh * W.b_cols + c * 32, raw);
         tmem_ld_wait();
+        if (!live) continue;
+        if (((W.ld_out & 3) == 0) && c * 32 + 32 <= W.n_cols) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          if (col < W.n_cols) atomicAdd(orow + col, __uint_as_float(raw[i]) * inv);
+          for (int i = 0; i < 32; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + i),
+                      make_float4(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv,
+                                  __uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < W.n_cols) atomicAdd(orow + c * 32 + i, __uint_as_float(raw[i]) * inv);
         }
       }
     }
@@ -1036,18 +1052,17 @@ static int sm_count() {
 static int ensure_attrs() {
   static bool done = false;
   if (done) return B200_OK;
-  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   done = true;
   return B200_OK;
 }
 
-// The job / item tables live at the start of the TC workspace region (device memory) and are rebuilt
-// by a tiny kernel-free cudaMemcpyAsync from a host staging copy kept alive per call site.  They depend
-// only on pointers, so they are uploaded once per (workspace, geometry) and reused inside graphs.
+// Job / item tables depend only on pointers and geometry: built by one eager call per (workspace, row
+// geometry, parameter buffers), kept in device memory, reused inside captured graphs.
 struct HostTables {
   const void* key_base = nullptr; int key_cap = 0, key_groups = 0; const void* key_params = nullptr;
   const void* key_grads = nullptr; bool key_atlas = false;
@@ -1083,16 +1098,19 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
     set_error("tensor-core tables must be built by one eager call before graph capture");
     return B200_ERR_INVALID;
   }
+  B200_REQUIRE(s.as->L == 8 && s.ms->L == 6 && s.as->skip[4] && s.as->skip[7] && s.as->pe == 10 && s.ms->pe == 0 &&
+               s.as->hidden == HID && s.ms->hidden == HID, "tensor-core path is specialised to the two stage-1 networks");
   if (g_n_tabs == MAX_TABLES) g_n_tabs = 0;          // recycle (device buffers are reused)
-  HostTables& g_tab = g_tabs[g_n_tabs];
-  if (!g_tab.d_prep) {
-    B200_CHECK_CUDA(cudaMalloc(&g_tab.d_prep, sizeof(PrepJobs)));
-    B200_CHECK_CUDA(cudaMalloc(&g_tab.d_wg, sizeof(WgradItems)));
+  HostTables& tab = g_tabs[g_n_tabs];
+  if (!tab.d_prep) {
+    B200_CHECK_CUDA(cudaMalloc(&tab.d_prep, sizeof(PrepJobs)));
+    B200_CHECK_CUDA(cudaMalloc(&tab.d_wg, sizeof(WgradItems)));
   }
   static PrepJobs pj; static WgradItems wi;
   pj.n = 0; wi.n = 0;
   const float* pm = s.params;
   const float* pa = s.params + s.ms->total;
+  const bool atlas = s.y_atlas != nullptr;
   // ---- forward / dgrad weight images
   for (int net = 0; net < 2; ++net) {
     const MlpShape& sh = net ? *s.as : *s.ms;
@@ -1108,8 +1126,7 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
         add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
     }
     for (int l = 0; l < sh.L - 1; ++l) {
-      const bool used = net ? true : (l >= 1);
-      if (!used) continue;
+      if (!net && l < 1) continue;
       char* dst = im.w_bwd + im.w_bwd_layer[l];
       const float* W = pp + sh.w_off[l];
       // image rows = input index k of layer l (256, or 40 for atlas layer 0), chunk over the output index n
@@ -1117,51 +1134,65 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
       for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], rows, kc * 64, 64, 1, dst + (int64_t)kc * 2 * STAGE_BYTES);
     }
   }
-  // ---- wgrad items
-  const int sms = sm_count();
-  const int map_layers = s.ms->L - 2;              // layers 1..L-2
-  const int atl_layers = s.as->L - 2;              // layers 1..L-2 main
-  // weights: mapping rows dominate; distribute ~sms CTAs proportionally to rows
-  const double rows_map = (double)s.n_groups, rows_atl = 3.0;
-  const double work = map_layers * rows_map + atl_layers * rows_atl + 2 * rows_atl * 0.3;
-  auto splits_for = [&](double rows) { int v = (int)(rows / work * sms + 0.5); return v < 1 ? 1 : v; };
+  // ---- wgrad items.  The kernel is HBM-bound: balance CTAs by bytes read per tile
+  //      (A + B, both terms): 256x256 -> 256 KB, 256x64 -> 160 KB, 64x256 -> 160 KB, 64x64 -> 64 KB
+  struct Proto { const char* a; int64_t a_term; int a_cols; const char* b; int64_t b_term; int b_cols;
+                 float* out; int ld; int n_rows, n_cols, groups; double bytes; };
+  Proto protos[32]; int np = 0;
   float* gm = s.grads;
   float* ga = s.grads + s.ms->total;
-  auto add_item = [&](const NetImages& im, int slot_a, const char* b_img, int64_t b_term, int b_cols, float* out,
-                      int ld_out, int n_cols, int cap, int groups, int n_split) {
-    for (int sp = 0; sp < n_split; ++sp) {
-      WgradItem& it = wi.it[wi.n++];
-      it.a_img = im.dz + (int64_t)slot_a * im.slot_stride; it.a_term = im.term_stride;
-      it.b_img = b_img; it.b_term = b_term; it.out = out; it.ld_out = ld_out; it.b_cols = b_cols; it.n_cols = n_cols;
-      it.cap = cap; it.n_groups = groups; it.split = sp; it.n_split = n_split;
-    }
+  auto add_proto = [&](const char* a, int64_t a_term, int a_cols, const char* b, int64_t b_term,
+                       int b_cols, float* out, int ld, int n_rows, int n_cols, int groups) {
+    protos[np++] = Proto{a, a_term, a_cols, b, b_term, b_cols, out, ld, n_rows, n_cols, groups,
+                         (double)groups * (a_cols + b_cols) * 512.0};
   };
   {
-    const int sp_m = splits_for(rows_map), sp_a = splits_for(rows_atl), sp_x = splits_for(rows_atl * 0.3);
-    for (int l = 1; l <= s.ms->L - 2; ++l)
-      add_item(lay.map, l, lay.map.act + (int64_t)(l - 1) * lay.map.slot_stride, lay.map.term_stride, 256,
-               gm + s.ms->w_off[l], s.ms->K[l], 256, s.cap, s.n_groups, sp_m);
-    if (s.y_atlas != nullptr) {
-      for (int l = 1; l <= s.as->L - 2; ++l)
-        add_item(lay.atl, l, lay.atl.act + (int64_t)(l - 1) * lay.atl.slot_stride, lay.atl.term_stride, 256,
-                 ga + s.as->w_off[l], s.as->K[l], 256, s.cap, 3, sp_a);
-      // positional-encoding parts: layer 0 and the skip layer(s) below the output layer
-      add_item(lay.atl, 0, lay.atl.pe, lay.atl.pe_term_stride, 64, ga + s.as->w_off[0], s.as->K[0], PE_COLS, s.cap, 3, sp_x);
-      for (int l = 1; l <= s.as->L - 2; ++l)
-        if (s.as->skip[l])
-          add_item(lay.atl, l, lay.atl.pe, lay.atl.pe_term_stride, 64, ga + s.as->w_off[l] + 256, s.as->K[l], PE_COLS,
-                   s.cap, 3, sp_x);
+    const NetImages& im = lay.map; const MlpShape& sh = *s.ms;
+    for (int l = 1; l <= sh.L - 2; ++l)
+      add_proto(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.act + (int64_t)(l - 1) * im.slot_stride,
+                im.term_stride, 256, gm + sh.w_off[l], sh.K[l], 256, 256, s.n_groups);
+    add_proto(im.dzl, im.w64_term_stride, 64, im.act + (int64_t)(sh.L - 2) * im.slot_stride, im.term_stride, 256,
+              gm + sh.w_off[sh.L - 1], sh.K[sh.L - 1], sh.out_dim, 256, s.n_groups);
+  }
+  if (atlas) {
+    const NetImages& im = lay.atl; const MlpShape& sh = *s.as;
+    for (int l = 1; l <= sh.L - 2; ++l)
+      add_proto(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.act + (int64_t)(l - 1) * im.slot_stride,
+                im.term_stride, 256, ga + sh.w_off[l], sh.K[l], 256, 256, 3);
+    // positional-encoding parts: layer 0 and the skip layers
+    add_proto(im.dz, im.term_stride, 256, im.pe, im.w64_term_stride, 64, ga + sh.w_off[0], sh.K[0], 256, PE_COLS, 3);
+    add_proto(im.dz + (int64_t)4 * im.slot_stride, im.term_stride, 256, im.pe, im.w64_term_stride, 64,
+              ga + sh.w_off[4] + 256, sh.K[4], 256, PE_COLS, 3);
+    // output layer: hidden part and skip part
+    add_proto(im.dzl, im.w64_term_stride, 64, im.act + (int64_t)(sh.L - 2) * im.slot_stride, im.term_stride, 256,
+              ga + sh.w_off[sh.L - 1], sh.K[sh.L - 1], sh.out_dim, 256, 3);
+    add_proto(im.dzl, im.w64_term_stride, 64, im.pe, im.w64_term_stride, 64, ga + sh.w_off[sh.L - 1] + 256,
+              sh.K[sh.L - 1], sh.out_dim, PE_COLS, 3);
+  }
+  double total_bytes = 0;
+  for (int i = 0; i < np; ++i) total_bytes += protos[i].bytes;
+  const int sms = sm_count();
+  for (int i = 0; i < np; ++i) {
+    int n_split = (int)(protos[i].bytes / total_bytes * sms + 0.5);
+    if (n_split < 1) n_split = 1;
+    for (int sp = 0; sp < n_split && wi.n < MAX_WGRAD_ITEMS; ++sp) {
+      WgradItem& it = wi.it[wi.n++];
+      const Proto& pr = protos[i];
+      it.a_img = pr.a; it.a_term = pr.a_term; it.a_cols = pr.a_cols;
+      it.b_img = pr.b; it.b_term = pr.b_term; it.b_cols = pr.b_cols;
+      it.out = pr.out; it.ld_out = pr.ld; it.n_rows = pr.n_rows; it.n_cols = pr.n_cols;
+      it.cap = s.cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split;
     }
   }
-  if (pj.n > MAX_PREP_JOBS || wi.n > MAX_WGRAD_ITEMS) { set_error("table overflow"); return B200_ERR_INVALID; }
-  B200_CHECK_CUDA(cudaMemcpyAsync(g_tab.d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
-  B200_CHECK_CUDA(cudaMemcpyAsync(g_tab.d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice, st));
+  if (pj.n > MAX_PREP_JOBS) { set_error("table overflow"); return B200_ERR_INVALID; }
+  B200_CHECK_CUDA(cudaMemcpyAsync(tab.d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
+  B200_CHECK_CUDA(cudaMemcpyAsync(tab.d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice, st));
   B200_CHECK_CUDA(cudaStreamSynchronize(st));
-  g_tab.n_wg = wi.n; g_tab.n_prep = pj.n;
-  g_tab.key_base = s.plan->base; g_tab.key_cap = s.cap; g_tab.key_groups = s.n_groups; g_tab.key_params = s.params;
-  g_tab.key_grads = s.grads; g_tab.key_atlas = s.y_atlas != nullptr;
+  tab.n_wg = wi.n; tab.n_prep = pj.n;
+  tab.key_base = s.plan->base; tab.key_cap = s.cap; tab.key_groups = s.n_groups; tab.key_params = s.params;
+  tab.key_grads = s.grads; tab.key_atlas = atlas;
   ++g_n_tabs;
-  *out = &g_tab;
+  *out = &tab;
   return B200_OK;
 }
 
@@ -1177,20 +1208,20 @@ static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   HostTables* tab = nullptr;
   B200_PROPAGATE(build_tables(s, lay, st, &tab));
   // weight images of both networks — every step, since Adam changed the parameters
-  tc_prep_kernel<<<tab->n_prep, 256, 0, st>>>(tab->d_prep);
+  tc_prep_kernel<<<tab->n_prep * 4, 128, 0, st>>>(tab->d_prep);
   B200_CHECK_LAUNCH();
   const int tiles_map = s.n_groups * (s.cap / TM);
   FwdParams pm{};
   fill_fwd(pm, *s.ms, lay.map, s.x_map, s.uv, s.params, s.cap, s.n_groups, s.counters);
   timer_begin(TAG_MAP_FWD, st);
-  tc_fwd_kernel<false><<<min(sm_count(), tiles_map), TC_THREADS, TC_SMEM_BYTES, st>>>(pm);
+  tc_fwd_kernel<false><<<min(sm_count(), tiles_map), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
   timer_end(TAG_MAP_FWD, st);
   B200_CHECK_LAUNCH();
   if (with_atlas) {
     FwdParams pa{};
     fill_fwd(pa, *s.as, lay.atl, s.uv, s.y_atlas, s.params + s.ms->total, s.cap, 3, s.counters);
     timer_begin(TAG_ATLAS_FWD, st);
-    tc_fwd_kernel<true><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pa);
+    tc_fwd_kernel<true><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, KCfg<true>::SMEM, st>>>(pa);
     timer_end(TAG_ATLAS_FWD, st);
     B200_CHECK_LAUNCH();
   }
@@ -1213,18 +1244,18 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
     fill(pa, *s.as, lay.atl, s.d_y, s.y_atlas, nullptr, const_cast<float*>(s.d_uv), s.params + s.ms->total,
          s.grads + s.ms->total, 3);
     timer_begin(TAG_ATLAS_BWD, st);
-    tc_bwd_kernel<true><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pa);
+    tc_bwd_kernel<true><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, KCfg<true>::SMEM, st>>>(pa);
     timer_end(TAG_ATLAS_BWD, st);
     B200_CHECK_LAUNCH();
   }
   BwdParams pm{};
   fill(pm, *s.ms, lay.map, s.d_uv, s.uv, s.x_map, nullptr, s.params, s.grads, s.n_groups);
   timer_begin(TAG_MAP_BWD, st);
-  tc_bwd_kernel<false><<<min(sm_count(), s.n_groups * (s.cap / TM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pm);
+  tc_bwd_kernel<false><<<min(sm_count(), s.n_groups * (s.cap / TM)), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
   timer_end(TAG_MAP_BWD, st);
   B200_CHECK_LAUNCH();
   timer_begin(TAG_WGRAD, st);
-  tc_wgrad_kernel<<<tab->n_wg, TC_THREADS, WG_SMEM, st>>>(tab->d_wg, s.counters, gmax);
+  tc_wgrad_kernel<<<tab->n_wg, WG_THREADS, WG_SMEM, st>>>(tab->d_wg, s.counters, gmax);
   timer_end(TAG_WGRAD, st);
   B200_CHECK_LAUNCH();
   return B200_OK;

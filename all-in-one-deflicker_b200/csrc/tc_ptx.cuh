@@ -154,3 +154,32 @@ __device__ __forceinline__ uint32_t pack2(__half a, __half b) {   // a -> low 16
 
 }  // namespace ptx
 }  // namespace b200
+
+namespace b200 {
+namespace ptx {
+// contiguous shared -> global through the TMA engine, tracked by bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// two floats -> packed half2 (a -> low half), round to nearest, saturating
+__device__ __forceinline__ uint32_t cvt_pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// split two already-scaled floats into packed (hi, lo) half2 words
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_pack_f16x2(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = cvt_pack_f16x2(a - hf.x, b - hf.y);
+}
+}  // namespace ptx
+}  // namespace b200
