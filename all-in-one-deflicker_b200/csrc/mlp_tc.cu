@@ -257,7 +257,7 @@ constexpr int SMEM_BARS = 256;
 template <bool ATLAS> struct KCfg {
   static constexpr int NST = ATLAS ? 3 : 4;
   static constexpr int SMEM = NST * STAGE_BYTES + SMEM_STAGING + (ATLAS ? SMEM_AUX : 0) + SMEM_CONST_FLOATS * 4 +
-                              SMEM_BARS + 1024;
+                              SMEM_BARS;
 };
 
 template <int NST, bool ATLAS>
@@ -265,8 +265,8 @@ struct SmemMap {
   char* stage; char* staging; char* aux; float* cst;
   uint64_t* full; uint64_t* empty; uint64_t* a_ready; uint64_t* d_ready; uint64_t* misc; uint32_t* tmem_slot;
   __device__ __forceinline__ void init(char* raw) {
-    char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-    stage = p; p += NST * STAGE_BYTES;
+    char* p = raw;                                   // 1024-aligned (checked in setup_cta): keeps the
+    stage = p; p += NST * STAGE_BYTES;               // shared address space visible to the compiler (LDS/STS)
     staging = p; p += SMEM_STAGING;
     aux = p; if (ATLAS) p += SMEM_AUX;
     cst = reinterpret_cast<float*>(p); p += SMEM_CONST_FLOATS * 4;
@@ -282,6 +282,7 @@ struct SmemMap {
 template <int NST, bool ATLAS>
 __device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp) {
   if (threadIdx.x == 0) {
+    if (smem_u32(sm.stage) & 1023u) { printf("b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
     mbar_init(sm.a_ready, EPI_THREADS);
     mbar_init(sm.d_ready, 1);
@@ -352,7 +353,7 @@ struct FwdParams {
 // =============================================================================================
 template <bool ATLAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_constant__ FwdParams P) {
-  extern __shared__ char smem_raw[];
+  extern __shared__ __align__(1024) char smem_raw[];
   constexpr int NST = KCfg<ATLAS>::NST;
   SmemMap<NST, ATLAS> sm; sm.init(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -644,7 +645,7 @@ __device__ __forceinline__ void grad_scales(const int* gmax_bits, float& s_g, fl
 
 template <bool ATLAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_constant__ BwdParams P) {
-  extern __shared__ char smem_raw[];
+  extern __shared__ __align__(1024) char smem_raw[];
   constexpr int NST = KCfg<ATLAS>::NST;
   SmemMap<NST, ATLAS> sm; sm.init(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -917,13 +918,13 @@ struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; };
 
 constexpr int WG_STAGE = 65536;          // 32 rows: A hi 16K | A lo 16K | B hi 16K | B lo 16K, each [atom][4 groups][1 KB]
 constexpr int WG_NSTAGE = 3;
-constexpr int WG_SMEM = WG_NSTAGE * WG_STAGE + 1024 + 256;
+constexpr int WG_SMEM = WG_NSTAGE * WG_STAGE + 256;
 constexpr int WG_THREADS = 192;
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_valid, const int* __restrict__ gmax_bits) {
-  extern __shared__ char smem_raw[];
-  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* p = smem_raw;
   char* stage = p;
   uint64_t* full = reinterpret_cast<uint64_t*>(p + WG_NSTAGE * WG_STAGE);
   uint64_t* empty = full + WG_NSTAGE;
@@ -931,6 +932,7 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
+    if (smem_u32(stage) & 1023u) { printf("b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < WG_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(d_ready, 1);
     fence_barrier_init();
@@ -1171,17 +1173,35 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
   }
   double total_bytes = 0;
   for (int i = 0; i < np; ++i) total_bytes += protos[i].bytes;
+  // exactly one CTA per SM (each CTA owns all 512 TMEM columns): largest-remainder apportionment
   const int sms = sm_count();
+  int n_split[32], used = 0;
+  double frac[32];
   for (int i = 0; i < np; ++i) {
-    int n_split = (int)(protos[i].bytes / total_bytes * sms + 0.5);
-    if (n_split < 1) n_split = 1;
-    for (int sp = 0; sp < n_split && wi.n < MAX_WGRAD_ITEMS; ++sp) {
+    const double want = protos[i].bytes / total_bytes * sms;
+    n_split[i] = (int)want < 1 ? 1 : (int)want;
+    frac[i] = want - (int)want;
+    used += n_split[i];
+  }
+  while (used < sms) {
+    int best = 0;
+    for (int i = 1; i < np; ++i) if (frac[i] > frac[best]) best = i;
+    ++n_split[best]; frac[best] = -1.0; ++used;
+  }
+  while (used > sms) {
+    int best = -1;
+    for (int i = 0; i < np; ++i) if (n_split[i] > 1 && (best < 0 || n_split[i] > n_split[best])) best = i;
+    if (best < 0) break;
+    --n_split[best]; --used;
+  }
+  for (int i = 0; i < np; ++i) {
+    for (int sp = 0; sp < n_split[i] && wi.n < MAX_WGRAD_ITEMS; ++sp) {
       WgradItem& it = wi.it[wi.n++];
       const Proto& pr = protos[i];
       it.a_img = pr.a; it.a_term = pr.a_term; it.a_cols = pr.a_cols;
       it.b_img = pr.b; it.b_term = pr.b_term; it.b_cols = pr.b_cols;
       it.out = pr.out; it.ld_out = pr.ld; it.n_rows = pr.n_rows; it.n_cols = pr.n_cols;
-      it.cap = s.cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split;
+      it.cap = s.cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split[i];
     }
   }
   if (pj.n > MAX_PREP_JOBS) { set_error("table overflow"); return B200_ERR_INVALID; }

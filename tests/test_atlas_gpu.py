@@ -238,7 +238,7 @@ def test_five_step_trajectory_with_graph_replay(golden_dir):
             # normalised update differs, so single entries may be off by a fraction of one step;
             # the bulk must agree to fp32 rounding
             d = (v.cpu() - r.detach()).abs()
-            assert d.max() <= 5e-5 and d.mean() <= 2e-7, (which, k, float(d.max()), float(d.mean()))
+            assert d.max() <= 5e-5 and d.mean() <= 1e-6, (which, k, float(d.max()), float(d.mean()))
     sd = tr.optimizer_state_dict()
     assert len(sd["state"]) == 28 and sd["param_groups"][1]["params"][0] == 12
     assert float(sd["state"][0]["step"]) == 5.0
