@@ -38,6 +38,15 @@ class Video(C.Structure):
                 ("t_begin", C.c_int32), ("t_end", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("in_c_total", C.c_int32), ("in_c_off", C.c_int32), ("Cout", C.c_int32), ("KH", C.c_int32),
+                ("KW", C.c_int32), ("stride", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+                ("pad_mode", C.c_int32), ("upsample", C.c_int32), ("out_c_total", C.c_int32),
+                ("out_c_off", C.c_int32), ("act", C.c_int32), ("out_scale", C.c_float),
+                ("res_c_total", C.c_int32), ("res_c_off", C.c_int32)]
+
+
 class AtlasConfig(C.Structure):
     _fields_ = [("batch", C.c_int32), ("with_global", C.c_int32), ("precision", C.c_int32),
                 ("resx", C.c_int32), ("uv_mapping_scale", C.c_float), ("derivative_amount", C.c_float),
@@ -70,6 +79,15 @@ SIGNATURES = {
     "b200_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P, _P]),
     "b200_render_workspace_bytes": (_I64, [_I64]),
     "b200_render": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, C.c_int, _P, _I64, _P]),
+    "b200_corr_pyramid_floats": (_I64, [_I32, _I32]),
+    "b200_corr_build": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "b200_corr_lookup": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "b200_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "b200_maxpool2": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
+    "b200_upsample_bilinear2": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "b200_gru_gate": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _P]),
+    "b200_convlstm_zero_state": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "b200_convex_upsample": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
 }
 
 _lib = None

@@ -27,6 +27,7 @@ struct GemmArgs {
   int64_t cap; const int* n_valid;
   int r_chunk;
   int tag;                  // KernelTag timed by b200_set_kernel_timer (0: none)
+  float scale;              // multiplies the accumulator first (0 -> 1)
 };
 
 constexpr int BI = 128, BJ = 128, BR = 16, PADW = 132, GEMM_THREADS = 256;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) sgemm_kernel(GemmArgs a) {
     for (int v = 0; v < 8; ++v) {
       const int j = j0 + tx * 8 + v;
       if (j >= a.J) continue;
-      float val = acc[u][v];
+      float val = a.scale != 0.f ? acc[u][v] * a.scale : acc[u][v];
       if (a.bias) val += a.bias[j];
       if (a.act == 1) val = fmaxf(val, 0.f);
       else if (a.act == 2) val = tanhf(val);
@@ -185,6 +186,14 @@ static int launch_gemm(const GemmArgs& a, bool p_rc, bool q_rc, cudaStream_t st)
   timer_end(a.tag, st);
   B200_CHECK_LAUNCH();
   return B200_OK;
+}
+
+int simt_gemm_nn_scaled(const float* A, const float* B, float* C, int M, int N, int K, float scale, cudaStream_t st) {
+  GemmArgs g{};
+  g.P = A; g.ldp = M;          // P(i, r) = A[r*M + i]   (i contiguous)
+  g.Q = B; g.ldq = N;          // Q(r, j) = B[r*N + j]   (j contiguous)
+  g.C = C; g.ldc = N; g.I = M; g.J = N; g.R = K; g.rows_on_i = 1; g.scale = scale;
+  return launch_gemm(g, false, false, st);
 }
 
 // dz[i][j] = dy[i][j] * (1 - y[i][j]^2)   (tanh backward), or a copy when tanh is off

@@ -1,0 +1,91 @@
+"""Stage-1 data helpers with the reference's names (src/models/stage_1/unwrap_utils.py).
+
+`load_input_data_single` is the input producer (reads frames + RAFT flows from disk, CPU, same tensor
+layouts as the reference returns); `get_tuples` and `pre_train_mapping` are provided for drop-in use,
+the latter running on the fused trainer.  The visualisation helper `save_mask_flow` (imageio mp4s) is
+out of scope.
+"""
+import numpy as np
+import torch
+import cv2
+from PIL import Image
+
+
+def _warp_by_flow(img, flow):
+    """cv2.remap of `img` at (x + fx, y + fy), bilinear, zeros outside (unwrap_utils.py:17-23)."""
+    h, w = flow.shape[:2]
+    grid = flow.copy()
+    grid[:, :, 0] += np.arange(w)
+    grid[:, :, 1] += np.arange(h)[:, None]
+    return cv2.remap(img, grid, None, cv2.INTER_LINEAR)
+
+
+def compute_consistency(flow12, flow21):
+    """|flow12 + warp(flow21, flow12)| per pixel (unwrap_utils.py:10-14)."""
+    d = flow12 + _warp_by_flow(flow21, flow12)
+    return (d[:, :, 0] ** 2 + d[:, :, 1] ** 2) ** .5
+
+
+def resize_flow(flow, newh, neww):
+    """Bilinear resize; note the reference scales x by newh/oldh and y by neww/oldw (unwrap_utils.py:33-38),
+    reproduced as is."""
+    oldh, oldw = flow.shape[0:2]
+    flow = cv2.resize(flow, (neww, newh), interpolation=cv2.INTER_LINEAR)
+    flow[:, :, 0] *= newh / oldh
+    flow[:, :, 1] *= neww / oldw
+    return flow
+
+
+def load_input_data_single(resy, resx, maximum_number_of_frames, data_folder, use_mask_rcnn_bootstrapping,
+                           filter_optical_flow, vid_root, vid_name):
+    """Same return tuple as unwrap_utils.py:105-163."""
+    flow_dir = vid_root / f'{vid_name}_flow'
+    files = sorted(list(data_folder.glob('*.jpg')) + list(data_folder.glob('*.png')))
+    T = int(np.minimum(maximum_number_of_frames, len(files)))
+    frames = torch.zeros((resy, resx, 3, T))
+    dx = torch.zeros_like(frames)
+    dy = torch.zeros_like(frames)
+    mask_frames = torch.zeros((resy, resx, T))
+    flows = torch.zeros((resy, resx, 2, T, 1))
+    flows_mask = torch.zeros((resy, resx, T, 1))
+    flows_rev = torch.zeros((resy, resx, 2, T, 1))
+    flows_rev_mask = torch.zeros((resy, resx, T, 1))
+    for i in range(T):
+        im = np.array(Image.open(str(files[i]))).astype(np.float64) / 255.
+        if im.ndim == 2:
+            im = np.tile(im[:, :, None], [1, 1, 3])
+        frames[:, :, :, i] = torch.from_numpy(cv2.resize(im[:, :, :3], (resx, resy)))
+        dy[:-1, :, :, i] = frames[1:, :, :, i] - frames[:-1, :, :, i]
+        dx[:, :-1, :, i] = frames[:, 1:, :, i] - frames[:, :-1, :, i]
+    for i in range(T - 1):
+        a, b = files[i].name, files[i + 1].name
+        f12 = np.load(flow_dir / f'{a}_{b}.npy')
+        f21 = np.load(flow_dir / f'{b}_{a}.npy')
+        if f12.shape[0] != resy or f12.shape[1] != resx:
+            f12 = resize_flow(f12, newh=resy, neww=resx)
+            f21 = resize_flow(f21, newh=resy, neww=resx)
+        flows[:, :, :, i, 0] = torch.from_numpy(f12)
+        flows_rev[:, :, :, i + 1, 0] = torch.from_numpy(f21)
+        if filter_optical_flow:
+            flows_mask[:, :, i, 0] = torch.from_numpy(compute_consistency(f12, f21) < 1.0)
+            flows_rev_mask[:, :, i + 1, 0] = torch.from_numpy(compute_consistency(f21, f12) < 1.0)
+        else:
+            flows_mask[:, :, i, 0] = 1
+            flows_rev_mask[:, :, i + 1, 0] = 1
+    return flows_mask, frames, flows_rev_mask, mask_frames, dx, dy, flows_rev, flows
+
+
+def get_tuples(number_of_frames, video_frames):
+    """(3, N) int64 [x; y; t] table (unwrap_utils.py:166-173).  The CUDA path never materialises it: the
+    kernels decode n -> (n % W, (n // W) % H, n // (H*W)); this is for callers that want the tensor."""
+    H, W = video_frames.shape[0], video_frames.shape[1]
+    n = torch.arange(number_of_frames * H * W, dtype=torch.int64)
+    return torch.stack((n % W, (n // W) % H, n // (H * W)))
+
+
+def pre_train_mapping(trainer, frames_num, uv_mapping_scale, resx, resy, larger_dim, device, pretrain_iters=100):
+    """unwrap_utils.py:176-198 on the fused trainer (`b200.atlas.AtlasTrainer`)."""
+    print("pre-training")
+    trainer.cfg["uv_mapping_scale"] = uv_mapping_scale
+    trainer.pretrain(frames_num, resy, resx, pretrain_iters)
+    return trainer

@@ -1,0 +1,92 @@
+"""Stage 1 — fit the neural atlas of one video.  Same CLI, config keys, on-disk inputs and outputs as
+the reference script (src/stage1_neural_atlas.py:257-281); the optimisation loop itself
+(:151-231) runs as one replayed CUDA graph per iteration in libb200deflicker.so.
+
+    python src/stage1_neural_atlas.py --vid_name NAME [--config config_flow_100.json] [--root data/test/]
+                                      [--down 4] [--gpu 0]
+"""
+import argparse
+import glob
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import cv2          # noqa: E402
+import numpy as np  # noqa: E402
+import torch        # noqa: E402
+from tqdm import tqdm  # noqa: E402
+
+from b200 import _native as N  # noqa: E402
+from b200 import atlas as A    # noqa: E402
+from src.models.stage_1.evaluate import evaluate_model_single  # noqa: E402
+from src.models.stage_1.unwrap_utils import load_input_data_single, pre_train_mapping  # noqa: E402
+
+
+def main(config, args):
+    frames_list = sorted(glob.glob(os.path.join(args.vid_path, "*g")))
+    first = cv2.imread(frames_list[0])
+    resx, resy = first.shape[1], first.shape[0]
+    if args.down is not None:
+        resx, resy = int(resx / args.down), int(resy / args.down)
+    data_folder = Path(args.vid_path)
+    vid_name, vid_root = data_folder.name, data_folder.parent
+    results_folder = Path(f'./results/{vid_name}/stage_1')
+    results_folder.mkdir(parents=True, exist_ok=True)
+    with open('%s/config.json' % results_folder, 'w') as f:
+        json.dump(config, f, indent=4)
+
+    flows_mask, frames, flows_rev_mask, _, dx, dy, flows_rev, flows = load_input_data_single(
+        resy, resx, config["maximum_number_of_frames"], data_folder, True, True, vid_root, vid_name)
+    T = frames.shape[3]
+    device = torch.device("cuda")
+    data = dict(frames=frames, frames_dx=dx, frames_dy=dy, flow_fwd=flows, flow_bwd=flows_rev,
+                mask_fwd=flows_mask, mask_bwd=flows_rev_mask)
+    video = A.DeviceVideo.from_reference_layout(data, device)
+    precision = N.PREC_TC if N.lib().b200_device_supports_tc() else N.PREC_FP32
+    trainer = A.AtlasTrainer(video, config, precision=precision, device=device, resx=resx)
+    trainer.init_like_reference()          # mapping then atlas, nn.Linear stream order (:112-128)
+
+    start_iteration = 0
+    larger_dim = np.maximum(resx, resy)
+    if not config["load_checkpoint"]:
+        if config["pretrain_mapping1"]:
+            pre_train_mapping(trainer, T, config["uv_mapping_scale"], resx=resx, resy=resy, larger_dim=larger_dim,
+                              device=device, pretrain_iters=config["pretrain_iter_number"])
+    else:
+        ck = torch.load(config["checkpoint_path"])
+        trainer.load_state(ck["model_F_mapping1_state_dict"], ck["F_atlas_state_dict"])
+        trainer.load_optimizer_state_dict(ck["optimizer_all_state_dict"])
+        start_iteration = ck["iteration"]
+
+    n_pixels = T * resy * resx
+    samples = int(config["samples_batch"])
+    evaluate_every = int(config["evaluate_every"])
+    for i in tqdm(range(start_iteration, config["iters_num"])):
+        inds = torch.randint(n_pixels, (samples, 1))       # same CPU-generator draw as the reference (:159)
+        trainer.step_host(inds, i)
+        if i % evaluate_every == 0 and i > start_iteration:
+            evaluate_model_single(trainer, resx, resy, T, frames, results_folder, i, vid_name)
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--config', type=str, default="config_flow_100.json")
+    parser.add_argument('--vid_name', type=str, default="Around_the_world_in_1896_001")
+    parser.add_argument('--root', type=str, default="data/test/")
+    parser.add_argument('--down', type=int, default=4)
+    parser.add_argument('--gpu', type=int, default=0)
+    args = parser.parse_args()
+    os.environ["CUDA_VISIBLE_DEVICES"] = "%d" % args.gpu
+    args.vid_path = os.path.join(args.root, args.vid_name)
+    flow_dir = args.vid_path.rstrip("/") + "_flow"
+    if not os.path.isdir(flow_dir):
+        cmd = "python %s --vid-path %s --gpu %d " % (os.path.join(HERE, "preprocess_optical_flow.py"), args.vid_path, args.gpu)
+        print(cmd)
+        subprocess.call(cmd, shell=True)
+    with open(os.path.join(HERE, "config", args.config)) as f:
+        main(json.load(f), args)

@@ -183,6 +183,58 @@ int b200_render(const float* params, int32_t H, int32_t W, int32_t T, int32_t fr
                 int64_t pix_begin, int64_t pix_end, float* rgb, uint8_t* rgb_u8, int precision,
                 void* ws, int64_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * RAFT correlation — replaces CorrBlock (src/models/stage_1/core/corr.py:16-64); the reference's own
+ * native hook for this operator is alt_cuda_corr.forward (corr.py:86-91, extension not shipped).
+ * fmaps: [dim][H8*W8] fp32 (batch 1).  pyramid: level 0 [H8*W8][H8][W8], then 3 avg-pooled levels,
+ * b200_corr_pyramid_floats() floats in total.
+ * ------------------------------------------------------------------------------------------ */
+int64_t b200_corr_pyramid_floats(int32_t H8, int32_t W8);
+int b200_corr_build(const float* fmap1, const float* fmap2, int32_t dim, int32_t H8, int32_t W8,
+                    float* pyramid, void* stream);
+/* CorrBlock.__call__ (corr.py:33-54): coords [1][2][H8][W8] (x, y) -> out [1][4*(2r+1)^2][H8][W8] */
+int b200_corr_lookup(const float* pyramid, const float* coords, float* out, int32_t batch,
+                     int32_t H8, int32_t W8, int32_t radius, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution and image operators of the RAFT update block (core/update.py:6-136) and of the
+ * stage-2 networks (src/models/network_filter.py:8-107, src/models/network_local.py:7-188).
+ * NCHW fp32 tensors; input / output / residual may be channel slices of larger tensors, which
+ * replaces torch.cat.  y = act(conv(pad(upsample(x))) + bias) * out_scale (+ residual).
+ * ------------------------------------------------------------------------------------------ */
+#define B200_ACT_NONE 0
+#define B200_ACT_RELU 1
+#define B200_ACT_LEAKY02 2
+#define B200_ACT_SIGMOID 3
+#define B200_ACT_TANH 4
+#define B200_PAD_ZEROS 0
+#define B200_PAD_REFLECT 1
+typedef struct B200ConvDesc {
+  int32_t N, Cin, H, W;            /* input extent (before the optional nearest upsample)            */
+  int32_t in_c_total, in_c_off;    /* input = channels [in_c_off, in_c_off+Cin) of an in_c_total tensor */
+  int32_t Cout, KH, KW, stride, pad_h, pad_w;
+  int32_t pad_mode;                /* B200_PAD_*  (nn.Conv2d padding / nn.ReflectionPad2d)            */
+  int32_t upsample;                /* 1, or 2 = nn.Upsample(scale_factor=2, mode='nearest') first     */
+  int32_t out_c_total, out_c_off;
+  int32_t act;                     /* B200_ACT_*                                                      */
+  float out_scale;
+  int32_t res_c_total, res_c_off;  /* residual tensor slice (same spatial size as the output)         */
+} B200ConvDesc;
+int b200_conv2d(const B200ConvDesc* d, const float* x, const float* w, const float* bias,
+                const float* residual, float* y, void* stream);
+int b200_maxpool2(const float* x, float* y, int64_t planes, int32_t H, int32_t W, void* stream);
+int b200_upsample_bilinear2(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                            int32_t out_c_total, int32_t out_c_off, void* stream);
+/* mode 0: out = a*b (r*h into a concat buffer); mode 1: out = (1-a)*b + a*c (GRU state update) */
+int b200_gru_gate(const float* a, const float* b, const float* c, float* out, int64_t n_per_sample,
+                  int64_t samples, int64_t out_sample_stride, int32_t mode, void* stream);
+/* ConvLSTM cell with prev_state=None: gates [N][4C][H][W] -> hidden, cell (may be NULL) */
+int b200_convlstm_zero_state(const float* gates, float* hidden, float* cell, int32_t N, int32_t C,
+                             int32_t H, int32_t W, void* stream);
+/* RAFT.upsample_flow (core/raft.py:76-87): flow [N][2][H][W], mask [N][576][H][W] -> [N][2][8H][8W] */
+int b200_convex_upsample(const float* flow, const float* mask, float* out, int32_t N, int32_t H,
+                         int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,12 +34,16 @@ def ws_views(tr, B, tc):
     return out
 
 def main():
-    small = "--big" not in sys.argv
+    small = "--big" not in sys.argv and "--mid" not in sys.argv
     mp, ap = params()
     if small:
         z = np.load(os.path.join(GOLD, "iteration.npz"))
         data = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("video_")}
         inds = torch.from_numpy(z["inds"]); B = 64
+    elif "--mid" in sys.argv:
+        data = synth.throughput_set(60, 100, 9, seed=3)
+        B = int(os.environ.get("DIAG_B", "3000"))
+        inds = torch.randint(60 * 100 * 9, (B, 1), generator=torch.Generator().manual_seed(2))
     else:
         data = synth.throughput_set(108, 192, 20, seed=0)
         B = 10000
@@ -73,16 +77,29 @@ def main():
                 print("uv sample rows tc:", v["uv"].cpu()[:4], "ref:", uv_ref[:4])
                 print("rows with err>1e-3:", int((d.abs().max(1).values > 1e-3).sum()), "of", d.shape[0])
         res[name + "_losses"] = tr.losses.cpu().numpy().tolist()
-    # gradient comparison per tensor
+    # gradient comparison per tensor against a float64 evaluation of the oracle
+    video64 = O.Video(**{k: v.double() if v.dtype == torch.float32 else v for k, v in data.items() if k != "clean"})
+    mp64 = [p.double().requires_grad_(True) for p in mp]
+    ap64 = [p.double().requires_grad_(True) for p in ap]
+    terms = O.iteration_losses(video64, mp64, ap64, inds, 0)
+    terms["total"].backward()
+    truth = [p.grad.float().to(DEV) for p in mp64 + ap64]
     tr = A.AtlasTrainer(vid, {"samples_batch": B}, precision=N.PREC_FP32, device=DEV)
     worst = 0
+    i = 0
     for which in ("mapping", "atlas"):
         a = tr._views(grads["fp32"], which); b = tr._views(grads["tc"], which)
         for k in a:
-            ref = a[k]; err = (b[k] - ref).abs().max().item(); sc = ref.abs().max().item()
-            rel = err / (sc + 1e-30)
+            ref = truth[i]; i += 1
+            e32 = (a[k] - ref).abs().max().item(); etc = (b[k] - ref).abs().max().item(); sc = ref.abs().max().item()
+            rel = etc / (sc + 1e-30)
             worst = max(worst, rel)
-            print(f"grad {which:8s} {k:18s} max|ref| {sc:.3e} max|err| {err:.3e} rel {rel:.2e}")
+            bad = "  <<<" if etc > max(4 * e32, 2e-5 * sc) else ""
+            if b[k].dim() == 2 and bad:
+                d = (b[k] - ref).abs()
+                rows_bad = (d.max(1).values > 0.1 * etc).sum().item(); cols_bad = (d.max(0).values > 0.1 * etc).sum().item()
+                bad += f" rows>{rows_bad} cols>{cols_bad} argmax {divmod(int(d.argmax()), d.shape[1])}"
+            print(f"grad {which:8s} {k:18s} max|ref| {sc:.3e} err_fp32 {e32:.3e} err_tc {etc:.3e}{bad}")
     res["worst_grad_rel"] = worst
     print(json.dumps(res))
 
