@@ -1,0 +1,109 @@
+"""Thin torch-tensor wrappers over the convolution / RAFT entry points of libb200deflicker.so
+(include/b200_deflicker.h).  CUDA tensors only; every call runs on the current stream."""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3, "tanh": 4}
+
+
+def _check(t):
+    if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+        raise N.B200Error("expected a contiguous fp32 CUDA tensor (no CPU fallback)")
+    return t
+
+
+def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", upsample=1, out=None, out_c_off=0,
+           in_slice=None, residual=None, res_c_off=0, out_scale=1.0):
+    """y = act(conv(pad(upsample(x[:, in_slice]))) + b) * out_scale (+ residual[:, res slice]) written into
+    out[:, out_c_off:out_c_off+Cout] (allocated when None).  Restates nn.Conv2d / ReflectionPad2d / Upsample."""
+    _check(x); _check(w); _check(b); _check(residual)
+    n, c_total, h, wd = x.shape
+    c_off, cin = (0, c_total) if in_slice is None else (in_slice[0], in_slice[1] - in_slice[0])
+    cout, cin_w, kh, kw = w.shape
+    if cin_w != cin:
+        raise N.B200Error(f"weight expects {cin_w} input channels, got {cin}")
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    hu, wu = h * upsample, wd * upsample
+    oh, ow = (hu + 2 * ph - kh) // stride + 1, (wu + 2 * pw - kw) // stride + 1
+    if out is None:
+        out = torch.empty(n, cout, oh, ow, dtype=torch.float32, device=x.device)
+    _check(out)
+    d = N.ConvDesc(n, cin, h, wd, c_total, c_off, cout, kh, kw, stride, ph, pw, 1 if pad_mode == "reflect" else 0,
+                   upsample, out.shape[1], out_c_off, ACT[act], float(out_scale),
+                   residual.shape[1] if residual is not None else 0, res_c_off)
+    N.check(N.lib().b200_conv2d(C.byref(d), N.ptr(x), N.ptr(w), N.ptr(b), N.ptr(residual), N.ptr(out),
+                                N.current_stream()), "b200_conv2d")
+    return out
+
+
+def maxpool2(x):
+    _check(x)
+    n, c, h, w = x.shape
+    y = torch.empty(n, c, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    N.check(N.lib().b200_maxpool2(N.ptr(x), N.ptr(y), n * c, h, w, N.current_stream()), "b200_maxpool2")
+    return y
+
+
+def upsample_bilinear2(x, out=None, out_c_off=0):
+    _check(x)
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty(n, c, 2 * h, 2 * w, dtype=torch.float32, device=x.device)
+    N.check(N.lib().b200_upsample_bilinear2(N.ptr(x), N.ptr(out), n, c, h, w, out.shape[1], out_c_off,
+                                            N.current_stream()), "b200_upsample_bilinear2")
+    return out
+
+
+def gru_gate(a, b, c=None, out=None, mode=0):
+    """mode 0: out[:, :C] = a*b ; mode 1: (1-a)*b + a*c."""
+    _check(a); _check(b); _check(c)
+    n = a.shape[0]
+    per = a.numel() // n
+    if out is None:
+        out = torch.empty_like(a)
+    N.check(N.lib().b200_gru_gate(N.ptr(a), N.ptr(b), N.ptr(c), N.ptr(out), per, n, out.numel() // n, mode,
+                                  N.current_stream()), "b200_gru_gate")
+    return out
+
+
+def convlstm_zero_state(gates, want_cell=True):
+    _check(gates)
+    n, c4, h, w = gates.shape
+    hidden = torch.empty(n, c4 // 4, h, w, dtype=torch.float32, device=gates.device)
+    cell = torch.empty_like(hidden) if want_cell else None
+    N.check(N.lib().b200_convlstm_zero_state(N.ptr(gates), N.ptr(hidden), N.ptr(cell), n, c4 // 4, h, w,
+                                             N.current_stream()), "b200_convlstm_zero_state")
+    return hidden, cell
+
+
+def convex_upsample(flow, mask):
+    _check(flow); _check(mask)
+    n, _, h, w = flow.shape
+    out = torch.empty(n, 2, 8 * h, 8 * w, dtype=torch.float32, device=flow.device)
+    N.check(N.lib().b200_convex_upsample(N.ptr(flow), N.ptr(mask), N.ptr(out), n, h, w, N.current_stream()),
+            "b200_convex_upsample")
+    return out
+
+
+def corr_build(fmap1, fmap2):
+    """fmaps (1, C, H8, W8) -> flat pyramid tensor (level 0 [HW][H8][W8] then 3 pooled levels)."""
+    _check(fmap1); _check(fmap2)
+    b, c, h, w = fmap1.shape
+    if b != 1:
+        raise N.B200Error("correlation kernels take batch 1 (the reference runs one frame pair at a time)")
+    pyr = torch.empty(int(N.lib().b200_corr_pyramid_floats(h, w)), dtype=torch.float32, device=fmap1.device)
+    N.check(N.lib().b200_corr_build(N.ptr(fmap1), N.ptr(fmap2), c, h, w, N.ptr(pyr), N.current_stream()),
+            "b200_corr_build")
+    return pyr
+
+
+def corr_lookup(pyr, coords, radius=4):
+    _check(pyr); _check(coords)
+    b, _, h, w = coords.shape
+    out = torch.empty(b, 4 * (2 * radius + 1) ** 2, h, w, dtype=torch.float32, device=coords.device)
+    N.check(N.lib().b200_corr_lookup(N.ptr(pyr), N.ptr(coords), N.ptr(out), b, h, w, radius, N.current_stream()),
+            "b200_corr_lookup")
+    return out

@@ -1,0 +1,60 @@
+"""`UNet` neural filter with the reference's constructor and state_dict keys
+(src/models/network_filter.py:8-107); inference runs in b200_conv2d / b200_maxpool2 /
+b200_upsample_bilinear2, skip concatenations are written in place (no torch.cat)."""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from b200 import nn as K
+
+
+class UNet(nn.Module):
+    def __init__(self, in_channels=3, out_channels=1, init_features=32):
+        super().__init__()
+        f = init_features
+        self.encoder1 = UNet._block(in_channels, f, "enc1")
+        self.encoder2 = UNet._block(f, f * 2, "enc2")
+        self.encoder3 = UNet._block(f * 2, f * 4, "enc3")
+        self.encoder4 = UNet._block(f * 4, f * 8, "enc4")
+        self.bottleneck = UNet._block(f * 8, f * 16, "bottleneck")
+        for i, (cin, cout) in zip((4, 3, 2, 1), ((f * 16, f * 8), (f * 8, f * 4), (f * 4, f * 2), (f * 2, f))):
+            setattr(self, f"upconv{i}", nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                                                      nn.Conv2d(cin, cout, kernel_size=3, padding=1)))
+            setattr(self, f"decoder{i}", UNet._block(cout * 2, cout, f"dec{i}"))
+        self.conv = nn.Conv2d(f, out_channels, kernel_size=1)
+
+    @staticmethod
+    def _block(cin, feat, name):
+        return nn.Sequential(OrderedDict([(name + "conv1", nn.Conv2d(cin, feat, 3, padding=1, bias=False)),
+                                          (name + "relu1", nn.ReLU(inplace=True)),
+                                          (name + "conv2", nn.Conv2d(feat, feat, 3, padding=1, bias=False)),
+                                          (name + "relu2", nn.ReLU(inplace=True))]))
+
+    @staticmethod
+    def _run_block(block, x, out=None, out_c_off=0):
+        convs = [m for m in block if isinstance(m, nn.Conv2d)]
+        t = K.conv2d(x, convs[0].weight.detach(), None, pad=1, act="relu")
+        return K.conv2d(t, convs[1].weight.detach(), None, pad=1, act="relu", out=out, out_c_off=out_c_off)
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = x.float().contiguous()
+        n, _, h, w = x.shape
+        dev = x.device
+        cur = x
+        cats = []
+        for i, enc in enumerate((self.encoder1, self.encoder2, self.encoder3, self.encoder4)):
+            c = enc[0].out_channels
+            hh, ww = h >> i, w >> i
+            cat = torch.empty(n, 2 * c, hh, ww, dtype=torch.float32, device=dev)   # [upconv | encoder] (dim=1 cat)
+            UNet._run_block(enc, cur, out=cat, out_c_off=c)
+            cats.append(cat)
+            cur = K.maxpool2(cat.narrow(1, c, c).contiguous())     # pool the encoder half of the concat buffer
+        cur = UNet._run_block(self.bottleneck, cur)
+        for i, cat in zip((4, 3, 2, 1), reversed(cats)):
+            up = getattr(self, f"upconv{i}")[1]
+            big = K.upsample_bilinear2(cur)
+            K.conv2d(big, up.weight.detach(), up.bias.detach(), pad=1, out=cat, out_c_off=0)
+            cur = UNet._run_block(getattr(self, f"decoder{i}"), cat)
+        return K.conv2d(cur, self.conv.weight.detach(), self.conv.bias.detach())

@@ -1,0 +1,104 @@
+"""`TransformNet` local refinement (Lai et al.) with the reference's constructor and state_dict keys
+(src/models/network_local.py:7-188).  Reflection padding, nearest upsampling, LeakyReLU, the residual
+adds and the ConvLSTM cell are fused into b200_conv2d / b200_convlstm_zero_state.  As in the reference
+the norm layers are constructed (their buffers are part of the state_dict) but never applied
+(`self.norm in ["BN" or "IN"]`, network_local.py:136,169)."""
+import torch
+import torch.nn as nn
+
+from b200 import nn as K
+
+
+class ConvLayer(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, norm=None, bias=True):
+        super().__init__()
+        self.reflection_pad = nn.ReflectionPad2d(kernel_size // 2)
+        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, bias=bias)
+        self.norm = norm
+        if norm == "BN":
+            self.norm_layer = nn.BatchNorm2d(out_channels)
+        elif norm == "IN":
+            self.norm_layer = nn.InstanceNorm2d(out_channels, track_running_stats=True)
+        self.upsample = None
+
+    def run(self, x, act="none", **kw):
+        if self.norm == "BN":
+            raise NotImplementedError("norm='BN' (the only value for which the reference applies a norm) is unused")
+        c = self.conv2d
+        return K.conv2d(x, c.weight.detach(), c.bias.detach() if c.bias is not None else None, stride=c.stride[0],
+                        pad=c.kernel_size[0] // 2, pad_mode="reflect", act=act, upsample=self.upsample or 1, **kw)
+
+
+class UpsampleConvLayer(ConvLayer):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, upsample=None, norm=None, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride, norm=norm, bias=bias)
+        self.upsample = upsample
+        if upsample:
+            self.upsample_layer = nn.Upsample(scale_factor=upsample, mode='nearest')
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, channels, norm=None, bias=True):
+        super().__init__()
+        self.conv1 = ConvLayer(channels, channels, kernel_size=3, stride=1, bias=bias, norm=norm)
+        self.conv2 = ConvLayer(channels, channels, kernel_size=3, stride=1, bias=bias, norm=norm)
+
+    def run(self, x):
+        return self.conv2.run(self.conv1.run(x, "leaky"), residual=x)
+
+
+class ConvLSTM(nn.Module):
+    def __init__(self, input_size, hidden_size, kernel_size):
+        super().__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.Gates = nn.Conv2d(input_size + hidden_size, 4 * hidden_size, kernel_size, padding=kernel_size // 2)
+
+    def run(self, x, prev_state=None):
+        if prev_state is not None:
+            raise NotImplementedError("the stage-2 script always passes prev_state=None "
+                                      "(src/neural_filter_and_refinement.py:106)")
+        # zero previous hidden state: only the input half of the gate weights contributes
+        w = self.Gates.weight.detach()[:, :self.input_size].contiguous()
+        gates = K.conv2d(x, w, self.Gates.bias.detach(), pad=self.Gates.padding)
+        return K.convlstm_zero_state(gates)
+
+
+class TransformNet(nn.Module):
+    def __init__(self, opts, nc_in, nc_out):
+        super().__init__()
+        self.blocks, self.epoch = opts.blocks, 0
+        nf, norm = opts.nf, opts.norm
+        use_bias = (norm == "IN")
+        self.conv1a = ConvLayer(3 + 3, nf, kernel_size=7, stride=1, bias=use_bias, norm=norm)
+        self.conv1b = ConvLayer(3 + 3, nf, kernel_size=7, stride=1, bias=use_bias, norm=norm)
+        self.conv2a = ConvLayer(nf, nf * 2, kernel_size=3, stride=2, bias=use_bias, norm=norm)
+        self.conv2b = ConvLayer(nf, nf * 2, kernel_size=3, stride=2, bias=use_bias, norm=norm)
+        self.conv3 = ConvLayer(nf * 4, nf * 4, kernel_size=3, stride=2, bias=use_bias, norm=norm)
+        self.ResBlocks = nn.ModuleList(ResidualBlock(nf * 4, bias=use_bias, norm=norm) for _ in range(self.blocks))
+        self.convlstm = ConvLSTM(input_size=nf * 4, hidden_size=nf * 4, kernel_size=3)
+        self.deconv1 = UpsampleConvLayer(nf * 4, nf * 2, kernel_size=3, stride=1, upsample=2, bias=use_bias, norm=norm)
+        self.deconv2 = UpsampleConvLayer(nf * 4, nf, kernel_size=3, stride=1, upsample=2, bias=use_bias, norm=norm)
+        self.deconv3 = ConvLayer(nf * 2, nc_out, kernel_size=7, stride=1)
+        self.nf = nf
+
+    @torch.no_grad()
+    def forward(self, X, prev_state):
+        X = X.float().contiguous()
+        n, _, h, w = X.shape
+        nf, dev = self.nf, X.device
+        c1 = torch.empty(n, 2 * nf, h, w, dtype=torch.float32, device=dev)          # [D1 | E1a]
+        c2 = torch.empty(n, 4 * nf, h // 2, w // 2, dtype=torch.float32, device=dev)  # [D2 | E2a]
+        e2 = torch.empty(n, 4 * nf, h // 2, w // 2, dtype=torch.float32, device=dev)  # [E2a | E2b]
+        self.conv1a.run(X, "leaky", in_slice=(0, 6), out=c1, out_c_off=nf)
+        e1b = self.conv1b.run(X, "leaky", in_slice=(6, 12))
+        self.conv2a.run(c1, "leaky", in_slice=(nf, 2 * nf), out=e2, out_c_off=0)
+        self.conv2b.run(e1b, "leaky", out=e2, out_c_off=2 * nf)
+        c2[:, 2 * nf:] = e2[:, :2 * nf]
+        rb = self.conv3.run(e2, "leaky")
+        for blk in self.ResBlocks:
+            rb = blk.run(rb)
+        hidden, cell = self.convlstm.run(rb, prev_state)
+        self.deconv1.run(hidden, "leaky", out=c2, out_c_off=0)
+        self.deconv2.run(c2, "leaky", out=c1, out_c_off=0)
+        y = self.deconv3.run(c1, "tanh")
+        return y, (hidden, cell)

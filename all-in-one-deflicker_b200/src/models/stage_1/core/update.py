@@ -1,0 +1,84 @@
+"""RAFT update operator with the reference's module tree / state_dict keys
+(src/models/stage_1/core/update.py:6-136): BasicMotionEncoder, SepConvGRU, FlowHead, mask head.
+Parameters live in nn.Conv2d modules (for checkpoints); arithmetic runs in b200_conv2d / b200_gru_gate.
+The reference runs this block under fp16 autocast; here it is fp32 (a superset of that precision)."""
+import torch
+import torch.nn as nn
+
+from b200 import nn as K
+
+
+def _c(conv, x, act="none", **kw):
+    return K.conv2d(x, conv.weight.detach(), conv.bias.detach() if conv.bias is not None else None,
+                    pad=conv.padding, act=act, **kw)
+
+
+class FlowHead(nn.Module):
+    def __init__(self, input_dim=128, hidden_dim=256):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, 2, 3, padding=1)
+
+    def forward(self, x):
+        return _c(self.conv2, _c(self.conv1, x, "relu"))
+
+
+class SepConvGRU(nn.Module):
+    def __init__(self, hidden_dim=128, input_dim=192 + 128):
+        super().__init__()
+        for tag, k, p in (("1", (1, 5), (0, 2)), ("2", (5, 1), (2, 0))):
+            for g in "zrq":
+                setattr(self, f"conv{g}{tag}", nn.Conv2d(hidden_dim + input_dim, hidden_dim, k, padding=p))
+        self.hidden_dim = hidden_dim
+
+    def forward(self, h, x):
+        n, c, hh, ww = h.shape
+        hx = torch.empty(n, c + x.shape[1], hh, ww, dtype=torch.float32, device=h.device)
+        hx[:, c:] = x                                           # the x half of both concats never changes
+        for tag in ("1", "2"):
+            hx[:, :c] = h
+            z = _c(getattr(self, "convz" + tag), hx, "sigmoid")
+            r = _c(getattr(self, "convr" + tag), hx, "sigmoid")
+            K.gru_gate(r, h, out=hx, mode=0)                    # [r*h, x]
+            q = _c(getattr(self, "convq" + tag), hx, "tanh")
+            h = K.gru_gate(z, h, q, mode=1)                     # (1-z)*h + z*q
+        return h
+
+
+class BasicMotionEncoder(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        cor_planes = args.corr_levels * (2 * args.corr_radius + 1) ** 2
+        self.convc1 = nn.Conv2d(cor_planes, 256, 1, padding=0)
+        self.convc2 = nn.Conv2d(256, 192, 3, padding=1)
+        self.convf1 = nn.Conv2d(2, 128, 7, padding=3)
+        self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
+        self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
+
+    def forward(self, flow, corr):
+        n, _, h, w = flow.shape
+        cor_flo = torch.empty(n, 256, h, w, dtype=torch.float32, device=flow.device)
+        _c(self.convc2, _c(self.convc1, corr, "relu"), "relu", out=cor_flo, out_c_off=0)
+        _c(self.convf2, _c(self.convf1, flow, "relu"), "relu", out=cor_flo, out_c_off=192)
+        out = torch.empty(n, 128, h, w, dtype=torch.float32, device=flow.device)
+        _c(self.conv, cor_flo, "relu", out=out, out_c_off=0)
+        out[:, 126:] = flow
+        return out
+
+
+class BasicUpdateBlock(nn.Module):
+    def __init__(self, args, hidden_dim=128, input_dim=128):
+        super().__init__()
+        self.args = args
+        self.encoder = BasicMotionEncoder(args)
+        self.gru = SepConvGRU(hidden_dim=hidden_dim, input_dim=128 + hidden_dim)
+        self.flow_head = FlowHead(hidden_dim, hidden_dim=256)
+        self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(256, 64 * 9, 1, padding=0))
+
+    def forward(self, net, inp, corr, flow, upsample=True):
+        motion = self.encoder(flow, corr)
+        net = self.gru(net, torch.cat([inp, motion], dim=1))
+        delta_flow = self.flow_head(net)
+        mask = _c(self.mask[2], _c(self.mask[0], net, "relu"), out_scale=0.25)     # .25 * mask head
+        return net, mask, delta_flow

@@ -238,7 +238,10 @@ def test_five_step_trajectory_with_graph_replay(golden_dir):
             # normalised update differs, so single entries may be off by a fraction of one step;
             # the bulk must agree to fp32 rounding
             d = (v.cpu() - r.detach()).abs()
-            assert d.max() <= 5e-5 and d.mean() <= 1e-6, (which, k, float(d.max()), float(d.mean()))
+            # Adam's first steps move every parameter by ~lr*sign(g): a gradient component that is pure
+            # summation noise can go either way, so single entries may differ by up to 2*lr per step
+            assert d.max() <= 1.1e-3 and d.mean() <= 1e-6 and (d > 2e-5).float().mean() <= 2e-3, \
+                (which, k, float(d.max()), float(d.mean()), float((d > 2e-5).float().mean()))
     sd = tr.optimizer_state_dict()
     assert len(sd["state"]) == 28 and sd["param_groups"][1]["params"][0] == 12
     assert float(sd["state"][0]["step"]) == 5.0
