@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const int64_t* _
     if ((loc_ballot[k] >> lane) & 1u)
       list[s_cnt[k * 32 + wid] + __popc(loc_ballot[k] & ((1u << lane) - 1u))] = k * SELECT_THREADS + tid;
   }
-  if (tid == 0) { counters[0] = s_tot[0]; counters[1] = s_tot[1]; counters[2] = s_tot[2]; counters[3] = 0; }
+  if (tid == 0) { counters[0] = s_tot[0]; counters[1] = s_tot[1]; counters[2] = s_tot[2]; counters[3] = 0; counters[4] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,7 +219,7 @@ __global__ void pretrain_sample_kernel(const int64_t* __restrict__ ys, const int
                                        int cap, float half_larger, float t_norm, float4* __restrict__ x_map,
                                        int* __restrict__ counters) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) { counters[0] = B; counters[3] = 0; }
+  if (s == 0) { counters[0] = B; counters[3] = 0; counters[4] = 0; }
   if (s >= cap) return;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s < B) r = make_float4(norm_coord((float)xs[s], half_larger), norm_coord((float)ys[s], half_larger), t_norm, 0.f);

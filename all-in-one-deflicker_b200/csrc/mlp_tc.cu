@@ -596,7 +596,7 @@ struct BwdParams {
   int64_t w_off[B200_MAX_LAYERS], b_off[B200_MAX_LAYERS];
   NetImages img;
   int cap, n_groups; const int* n_valid;
-  const int* gmax_bits;      // max |dL/dy| of this iteration as float bits
+  int* gmax_bits;            // [0] max |dL/dy| from the loss head, [1] max |dL/duv| after the atlas backward
 };
 
 // column sums over the 32 rows of a warp: lane j ends with sum_rows v[j]
@@ -634,8 +634,11 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
-__device__ __forceinline__ void grad_scales(const int* gmax_bits, float& s_g, float& inv_sg) {
-  const float mx = __int_as_float(*gmax_bits);
+// gmax_bits[0]: max |dL/dy| seen by the loss head; gmax_bits[1]: max |dL/duv| after the atlas backward added
+// its share (the positional encoding multiplies gradients by up to 2^9*pi).  use_second: mapping network.
+__device__ __forceinline__ void grad_scales(const int* gmax_bits, bool use_second, float& s_g, float& inv_sg) {
+  float mx = __int_as_float(gmax_bits[0]);
+  if (use_second) mx = fmaxf(mx, __int_as_float(gmax_bits[1]));
   int e = 0;
   if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);        // mx < 2^e
   e = max(-60, min(60, e));
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
   constexpr uint32_t IDESC64 = make_idesc(128, 64, 0, 0);
   float s_g, inv_sg;
-  grad_scales(P.gmax_bits, s_g, inv_sg);
+  grad_scales(P.gmax_bits, !ATLAS, s_g, inv_sg);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -874,6 +877,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
           cur.x += 0.5f * din[0];
           cur.y += 0.5f * din[1];
           *dst = cur;
+          float mx = fmaxf(fabsf(cur.x), fabsf(cur.y));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (lane == 0 && mx > 0.f) atomicMax(P.gmax_bits + 1, __float_as_int(mx));
         }
         tc_fence_before();
         mbar_arrive(&sm.misc[1]);                         // aux tile may be overwritten
@@ -912,6 +919,7 @@ struct WgradItem {
   int n_rows, n_cols;     // real rows / columns to write
   int cap, n_groups;      // row geometry of the network this item belongs to
   int split, n_split;     // this CTA's share of the live tiles
+  int mapping;            // 1: gradients of the mapping network (second gradient scale)
 };
 constexpr int MAX_WGRAD_ITEMS = 320;
 struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; };
@@ -1001,7 +1009,7 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
     }
   } else if (n_steps > 0) {
     float s_g, inv_sg;
-    grad_scales(gmax_bits, s_g, inv_sg);
+    grad_scales(gmax_bits, W.mapping != 0, s_g, inv_sg);
     const float inv = inv_sg * (1.0f / S_ACT);
     const int q = warp & 3;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
@@ -1139,14 +1147,14 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
   // ---- wgrad items.  The kernel is HBM-bound: balance CTAs by bytes read per tile
   //      (A + B, both terms): 256x256 -> 256 KB, 256x64 -> 160 KB, 64x256 -> 160 KB, 64x64 -> 64 KB
   struct Proto { const char* a; int64_t a_term; int a_cols; const char* b; int64_t b_term; int b_cols;
-                 float* out; int ld; int n_rows, n_cols, groups; double bytes; };
+                 float* out; int ld; int n_rows, n_cols, groups; double bytes; int mapping; };
   Proto protos[32]; int np = 0;
   float* gm = s.grads;
   float* ga = s.grads + s.ms->total;
   auto add_proto = [&](const char* a, int64_t a_term, int a_cols, const char* b, int64_t b_term,
                        int b_cols, float* out, int ld, int n_rows, int n_cols, int groups) {
     protos[np++] = Proto{a, a_term, a_cols, b, b_term, b_cols, out, ld, n_rows, n_cols, groups,
-                         (double)groups * (a_cols + b_cols) * 512.0};
+                         (double)groups * (a_cols + b_cols) * 512.0, out < ga ? 1 : 0};
   };
   {
     const NetImages& im = lay.map; const MlpShape& sh = *s.ms;
@@ -1201,7 +1209,7 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
       it.a_img = pr.a; it.a_term = pr.a_term; it.a_cols = pr.a_cols;
       it.b_img = pr.b; it.b_term = pr.b_term; it.b_cols = pr.b_cols;
       it.out = pr.out; it.ld_out = pr.ld; it.n_rows = pr.n_rows; it.n_cols = pr.n_cols;
-      it.cap = s.cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split[i];
+      it.cap = s.cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split[i]; it.mapping = pr.mapping;
     }
   }
   if (pj.n > MAX_PREP_JOBS) { set_error("table overflow"); return B200_ERR_INVALID; }
@@ -1252,7 +1260,7 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   const TcLayout lay = layout_of(s);
   HostTables* tab = find_tables(s);
   if (!tab) { set_error("tensor-core backward called before forward"); return B200_ERR_INVALID; }
-  const int* gmax = s.counters + 3;
+  int* gmax = const_cast<int*>(s.counters) + 3;
   auto fill = [&](BwdParams& P, const MlpShape& sh, const NetImages& im, const float* dy, const float* y,
                   const float* x, float* d_in, const float* params, float* grads, int groups) {
     P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = im;

@@ -102,7 +102,7 @@ def test_tc_forward_and_gradients(golden_dir, B, shape):
             qtc = torch.quantile(etc[:: max(1, etc.numel() // 100000)], 0.9).item()
             if qtc > max(10 * q32, 1e-5 * ref.abs().max().item()) + 1e-9:
                 problems.append((which, k, "q90", qtc, q32, ref.abs().max().item()))
-            if etc.norm().item() > 3e-3 * ref.norm().item() + 1e-9:
+            if etc.norm().item() > max(3e-3 * ref.norm().item(), 3 * e32.norm().item()) + 1e-9:
                 problems.append((which, k, "frobenius", etc.norm().item(), e32.norm().item(), ref.norm().item()))
     assert not problems, problems
 
@@ -130,7 +130,7 @@ def test_tc_trajectory_and_pretrain(golden_dir):
             d = (v.cpu() - r.detach()).abs()
             # Adam's first steps move every parameter by ~lr*sign(g): a gradient component that is pure
             # summation noise can go either way, so single entries may differ by up to 2*lr per step
-            assert d.max() <= 1.1e-3 and d.mean() <= 1e-6 and (d > 2e-5).float().mean() <= 2e-3, \
+            assert d.max() <= 1.1e-3 and d.mean() <= 5e-6 and (d > 2e-5).float().mean() <= 2e-3, \
                 (which, k, float(d.max()), float(d.mean()), float((d > 2e-5).float().mean()))
     # pre-training on the tensor-core path
     tr2 = A.AtlasTrainer(vid, {"samples_batch": 10000}, precision=N.PREC_TC, device=DEV)
