@@ -85,6 +85,8 @@ SIGNATURES = {
     "b200_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "b200_maxpool2": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
     "b200_upsample_bilinear2": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "b200_instance_norm": (C.c_int, [_P, _P, _I64, _I64, _F, _I32, _P]),
+    "b200_add_relu": (C.c_int, [_P, _P, _P, _I64, _P]),
     "b200_gru_gate": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _P]),
     "b200_convlstm_zero_state": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "b200_convex_upsample": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),

@@ -107,3 +107,19 @@ def corr_lookup(pyr, coords, radius=4):
     N.check(N.lib().b200_corr_lookup(N.ptr(pyr), N.ptr(coords), N.ptr(out), b, h, w, radius, N.current_stream()),
             "b200_corr_lookup")
     return out
+
+
+def instance_norm(x, eps=1e-5, relu=False):
+    _check(x)
+    n, c, h, w = x.shape
+    y = torch.empty_like(x)
+    N.check(N.lib().b200_instance_norm(N.ptr(x), N.ptr(y), n * c, h * w, eps, 1 if relu else 0, N.current_stream()),
+            "b200_instance_norm")
+    return y
+
+
+def add_relu(a, b):
+    _check(a); _check(b)
+    out = torch.empty_like(a)
+    N.check(N.lib().b200_add_relu(N.ptr(a), N.ptr(b), N.ptr(out), a.numel(), N.current_stream()), "b200_add_relu")
+    return out

@@ -239,11 +239,59 @@ __global__ void convex_upsample_kernel(const float* __restrict__ flow, const flo
   }
 }
 
+// nn.InstanceNorm2d (affine=False, eps) over each (n, c) plane, optional ReLU; one block per plane.
+// Two passes (mean, then centred variance) like ATen's batch_norm statistics.
+__global__ void instance_norm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t hw, float eps, int relu) {
+  const float* s = x + (int64_t)blockIdx.x * hw;
+  float* d = y + (int64_t)blockIdx.x * hw;
+  __shared__ float red[32];
+  __shared__ float stat[2];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) acc += s[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; stat[0] = t / (float)hw; }
+  __syncthreads();
+  const float mean = stat[0];
+  acc = 0.f;
+  for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) { const float c = s[i] - mean; acc += c * c; }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; stat[1] = rsqrtf(t / (float)hw + eps); }
+  __syncthreads();
+  const float inv = stat[1];
+  for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) {
+    const float v = (s[i] - mean) * inv;
+    d[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+__global__ void add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaxf(a[i] + b[i], 0.f);
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" {
+
+int b200_instance_norm(const float* x, float* y, int64_t planes, int64_t hw, float eps, int32_t relu, void* stream) {
+  B200_REQUIRE(x && y && planes > 0 && hw > 0, "bad arguments");
+  instance_norm_kernel<<<(unsigned)planes, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, hw, eps, relu);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int b200_add_relu(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  B200_REQUIRE(a && b && out && n > 0, "bad arguments");
+  add_relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, out, n);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
 
 int b200_conv2d(const B200ConvDesc* d, const float* x, const float* w, const float* bias, const float* residual,
                 float* y, void* stream) {

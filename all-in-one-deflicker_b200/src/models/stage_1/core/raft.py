@@ -1,0 +1,59 @@
+"""`RAFT` (basic variant, the only one the reference's wrapper builds: raft_wrapper.py:17-20) with the
+reference's module tree / state_dict keys and forward signature (src/models/stage_1/core/raft.py:28-148).
+Inference only (the reference never trains it).  fp32 throughout — the reference autocasts the encoders
+and the update block to fp16, correlation is fp32 in both."""
+import torch
+import torch.nn as nn
+
+from b200 import nn as K
+from src.models.stage_1.core.corr import CorrBlock
+from src.models.stage_1.core.extractor import BasicEncoder
+from src.models.stage_1.core.update import BasicUpdateBlock
+from src.models.stage_1.core.utils.utils import coords_grid
+
+
+class RAFT(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        if getattr(args, "small", False):
+            raise NotImplementedError("RAFT-small is unreachable with the reference's arguments")
+        self.hidden_dim = hdim = 128
+        self.context_dim = cdim = 128
+        args.corr_levels, args.corr_radius = 4, 4
+        if not hasattr(args, "dropout"):
+            args.dropout = 0
+        if not hasattr(args, "alternate_corr"):
+            args.alternate_corr = False
+        self.fnet = BasicEncoder(output_dim=256, norm_fn='instance', dropout=args.dropout)
+        self.cnet = BasicEncoder(output_dim=hdim + cdim, norm_fn='batch', dropout=args.dropout)
+        self.update_block = BasicUpdateBlock(self.args, hidden_dim=hdim)
+
+    def initialize_flow(self, img):
+        n, _, h, w = img.shape
+        c = coords_grid(n, h // 8, w // 8).to(img.device)
+        return c, c.clone()
+
+    @torch.no_grad()
+    def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        fmap1, fmap2 = self.fnet([image1, image2])
+        corr_fn = CorrBlock(fmap1.float(), fmap2.float(), radius=self.args.corr_radius)
+        cnet = self.cnet(image1)
+        net, inp = torch.split(cnet, [self.hidden_dim, self.context_dim], dim=1)
+        net, inp = torch.tanh(net).contiguous(), torch.relu(inp).contiguous()
+        coords0, coords1 = self.initialize_flow(image1)
+        if flow_init is not None:
+            coords1 = coords1 + flow_init
+        flow_up, preds = None, []
+        for _ in range(iters):
+            corr = corr_fn(coords1)
+            flow = (coords1 - coords0).contiguous()
+            net, up_mask, delta_flow = self.update_block(net, inp, corr, flow)
+            coords1 = coords1 + delta_flow
+            flow_up = K.convex_upsample((coords1 - coords0).contiguous(), up_mask)
+            preds.append(flow_up)
+        if test_mode:
+            return coords1 - coords0, flow_up
+        return preds

@@ -294,9 +294,16 @@ def main():
                                     "sample": f"{done} full iterations of the oracle (torch CPU fp32 restatement of "
                                               f"src/stage1_neural_atlas.py:151-231) on the same synthetic video, "
                                               f"{threads} threads of {cores} cores"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # orderly teardown: every rank is past its last collective; drop the captured graphs (they hold NCCL
+        # work) before the communicator, and never block the launcher on a straggling destructor
+        torch.cuda.synchronize()
+        dist.barrier()
+        trainer._graphs.clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def C_void(ev):

@@ -225,6 +225,11 @@ int b200_conv2d(const B200ConvDesc* d, const float* x, const float* w, const flo
 int b200_maxpool2(const float* x, float* y, int64_t planes, int32_t H, int32_t W, void* stream);
 int b200_upsample_bilinear2(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
                             int32_t out_c_total, int32_t out_c_off, void* stream);
+/* nn.InstanceNorm2d(affine=False) per (n,c) plane (+ReLU) and relu(a+b): the RAFT encoder's residual
+ * blocks (src/models/stage_1/core/extractor.py:6-57,118-192) */
+int b200_instance_norm(const float* x, float* y, int64_t planes, int64_t hw, float eps, int32_t relu,
+                       void* stream);
+int b200_add_relu(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* mode 0: out = a*b (r*h into a concat buffer); mode 1: out = (1-a)*b + a*c (GRU state update) */
 int b200_gru_gate(const float* a, const float* b, const float* c, float* out, int64_t n_per_sample,
                   int64_t samples, int64_t out_sample_stride, int32_t mode, void* stream);

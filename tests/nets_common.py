@@ -10,5 +10,8 @@ def seeded_weights(shapes, seed):
         for d in shape[1:]:
             fan *= d
         scale = (1.0 / max(fan, 1)) ** 0.5
-        out[name] = (torch.rand(*shape, generator=g) * 2 - 1) * scale if len(shape) else torch.zeros(())
+        if name.endswith("running_var"):
+            out[name] = torch.rand(*shape, generator=g) + 0.5
+        else:
+            out[name] = (torch.rand(*shape, generator=g) * 2 - 1) * scale if len(shape) else torch.zeros(())
     return out

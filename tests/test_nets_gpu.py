@@ -73,3 +73,20 @@ def test_unet_and_transformnet(golden_dir):
     assert (yy.cpu() - oy).abs().max() <= 1e-4
     assert (hid.cpu() - oh).abs().max() <= 1e-4
     assert (cell.cpu() - oc).abs().max() <= 1e-4
+
+
+def test_full_raft_against_reference_fixture(golden_dir):
+    """Whole RAFT (encoders with instance / folded batch norm, correlation, 3 update iterations, convex
+    upsampling) against outputs of the reference model frozen by make_golden_nets.py."""
+    import argparse
+    from src.models.stage_1.core.raft import RAFT
+    fx = torch.load(os.path.join(golden_dir, "raft_full.pt"))
+    model = RAFT(argparse.Namespace(small=False, mixed_precision=True))
+    assert len(model.state_dict()) == 179
+    model.load_state_dict(seeded_weights(fx["shapes"], fx["seed"]), strict=False)
+    model = model.to(DEV).eval()
+    low, up = model(fx["im1"].to(DEV), fx["im2"].to(DEV), iters=3, test_mode=True)
+    assert low.shape == fx["flow_low"].shape and up.shape == fx["flow_up"].shape == (1, 2, 64, 96)
+    scale = fx["flow_up"].abs().max().item()
+    assert (low.cpu() - fx["flow_low"]).abs().max() <= 2e-3 * max(fx["flow_low"].abs().max().item(), 1.0)
+    assert (up.cpu() - fx["flow_up"]).abs().max() <= 2e-3 * max(scale, 1.0)
