@@ -266,7 +266,7 @@ int launch_pretrain_sample(const int64_t* ys, const int64_t* xs, int B, int cap,
 int launch_pretrain_loss(const float* x_map, const float* uv, int B, int cap, float uv_scale, float* d_uv,
                          float* losses, int* counters, cudaStream_t st) {
   pretrain_loss_kernel<<<(cap + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4*>(x_map), uv, B, cap,
-                                                           uv_scale, d_uv, losses, counters + 3);
+                                                           uv_scale, d_uv, losses, counters + 4);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -369,7 +369,7 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
   cfg.inv_nf = n_f > 0 ? 1.0f / (float)n_f : 0.f;
   cfg.inv_nb = n_b > 0 ? 1.0f / (float)n_b : 0.f;
   float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float gmx = 0.f;
+  float gmx = 0.f, gmy = 0.f;
   if (s < cap) {
     SampleOut out;
     if (s < n_local) {
@@ -409,13 +409,16 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gmx = fmaxf(gmx, fabsf(out.dy[g][c]));
+      for (int c = 0; c < 3; ++c) gmy = fmaxf(gmy, fabsf(out.dy[g][c]));
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
       for (int c = 0; c < 3; ++c) d_y[((int64_t)g * cap + s) * 3 + c] = out.dy[g][c];
   }
-  publish_gmax(gmx, counters + 3);     // scale of this iteration's gradients (tensor-core path)
+  // scales of this iteration's gradients for the tensor-core path: [3] atlas (dL/drgb), [4] mapping (dL/duv,
+  // completed by the atlas backward)
+  publish_gmax(gmy, counters + 3);
+  publish_gmax(gmx, counters + 4);
   // block reduction of the six partial sums -> atomics on the loss vector
   __shared__ float red[6][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

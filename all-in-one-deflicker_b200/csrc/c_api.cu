@@ -265,7 +265,7 @@ int64_t b200_atlas_param_floats(void) {
 int64_t b200_atlas_workspace_bytes(const B200AtlasConfig* cfg) {
   AtlasPlan pl;
   if (plan_atlas(cfg, nullptr, &pl) != B200_OK) return -1;
-  return pl.bytes + 256;
+  return pl.bytes + 256 + 2048;      // slack for the 256 / 1024-byte alignment of the real base address
 }
 
 static int atlas_prepare(const B200AtlasConfig* cfg, void* ws, int64_t ws_bytes, AtlasPlan* pl) {

@@ -634,16 +634,15 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
-// gmax_bits[0]: max |dL/dy| seen by the loss head; gmax_bits[1]: max |dL/duv| after the atlas backward added
-// its share (the positional encoding multiplies gradients by up to 2^9*pi).  use_second: mapping network.
-__device__ __forceinline__ void grad_scales(const int* gmax_bits, bool use_second, float& s_g, float& inv_sg) {
-  float mx = __int_as_float(gmax_bits[0]);
-  if (use_second) mx = fmaxf(mx, __int_as_float(gmax_bits[1]));
+// gmax_bits[0]: max |dL/drgb| (atlas network);  gmax_bits[1]: max |dL/duv| (mapping network: loss head,
+// then raised by the atlas backward, whose positional encoding multiplies gradients by up to 2^9*pi).
+__device__ __forceinline__ void grad_scales(const int* gmax_bits, bool mapping, float& s_g, float& inv_sg) {
+  const float mx = __int_as_float(gmax_bits[mapping ? 1 : 0]);
   int e = 0;
   if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);        // mx < 2^e
   e = max(-60, min(60, e));
-  s_g = ldexpf(1.0f, 10 - e);                           // mx * s_g < 1024
-  inv_sg = ldexpf(1.0f, e - 10);
+  s_g = ldexpf(1.0f, 13 - e);                           // mx * s_g < 8192: 8x headroom below the fp16 range
+  inv_sg = ldexpf(1.0f, e - 13);                        // (conversions saturate), small entries keep their lo term
 }
 
 template <bool ATLAS>

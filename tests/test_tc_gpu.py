@@ -132,7 +132,7 @@ def test_tc_trajectory_and_pretrain(golden_dir):
             # summation noise can go either way, so single entries may differ by up to 2*lr per step
             assert d.max() <= 1.1e-3, (which, k, float(d.max()))
             if d.numel() >= 1000:
-                assert d.median() <= 2e-6 and (d > 2e-5).float().mean() <= 1e-2, \
+                assert d.median() <= 1e-5 and (d > 2e-5).float().mean() <= 1e-2, \
                     (which, k, float(d.median()), float((d > 2e-5).float().mean()))
     # pre-training on the tensor-core path
     tr2 = A.AtlasTrainer(vid, {"samples_batch": 10000}, precision=N.PREC_TC, device=DEV)
