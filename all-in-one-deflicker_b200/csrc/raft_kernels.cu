@@ -49,9 +49,9 @@ __global__ void corr_lookup_kernel(LookupArgs a) {
   // bilinear_sampler: xgrid = 2*x/(W-1) - 1, then grid_sample(align_corners=True): ((g + 1) / 2) * (W - 1)
   const float gx = 2.0f * x / (float)(W - 1) - 1.0f, gy = 2.0f * y / (float)(H - 1) - 1.0f;
   const float ix = ((gx + 1.0f) / 2.0f) * (float)(W - 1), iy = ((gy + 1.0f) / 2.0f) * (float)(H - 1);
-  // a 1-pixel-wide level makes (W-1) == 0: the reference's coordinates become inf/NaN there and ATen's
-  // bounds test on the converted indices fails for every tap, i.e. the sample is 0
-  if (!isfinite(ix) || !isfinite(iy)) { a.out[((int64_t)b * 4 * taps + l * taps + tap) * plane + pix] = 0.f; return; }
+  // a 1-pixel-wide level makes (W-1) == 0: the reference's coordinates are inf/NaN there and F.grid_sample
+  // returns NaN for the whole level (frames smaller than 128 px are unusable in the reference as well)
+  if (!isfinite(ix) || !isfinite(iy)) { a.out[((int64_t)b * 4 * taps + l * taps + tap) * plane + pix] = nanf(""); return; }
   const float fx0 = floorf(ix), fy0 = floorf(iy);
   const int x0 = (int)fx0, y0 = (int)fy0;
   const float tx = ix - fx0, ty = iy - fy0;

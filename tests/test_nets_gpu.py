@@ -86,7 +86,7 @@ def test_full_raft_against_reference_fixture(golden_dir):
     model.load_state_dict(seeded_weights(fx["shapes"], fx["seed"]), strict=False)
     model = model.to(DEV).eval()
     low, up = model(fx["im1"].to(DEV), fx["im2"].to(DEV), iters=3, test_mode=True)
-    assert low.shape == fx["flow_low"].shape and up.shape == fx["flow_up"].shape == (1, 2, 64, 96)
+    assert low.shape == fx["flow_low"].shape and up.shape == fx["flow_up"].shape == (1, 2, 128, 192)
     scale = fx["flow_up"].abs().max().item()
     assert (low.cpu() - fx["flow_low"]).abs().max() <= 2e-3 * max(fx["flow_low"].abs().max().item(), 1.0)
     assert (up.cpu() - fx["flow_up"]).abs().max() <= 2e-3 * max(scale, 1.0)
