@@ -5,7 +5,7 @@ Tolerances
   forward       |uv err| <= 5e-6, |atlas output err| <= 5e-5 (PE frequencies up to 2^9*pi amplify the
                 uv rounding), against the fp32 oracle
   gradients     measured against a FLOAT64 evaluation of the oracle, per tensor:
-                  90th percentile of |err| <= max(10 x the fp32 CUDA-core path's, 3e-4 max|grad|)
+                  90th percentile of |err| <= max(10 x the fp32 CUDA-core path's, 2e-3 max|grad|)
                   (the TC forward differs from the fp32 one by ~1e-7 in uv; the 2^9*pi positional frequency
                   turns that into ~1e-5 in rgb and hence ~1e-4 relative in dL/drgb — same mechanism, smaller
                   factor, for the fp32 path against float64)
@@ -103,7 +103,7 @@ def test_tc_forward_and_gradients(golden_dir, B, shape):
             etc = (gtc[k] - ref).abs().flatten()
             q32 = torch.quantile(e32[:: max(1, e32.numel() // 100000)], 0.9).item()
             qtc = torch.quantile(etc[:: max(1, etc.numel() // 100000)], 0.9).item()
-            if qtc > max(10 * q32, 3e-4 * ref.abs().max().item()) + 1e-9:
+            if qtc > max(10 * q32, 2e-3 * ref.abs().max().item()) + 1e-9:
                 problems.append((which, k, "q90", qtc, q32, ref.abs().max().item()))
             if etc.norm().item() > max(3e-3 * ref.norm().item(), 3 * e32.norm().item()) + 1e-9:
                 problems.append((which, k, "frobenius", etc.norm().item(), e32.norm().item(), ref.norm().item()))
