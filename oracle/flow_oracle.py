@@ -37,7 +37,7 @@ def corr_lookup(pyramid, coords, radius=4):
     b, h, w, _ = coords.shape
     outs = []
     for i, corr in enumerate(pyramid):
-        d = torch.linspace(-r, r, 2 * r + 1)
+        d = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
         delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1)        # (dy, dx) added to (x, y): :41-47
         cl = coords.reshape(b * h * w, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
         outs.append(bilinear_sampler(corr, cl).view(b, h, w, -1))
