@@ -34,8 +34,7 @@ using namespace ptx;
 
 constexpr int TM = 128;                 // rows per tile (UMMA M)
 constexpr int HID = 256;
-constexpr int STAGE_BYTES = 32768;      // hi or lo weights of one 64-wide k chunk: 256 rows x 64 k (fp16)
-constexpr int ITEM_BYTES = 16384;       // one ring item: the 128-row half of such an image (128B swizzle)
+constexpr int STAGE_BYTES = 32768;      // one weight image: 256 rows x 64 k (fp16), 128B swizzle
 constexpr float S_ACT = 16.0f;          // activation scale before the fp16 split
 constexpr float S_W = 256.0f;           // weight scale
 constexpr int ATOM_BYTES = TM * 128;    // one 64-column block of a tile image, one term: 16 KB
@@ -132,18 +131,16 @@ struct PrepJob {
   const float* W; int ldw;          // fp32 weight [N][ldw]
   int n_rows, k0, k_cnt;            // valid image rows and the window [k0, k0+k_cnt) of the other index
   int transpose;                    // 0: image(row=n, col=k-k0) = W[n][k];  1: image(row=k, col=n-k0) = W[n][k]
-  int row0;                         // first image row (0 or 128): each job fills one 128-row half image
-  char* hi; char* lo;               // destination images (16 KB each, zero padded)
+  char* hi; char* lo;               // destination images (32 KB each, zero padded)
 };
-constexpr int MAX_PREP_JOBS = 192;
+constexpr int MAX_PREP_JOBS = 96;
 struct PrepJobs { PrepJob j[MAX_PREP_JOBS]; int n; };
 
 __global__ void tc_prep_kernel(const PrepJobs* __restrict__ jobs_ptr) {
-  const PrepJob jb = jobs_ptr->j[blockIdx.x >> 1];
-  // one half image = 128 rows x 64 cols; this block does 64 rows; thread handles one 16-byte chunk at a time
+  const PrepJob jb = jobs_ptr->j[blockIdx.x >> 2];
+  // one image = 256 rows x 64 cols; this block does 64 rows; thread handles one 16-byte chunk at a time
   for (int e = threadIdx.x; e < 64 * 8; e += blockDim.x) {
-    const int lrow = (blockIdx.x & 1) * 64 + (e >> 3), c8 = (e & 7) * 8;
-    const int row = jb.row0 + lrow;
+    const int row = (blockIdx.x & 3) * 64 + (e >> 3), c8 = (e & 7) * 8;
     float v[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -155,7 +152,7 @@ __global__ void tc_prep_kernel(const PrepJobs* __restrict__ jobs_ptr) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) split2_f16(v[2 * q] * S_W, v[2 * q + 1] * S_W, h[q], l[q]);
-    const int off = atom_off(lrow, c8);
+    const int off = atom_off(row, c8);
     *reinterpret_cast<uint4*>(jb.hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(jb.lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
@@ -182,21 +179,20 @@ struct TileIter {                    // static round-robin over the live tiles o
   __device__ __forceinline__ int global_tile(int t) const { return (t / ntg) * cap_tiles + (t % ntg); }
 };
 
-// MMAs of one 64-wide k chunk for one 128-column half of the layer output.  A operand in TMEM (hi at
-// TM_AHI, lo at TM_ALO):  D += A_hi*B_hi + A_lo*B_hi  (B_hi item)  then  D += A_hi*B_lo  (B_lo item)
+// MMAs of one 64-wide k chunk whose A operand is in TMEM (hi at TM_AHI, lo at TM_ALO):
+//   D += A_hi*B_hi + A_lo*B_hi   (B_hi image)    then   D += A_hi*B_lo   (B_lo image)
 template <int NST>
-__device__ __forceinline__ void mma_chunk_ts(Pipe<NST>& pp, uint32_t tmem, uint32_t d_col, int kchunk, uint32_t idesc,
-                                             bool& first) {
+__device__ __forceinline__ void mma_chunk_ts(Pipe<NST>& pp, uint32_t tmem, int kchunk, uint32_t idesc, bool& first) {
   {
     mbar_wait(&pp.full[pp.slot()], pp.parity());
     tc_fence_after();
-    const uint32_t sb = smem_u32(pp.stage + pp.slot() * ITEM_BYTES);
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       const uint64_t bd = make_desc(sb + ks * 32, 16, 1024);
-      mma_ts(tmem + d_col, tmem + TM_AHI + kchunk * 32 + ks * 8, bd, idesc, first ? 0u : 1u);
+      mma_ts(tmem + TM_D, tmem + TM_AHI + kchunk * 32 + ks * 8, bd, idesc, first ? 0u : 1u);
       first = false;
-      mma_ts(tmem + d_col, tmem + TM_ALO + kchunk * 32 + ks * 8, bd, idesc, 1u);
+      mma_ts(tmem + TM_D, tmem + TM_ALO + kchunk * 32 + ks * 8, bd, idesc, 1u);
     }
     mma_commit(&pp.empty[pp.slot()]);
     ++pp.it;
@@ -204,29 +200,29 @@ __device__ __forceinline__ void mma_chunk_ts(Pipe<NST>& pp, uint32_t tmem, uint3
   {
     mbar_wait(&pp.full[pp.slot()], pp.parity());
     tc_fence_after();
-    const uint32_t sb = smem_u32(pp.stage + pp.slot() * ITEM_BYTES);
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
-      mma_ts(tmem + d_col, tmem + TM_AHI + kchunk * 32 + ks * 8, make_desc(sb + ks * 32, 16, 1024), idesc, 1u);
+      mma_ts(tmem + TM_D, tmem + TM_AHI + kchunk * 32 + ks * 8, make_desc(sb + ks * 32, 16, 1024), idesc, 1u);
     mma_commit(&pp.empty[pp.slot()]);
     ++pp.it;
   }
 }
 // same with the A operand in shared memory (64-wide K-major SW128 tile: hi image, lo image)
 template <int NST>
-__device__ __forceinline__ void mma_chunk_ss(Pipe<NST>& pp, uint32_t tmem, uint32_t d_col, const char* a_hi,
-                                             const char* a_lo, uint32_t idesc, bool& first) {
+__device__ __forceinline__ void mma_chunk_ss(Pipe<NST>& pp, uint32_t tmem, const char* a_hi, const char* a_lo,
+                                             uint32_t idesc, bool& first) {
   const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
   {
     mbar_wait(&pp.full[pp.slot()], pp.parity());
     tc_fence_after();
-    const uint32_t sb = smem_u32(pp.stage + pp.slot() * ITEM_BYTES);
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       const uint64_t bd = make_desc(sb + ks * 32, 16, 1024);
-      mma_ss(tmem + d_col, make_desc(ah + ks * 32, 16, 1024), bd, idesc, first ? 0u : 1u);
+      mma_ss(tmem + TM_D, make_desc(ah + ks * 32, 16, 1024), bd, idesc, first ? 0u : 1u);
       first = false;
-      mma_ss(tmem + d_col, make_desc(al + ks * 32, 16, 1024), bd, idesc, 1u);
+      mma_ss(tmem + TM_D, make_desc(al + ks * 32, 16, 1024), bd, idesc, 1u);
     }
     mma_commit(&pp.empty[pp.slot()]);
     ++pp.it;
@@ -234,10 +230,10 @@ __device__ __forceinline__ void mma_chunk_ss(Pipe<NST>& pp, uint32_t tmem, uint3
   {
     mbar_wait(&pp.full[pp.slot()], pp.parity());
     tc_fence_after();
-    const uint32_t sb = smem_u32(pp.stage + pp.slot() * ITEM_BYTES);
+    const uint32_t sb = smem_u32(pp.stage + pp.slot() * STAGE_BYTES);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
-      mma_ss(tmem + d_col, make_desc(ah + ks * 32, 16, 1024), make_desc(sb + ks * 32, 16, 1024), idesc, 1u);
+      mma_ss(tmem + TM_D, make_desc(ah + ks * 32, 16, 1024), make_desc(sb + ks * 32, 16, 1024), idesc, 1u);
     mma_commit(&pp.empty[pp.slot()]);
     ++pp.it;
   }
@@ -247,8 +243,8 @@ template <int NST>
 __device__ __forceinline__ void produce_items(Pipe<NST>& pp, const char* src, int n_items) {
   for (int i = 0; i < n_items; ++i) {
     mbar_wait(&pp.empty[pp.slot()], pp.parity() ^ 1);
-    mbar_expect_tx(&pp.full[pp.slot()], ITEM_BYTES);
-    bulk_g2s(pp.stage + pp.slot() * ITEM_BYTES, src + (int64_t)i * ITEM_BYTES, ITEM_BYTES, &pp.full[pp.slot()]);
+    mbar_expect_tx(&pp.full[pp.slot()], STAGE_BYTES);
+    bulk_g2s(pp.stage + pp.slot() * STAGE_BYTES, src + (int64_t)i * STAGE_BYTES, STAGE_BYTES, &pp.full[pp.slot()]);
     ++pp.it;
   }
 }
@@ -259,8 +255,8 @@ constexpr int SMEM_AUX = 2 * ATOM_BYTES;                     // 32 KB
 constexpr int SMEM_CONST_FLOATS = 3584;                      // 14 KB
 constexpr int SMEM_BARS = 256;
 template <bool ATLAS> struct KCfg {
-  static constexpr int NST = ATLAS ? 6 : 8;                     // ring items of 16 KB
-  static constexpr int SMEM = NST * ITEM_BYTES + SMEM_STAGING + (ATLAS ? SMEM_AUX : 0) + SMEM_CONST_FLOATS * 4 +
+  static constexpr int NST = ATLAS ? 3 : 4;
+  static constexpr int SMEM = NST * STAGE_BYTES + SMEM_STAGING + (ATLAS ? SMEM_AUX : 0) + SMEM_CONST_FLOATS * 4 +
                               SMEM_BARS;
 };
 
@@ -270,15 +266,15 @@ struct SmemMap {
   uint64_t* full; uint64_t* empty; uint64_t* a_ready; uint64_t* d_ready; uint64_t* misc; uint32_t* tmem_slot;
   __device__ __forceinline__ void init(char* raw) {
     char* p = raw;                                   // 1024-aligned (checked in setup_cta): keeps the
-    stage = p; p += NST * ITEM_BYTES;                // shared address space visible to the compiler (LDS/STS)
+    stage = p; p += NST * STAGE_BYTES;               // shared address space visible to the compiler (LDS/STS)
     staging = p; p += SMEM_STAGING;
     aux = p; if (ATLAS) p += SMEM_AUX;
     cst = reinterpret_cast<float*>(p); p += SMEM_CONST_FLOATS * 4;
     full = reinterpret_cast<uint64_t*>(p);
     empty = full + NST;
     a_ready = empty + NST;
-    d_ready = a_ready + 1;                           // two barriers: one per 128-column half of D
-    misc = d_ready + 2;
+    d_ready = a_ready + 1;
+    misc = d_ready + 1;
     tmem_slot = reinterpret_cast<uint32_t*>(misc + 2);
   }
 };
@@ -289,8 +285,7 @@ __device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp)
     if (smem_u32(sm.stage) & 1023u) { printf("b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
     mbar_init(sm.a_ready, EPI_THREADS);
-    mbar_init(&sm.d_ready[0], 1);
-    mbar_init(&sm.d_ready[1], 1);
+    mbar_init(sm.d_ready, 1);
     mbar_init(&sm.misc[0], 1);
     mbar_init(&sm.misc[1], EPI_THREADS);
     fence_barrier_init();
@@ -381,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   if (!ATLAS) for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[i] = P.params[P.w_off[0] + i] * S_ACT;
   const uint32_t tmem = setup_cta(sm, warp);
   TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid);
-  constexpr uint32_t IDESC = make_idesc(128, 128, 0, 0);      // one 128-column half of a layer per accumulator
+  constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -389,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x)
         for (int l = FIRST_TC; l <= LAST_TC; ++l)
-          produce_items(pp, P.img.w_fwd + P.img.w_fwd_layer[l], P.img.n_chunks_fwd[l] * 4);
+          produce_items(pp, P.img.w_fwd + P.img.w_fwd_layer[l], P.img.n_chunks_fwd[l] * 2);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -400,14 +395,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         for (int l = FIRST_TC; l <= LAST_TC; ++l) {
           mbar_wait(sm.a_ready, a_par); a_par ^= 1;
           tc_fence_after();
-          // two output halves back to back: the epilogue drains half 0 while the tensor pipe runs half 1
-          for (int half = 0; half < 2; ++half) {
-            bool first = true;
-            if (l > 0) for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, TM_D + half * 128, kc, IDESC, first);
-            if (ATLAS && (l == 0 || l == 4))
-              mma_chunk_ss(pp, tmem, TM_D + half * 128, sm.aux, sm.aux + ATOM_BYTES, IDESC, first);
-            mma_commit(&sm.d_ready[half]);
-          }
+          bool first = true;
+          if (l > 0) for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC, first);
+          if (ATLAS && (l == 0 || l == 4)) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + ATOM_BYTES, IDESC, first);
+          mma_commit(sm.d_ready);
         }
       }
     }
@@ -509,72 +500,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       for (int j = 0; j < OUT; ++j) outacc[j] = 0.f;
 #pragma unroll 1
       for (int l = FIRST_TC; l <= LAST_TC; ++l) {
+        mbar_wait(sm.d_ready, d_par); d_par ^= 1;
+        tc_fence_after();
         const bool last = (l == LAST_TC);
         char* img = P.img.act + (int64_t)l * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
-        uint32_t keep_h[32], keep_l[32];                // round-0 operand words, stored to TMEM once half 1 is done
+        const float* bias = s_bias + l * 256 + hh * 128;
+        uint32_t bits[4];
 #pragma unroll
-        for (int rd = 0; rd < 2; ++rd) {                // round rd: columns [rd*128 + hh*64, +64) = atom block rd*2+hh
-          mbar_wait(&sm.d_ready[rd], d_par);
-          tc_fence_after();
-          if (rd == 1 && !last) {
-            // all MMAs of this layer are complete: the A region may be overwritten with the next layer's input
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t th[16], tl[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) { th[i] = keep_h[cc * 16 + i]; tl[i] = keep_l[cc * 16 + i]; }
-              tmem_st16(et.tlane + TM_AHI + hh * 32 + cc * 16, th);
-              tmem_st16(et.tlane + TM_ALO + hh * 32 + cc * 16, tl);
-            }
-          }
-          const int col0 = rd * 128 + hh * 64;
-          const float* bias = s_bias + l * 256 + col0;
-          uint32_t ph[32], pl[32], bits[2];
+        for (int ab = 0; ab < 2; ++ab) {
+          uint32_t ph[32], pl[32];
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
+            const int c = ab * 2 + cc;
             uint32_t raw[32];
-            tmem_ld32(et.tlane + TM_D + col0 + cc * 32, raw);
+            tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw);
             tmem_ld_wait();
             uint32_t bw = 0;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float z0 = fmaf(__uint_as_float(raw[i]), inv_scale, bias[cc * 32 + i]);
-              const float z1 = fmaf(__uint_as_float(raw[i + 1]), inv_scale, bias[cc * 32 + i + 1]);
+              const float z0 = fmaf(__uint_as_float(raw[i]), inv_scale, bias[c * 32 + i]);
+              const float z1 = fmaf(__uint_as_float(raw[i + 1]), inv_scale, bias[c * 32 + i + 1]);
               bw |= (z0 > 0.f ? 1u : 0u) << i;
               bw |= (z1 > 0.f ? 1u : 0u) << (i + 1);
               const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
               if (last) {
 #pragma unroll
                 for (int j = 0; j < OUT; ++j) {
-                  outacc[j] = fmaf(v0, s_wlast[j * KLAST + col0 + cc * 32 + i], outacc[j]);
-                  outacc[j] = fmaf(v1, s_wlast[j * KLAST + col0 + cc * 32 + i + 1], outacc[j]);
+                  outacc[j] = fmaf(v0, s_wlast[j * KLAST + hh * 128 + c * 32 + i], outacc[j]);
+                  outacc[j] = fmaf(v1, s_wlast[j * KLAST + hh * 128 + c * 32 + i + 1], outacc[j]);
                 }
               }
               split2_f16(v0, v1, ph[cc * 16 + i / 2], pl[cc * 16 + i / 2]);
             }
-            bits[cc] = bw;
-          }
-          if (!last) {
-            if (rd == 0) {
+            bits[c] = bw;
+            if (!last) {
+              uint32_t th[16], tl[16];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { keep_h[i] = ph[i]; keep_l[i] = pl[i]; }
-            } else {
-#pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                uint32_t th[16], tl[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { th[i] = ph[cc * 16 + i]; tl[i] = pl[cc * 16 + i]; }
-                tmem_st16(et.tlane + TM_AHI + 64 + hh * 32 + cc * 16, th);
-                tmem_st16(et.tlane + TM_ALO + 64 + hh * 32 + cc * 16, tl);
-              }
+              for (int i = 0; i < 16; ++i) { th[i] = ph[cc * 16 + i]; tl[i] = pl[cc * 16 + i]; }
+              tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
+              tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
             }
           }
-          char* g = img + (rd * 2 + hh) * ATOM_BYTES;
+          char* g = img + (hh * 2 + ab) * ATOM_BYTES;
           stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
-          *reinterpret_cast<uint2*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8 + rd * 4 + hh * 2) =
-              make_uint2(bits[0], bits[1]);
         }
-        d_par ^= 1;
+        *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8 + hh * 4) =
+            make_uint4(bits[0], bits[1], bits[2], bits[3]);
         if (!last) {
           tmem_st_wait();
           tc_fence_before();
@@ -693,7 +664,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
   for (int i = threadIdx.x; i < (L - 1) * 256 + (ATLAS ? 0 : 768); i += blockDim.x) s_bacc[i] = 0.f;
   const uint32_t tmem = setup_cta(sm, warp);
   TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid);
-  constexpr uint32_t IDESC = make_idesc(128, 128, 0, 0);      // one 128-column half per accumulator
+  constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
   constexpr uint32_t IDESC64 = make_idesc(128, 64, 0, 0);
   float s_g, inv_sg;
   grad_scales(P.gmax_bits, !ATLAS, s_g, inv_sg);
@@ -713,8 +684,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
                    &sm.misc[0]);
           h_par ^= 1;
         }
-        for (int l = L - 2; l >= LOW; --l) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[l], 16);
-        if (ATLAS) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[0], 8);      // dPE: rows 0..63 live in half 0
+        for (int l = L - 2; l >= LOW; --l) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[l], 8);
+        if (ATLAS) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[0], 8);
       }
     }
   } else if (warp == 1) {
@@ -725,18 +696,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         for (int l = 0; l < N_DGRAD + (ATLAS ? 1 : 0); ++l) {
           mbar_wait(sm.a_ready, a_par); a_par ^= 1;
           tc_fence_after();
-          if (ATLAS && l == N_DGRAD) {
-            bool first = true;                              // dPE: one 64-column product
-            for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, TM_D, kc, IDESC64, first);
-            mma_commit(&sm.d_ready[0]);
-            mma_commit(&sm.d_ready[1]);                     // keeps the two barriers in phase
-          } else {
-            for (int half = 0; half < 2; ++half) {
-              bool first = true;
-              for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, TM_D + half * 128, kc, IDESC, first);
-              mma_commit(&sm.d_ready[half]);
-            }
-          }
+          bool first = true;
+          const uint32_t idesc = (ATLAS && l == N_DGRAD) ? IDESC64 : IDESC;
+          for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, idesc, first);
+          mma_commit(sm.d_ready);
         }
       }
     }
@@ -819,43 +782,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       // ---------------- hidden layers: dA_l = dZ_l W_l  ->  dZ_{l-1}
 #pragma unroll 1
       for (int l = L - 2; l >= LOW; --l) {
+        mbar_wait(sm.d_ready, d_par); d_par ^= 1;
+        tc_fence_after();
         const int slot = l - 1;                           // produces dZ_{l-1}
+        const uint4 bb = *reinterpret_cast<const uint4*>(P.img.bits + ((int64_t)slot * P.img.rows + row) * 8 + hh * 4);
+        const uint32_t bits[4] = {bb.x, bb.y, bb.z, bb.w};
         const bool need_img = ATLAS || slot >= 1;         // mapping dZ_0 feeds only the CUDA-core layer-0 gradient
         const bool need_tmem = ATLAS ? true : (slot >= 1);
         char* img = P.img.dz + (int64_t)slot * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!ATLAS && slot == 0) xv = *reinterpret_cast<const float4*>(P.x + row * 4);
-        uint32_t keep_h[32], keep_l[32];
 #pragma unroll
-        for (int rd = 0; rd < 2; ++rd) {                  // round rd: columns [rd*128 + hh*64, +64)
-          mbar_wait(&sm.d_ready[rd], d_par);
-          tc_fence_after();
-          if (rd == 1 && need_tmem) {
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t th[16], tl[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) { th[i] = keep_h[cc * 16 + i]; tl[i] = keep_l[cc * 16 + i]; }
-              tmem_st16(et.tlane + TM_AHI + hh * 32 + cc * 16, th);
-              tmem_st16(et.tlane + TM_ALO + hh * 32 + cc * 16, tl);
-            }
-          }
-          const int col0 = rd * 128 + hh * 64;
-          const uint2 bb = *reinterpret_cast<const uint2*>(P.img.bits + ((int64_t)slot * P.img.rows + row) * 8 + rd * 4 + hh * 2);
-          const uint32_t bits[2] = {bb.x, bb.y};
+        for (int ab = 0; ab < 2; ++ab) {
           uint32_t ph[32], pl[32];
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
+            const int c = ab * 2 + cc;
             uint32_t raw[32];
-            tmem_ld32(et.tlane + TM_D + col0 + cc * 32, raw);
+            tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw);
             tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ((bits[cc] >> i) & 1u) ? __uint_as_float(raw[i]) * inv_dgrad : 0.f;
-            atomicAdd(&s_bacc[slot * 256 + col0 + cc * 32 + lane], warp_colsum32(v, lane));
+            for (int i = 0; i < 32; ++i) v[i] = ((bits[c] >> i) & 1u) ? __uint_as_float(raw[i]) * inv_dgrad : 0.f;
+            atomicAdd(&s_bacc[slot * 256 + hh * 128 + c * 32 + lane], warp_colsum32(v, lane));
             if (!ATLAS && slot == 0) {
               // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
-              const int n = col0 + cc * 32 + lane;
+              const int n = hh * 128 + c * 32 + lane;
               float w[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.x;
@@ -868,31 +820,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
               atomicAdd(&s_w0acc[n * 3 + 2], warp_colsum32(w, lane));
             }
             if (need_img || need_tmem) {
+              uint32_t th[16], tl[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[cc * 16 + i], pl[cc * 16 + i]);
-            }
-          }
-          if (need_tmem) {
-            if (rd == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) { keep_h[i] = ph[i]; keep_l[i] = pl[i]; }
-            } else {
-#pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                uint32_t th[16], tl[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { th[i] = ph[cc * 16 + i]; tl[i] = pl[cc * 16 + i]; }
-                tmem_st16(et.tlane + TM_AHI + 64 + hh * 32 + cc * 16, th);
-                tmem_st16(et.tlane + TM_ALO + 64 + hh * 32 + cc * 16, tl);
+              for (int i = 0; i < 16; ++i) {
+                split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, th[i], tl[i]);
+                ph[cc * 16 + i] = th[i]; pl[cc * 16 + i] = tl[i];
+              }
+              if (need_tmem) {
+                tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
+                tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
               }
             }
           }
           if (need_img) {
-            char* g = img + (rd * 2 + hh) * ATOM_BYTES;
+            char* g = img + (hh * 2 + ab) * ATOM_BYTES;
             stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
           }
         }
-        d_par ^= 1;
         if (need_tmem) {
           tmem_st_wait();
           tc_fence_before();
@@ -901,9 +845,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       }
       if (ATLAS) {
         // ---------------- dPE = dZ_0 W_0 (64 columns, 40 real) -> d(in) -> d_uv += 0.5 * d(in)
-        mbar_wait(&sm.d_ready[0], d_par);
-        mbar_wait(&sm.d_ready[1], d_par);
-        d_par ^= 1;
+        mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
         mbar_wait(&sm.misc[0], aux_par);                  // PE tile of this row block
         if (hh == 0) {
@@ -1151,15 +1093,10 @@ static HostTables* find_tables(const TcStep& s) {
   return nullptr;
 }
 
-// one job per (64-wide chunk, 128-row half); item order inside a layer: [half][chunk][hi, lo]
-static void add_prep(PrepJobs& pj, const float* W, int ldw, int n_rows, int k0, int k_cnt, int transpose,
-                     char* layer_base, int n_chunks, int chunk) {
-  for (int half = 0; half < 2; ++half) {
-    PrepJob& j = pj.j[pj.n++];
-    j.W = W; j.ldw = ldw; j.n_rows = n_rows; j.k0 = k0; j.k_cnt = k_cnt; j.transpose = transpose; j.row0 = half * 128;
-    j.hi = layer_base + (int64_t)((half * n_chunks + chunk) * 2) * ITEM_BYTES;
-    j.lo = j.hi + ITEM_BYTES;
-  }
+static void add_prep(PrepJobs& pj, const float* W, int ldw, int n_rows, int k0, int k_cnt, int transpose, char* dst) {
+  PrepJob& j = pj.j[pj.n++];
+  j.W = W; j.ldw = ldw; j.n_rows = n_rows; j.k0 = k0; j.k_cnt = k_cnt; j.transpose = transpose;
+  j.hi = dst; j.lo = dst + STAGE_BYTES;
 }
 
 static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, HostTables** out) {
@@ -1190,12 +1127,12 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
     const float* pp = net ? pa : pm;
     for (int l = 0; l < sh.L; ++l) {
       char* dst = im.w_fwd + im.w_fwd_layer[l];
-      const int nc = im.n_chunks_fwd[l];
-      if (nc == 0) continue;
+      if (im.n_chunks_fwd[l] == 0) continue;
       const float* W = pp + sh.w_off[l];
-      int chunk = 0;
-      if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], 256, kc * 64, 64, 0, dst, nc, chunk++);
-      if (net && (l == 0 || sh.skip[l])) add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst, nc, chunk++);
+      int item = 0;
+      if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+      if (net && (l == 0 || sh.skip[l]))
+        add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
     }
     for (int l = 0; l < sh.L - 1; ++l) {
       if (!net && l < 1) continue;
@@ -1203,7 +1140,7 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
       const float* W = pp + sh.w_off[l];
       // image rows = input index k of layer l (256, or 40 for atlas layer 0), chunk over the output index n
       const int rows = (net && l == 0) ? PE_COLS : 256;
-      for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], rows, kc * 64, 64, 1, dst, 4, kc);
+      for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], rows, kc * 64, 64, 1, dst + (int64_t)kc * 2 * STAGE_BYTES);
     }
   }
   // ---- wgrad items.  The kernel is HBM-bound: balance CTAs by bytes read per tile
@@ -1298,7 +1235,7 @@ static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   HostTables* tab = nullptr;
   B200_PROPAGATE(build_tables(s, lay, st, &tab));
   // weight images of both networks — every step, since Adam changed the parameters
-  tc_prep_kernel<<<tab->n_prep * 2, 128, 0, st>>>(tab->d_prep);
+  tc_prep_kernel<<<tab->n_prep * 4, 128, 0, st>>>(tab->d_prep);
   B200_CHECK_LAUNCH();
   const int tiles_map = s.n_groups * (s.cap / TM);
   FwdParams pm{};
