@@ -152,19 +152,25 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const int64_t* _
 // src/stage1_neural_atlas.py:162-171 (rgb gather, xyt), loss_utils.py:138-151 (x+1 / y+1 rows, dx/dy
 // gather), :230-233 (rigidity rows), :326-351 (flow-matched rows).
 // ---------------------------------------------------------------------------------------------
-__global__ void sample_kernel(const int64_t* __restrict__ indices, const int* __restrict__ counters,
-                              const int* __restrict__ list, B200Video vid, SampleGeom geo, int cap,
+// ALL_LOCAL: the whole video is resident (single GPU): no selection pass, slot s == sample s, and the flow-row
+// counts are accumulated here (counters zeroed by a memset node before the launch).
+template <bool ALL_LOCAL>
+__global__ void sample_kernel(const int64_t* __restrict__ indices, int* __restrict__ counters,
+                              const int* __restrict__ list, B200Video vid, SampleGeom geo, int cap, int batch,
                               int n_groups, float4* __restrict__ x_map, float* __restrict__ targets) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= cap) return;
+  if (ALL_LOCAL) {
+    // every thread of the block takes part in the count reduction below
+  } else if (s >= cap) return;
   float4 rows[G_COUNT];
 #pragma unroll
   for (int g = 0; g < G_COUNT; ++g) rows[g] = make_float4(0.f, 0.f, 0.f, 0.f);
   float tg[TARGET_FLOATS];
 #pragma unroll
   for (int q = 0; q < TARGET_FLOATS; ++q) tg[q] = 0.f;
-  if (s < counters[0]) {
-    const int64_t n = indices[list[s]];
+  int cnt_f = 0, cnt_b = 0;
+  if (s < (ALL_LOCAL ? batch : counters[0])) {
+    const int64_t n = indices[ALL_LOCAL ? s : list[s]];
     const int64_t HW = (int64_t)vid.H * vid.W;
     const int t = (int)(n / HW);
     const int y = (int)((n / vid.W) % vid.H);
@@ -179,6 +185,7 @@ __global__ void sample_kernel(const int64_t* __restrict__ indices, const int* __
     const bool wf = v[13] != 0.f, wb = v[14] != 0.f;
     tg[9] = wf ? 1.f : 0.f;
     tg[10] = wb ? 1.f : 0.f;
+    cnt_f = wf; cnt_b = wb;
     const float fx = (float)x, fy = (float)y, ft = (float)t;
     const float hL = geo.half_larger, hX = geo.half_resx, hT = geo.half_frames;
     const float tn = norm_coord(ft, hT);
@@ -194,22 +201,43 @@ __global__ void sample_kernel(const int64_t* __restrict__ indices, const int* __
     rows[G_YMG] = make_float4(norm_coord(fx, hL), norm_coord(fy - geo.d_global, hL), tn, 0.f);
     rows[G_XMG] = make_float4(norm_coord(fx - geo.d_global, hL), norm_coord(fy, hL), tn, 0.f);
   }
+  if (s < cap) {
 #pragma unroll
-  for (int g = 0; g < G_COUNT; ++g)
-    if (g < n_groups) x_map[(int64_t)g * cap + s] = rows[g];
-  float4* tdst = reinterpret_cast<float4*>(targets + (int64_t)s * TARGET_FLOATS);
-  tdst[0] = make_float4(tg[0], tg[1], tg[2], tg[3]);
-  tdst[1] = make_float4(tg[4], tg[5], tg[6], tg[7]);
-  tdst[2] = make_float4(tg[8], tg[9], tg[10], tg[11]);
+    for (int g = 0; g < G_COUNT; ++g)
+      if (g < n_groups) x_map[(int64_t)g * cap + s] = rows[g];
+    float4* tdst = reinterpret_cast<float4*>(targets + (int64_t)s * TARGET_FLOATS);
+    tdst[0] = make_float4(tg[0], tg[1], tg[2], tg[3]);
+    tdst[1] = make_float4(tg[4], tg[5], tg[6], tg[7]);
+    tdst[2] = make_float4(tg[8], tg[9], tg[10], tg[11]);
+  }
+  if (ALL_LOCAL) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt_f += __shfl_xor_sync(0xffffffffu, cnt_f, o);
+      cnt_b += __shfl_xor_sync(0xffffffffu, cnt_b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (cnt_f) atomicAdd(counters + 1, cnt_f);
+      if (cnt_b) atomicAdd(counters + 2, cnt_b);
+    }
+    if (s == 0) counters[0] = batch;
+  }
 }
 
 int launch_select_sample(const int64_t* indices, int B, const B200Video& vid, const SampleGeom& geo, int cap,
                          int n_groups, int* counters, int* list, float* x_map, float* targets,
                          cudaStream_t st) {
+  if (vid.t_begin == 0 && vid.t_end == vid.T) {
+    B200_CHECK_CUDA(cudaMemsetAsync(counters, 0, 32, st));
+    sample_kernel<true><<<(cap + 127) / 128, 128, 0, st>>>(indices, counters, list, vid, geo, cap, B, n_groups,
+                                                            reinterpret_cast<float4*>(x_map), targets);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+  }
   select_kernel<<<1, SELECT_THREADS, 0, st>>>(indices, B, vid, counters, list);
   B200_CHECK_LAUNCH();
-  sample_kernel<<<(cap + 127) / 128, 128, 0, st>>>(indices, counters, list, vid, geo, cap, n_groups,
-                                                    reinterpret_cast<float4*>(x_map), targets);
+  sample_kernel<false><<<(cap + 127) / 128, 128, 0, st>>>(indices, counters, list, vid, geo, cap, B, n_groups,
+                                                             reinterpret_cast<float4*>(x_map), targets);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
