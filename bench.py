@@ -165,6 +165,7 @@ def main():
     dev = torch.device("cuda", local)
     pg = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")   # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     lib = N.lib()
