@@ -189,8 +189,8 @@ def gradient_loss(video: Video, jif, mapping, atlas, rgb_out, resx: int):
                     jif[2] / (T / 2.0) - 1), dim=1)
     yp = torch.cat((jif[0] / _half(resx) - 1, (jif[1] + 1) / _half(resx) - 1,
                     jif[2] / (T / 2.0) - 1), dim=1)
-    dx_gt = video.frames_dx[jif[1], jif[0], :, jif[2]].squeeze(1)
-    dy_gt = video.frames_dy[jif[1], jif[0], :, jif[2]].squeeze(1)
+    dx_gt = video.frames_dx[jif[1], jif[0], :, jif[2]].squeeze(1).to(rgb_out.device)   # loss_utils.py:148-151
+    dy_gt = video.frames_dy[jif[1], jif[0], :, jif[2]].squeeze(1).to(rgb_out.device)
     uv_yp = mapping(yp)
     uv_xp = mapping(xp)
     rgb_yp = (atlas(uv_yp * 0.5 + 0.5) + 1.0) * 0.5
