@@ -83,6 +83,9 @@ SIGNATURES = {
     "b200_corr_build": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "b200_corr_lookup": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "b200_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "b200_conv_weight_image_bytes": (C.c_int64, [C.POINTER(ConvDesc)]),
+    "b200_conv_weight_images": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P]),
+    "b200_conv2d_tc": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "b200_maxpool2": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
     "b200_upsample_bilinear2": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "b200_instance_norm": (C.c_int, [_P, _P, _I64, _I64, _F, _I32, _P]),

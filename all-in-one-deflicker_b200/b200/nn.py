@@ -8,6 +8,41 @@ from . import _native as N
 
 ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3, "tanh": 4}
 
+# Convolution arithmetic: "fp32" = CUDA-core FFMA (bit-comparable with an fp32 cuDNN/CPU convolution up to
+# summation order), "tc" = tcgen05 with fp16 operands and fp32 accumulation — the operand precision the
+# reference itself uses for these layers (fp16 autocast in RAFT, TF32 cuDNN in stage 2).
+_conv_precision = "fp32"
+_weight_images = {}        # (data_ptr, version, shape) -> packed fp16 images
+
+
+def set_conv_precision(mode):
+    """'fp32' or 'tc'.  Returns the previous mode."""
+    global _conv_precision
+    if mode not in ("fp32", "tc"):
+        raise N.B200Error(f"unknown convolution precision {mode!r}")
+    prev, _conv_precision = _conv_precision, mode
+    return prev
+
+
+def conv_precision():
+    return _conv_precision
+
+
+def _images_for(d, w):
+    key = (w.data_ptr(), w._version, tuple(w.shape))
+    img = _weight_images.get(key)
+    if img is None:
+        if len(_weight_images) > 512:
+            _weight_images.clear()
+        nbytes = N.lib().b200_conv_weight_image_bytes(C.byref(d))
+        if nbytes <= 0:
+            raise N.B200Error("b200_conv_weight_image_bytes: invalid descriptor")
+        img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        N.check(N.lib().b200_conv_weight_images(C.byref(d), N.ptr(w), N.ptr(img), N.current_stream()),
+                "b200_conv_weight_images")
+        _weight_images[key] = img
+    return img
+
 
 def _check(t):
     if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
@@ -16,7 +51,7 @@ def _check(t):
 
 
 def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", upsample=1, out=None, out_c_off=0,
-           in_slice=None, residual=None, res_c_off=0, out_scale=1.0):
+           in_slice=None, residual=None, res_c_off=0, out_scale=1.0, precision=None):
     """y = act(conv(pad(upsample(x[:, in_slice]))) + b) * out_scale (+ residual[:, res slice]) written into
     out[:, out_c_off:out_c_off+Cout] (allocated when None).  Restates nn.Conv2d / ReflectionPad2d / Upsample."""
     _check(x); _check(w); _check(b); _check(residual)
@@ -34,8 +69,12 @@ def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", ups
     d = N.ConvDesc(n, cin, h, wd, c_total, c_off, cout, kh, kw, stride, ph, pw, 1 if pad_mode == "reflect" else 0,
                    upsample, out.shape[1], out_c_off, ACT[act], float(out_scale),
                    residual.shape[1] if residual is not None else 0, res_c_off)
-    N.check(N.lib().b200_conv2d(C.byref(d), N.ptr(x), N.ptr(w), N.ptr(b), N.ptr(residual), N.ptr(out),
-                                N.current_stream()), "b200_conv2d")
+    if (_conv_precision if precision is None else precision) == "tc":
+        N.check(N.lib().b200_conv2d_tc(C.byref(d), N.ptr(x), N.ptr(_images_for(d, w)), N.ptr(b), N.ptr(residual),
+                                       N.ptr(out), N.current_stream()), "b200_conv2d_tc")
+    else:
+        N.check(N.lib().b200_conv2d(C.byref(d), N.ptr(x), N.ptr(w), N.ptr(b), N.ptr(residual), N.ptr(out),
+                                    N.current_stream()), "b200_conv2d")
     return out
 
 

@@ -39,8 +39,10 @@ def timed(fn, iters=3, warm=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--small", action="store_true", help="quarter resolution (quick check)")
+    ap.add_argument("--conv", choices=["fp32", "tc"], default="tc", help="convolution arithmetic (b200.nn)")
     args = ap.parse_args()
     from b200 import nn as K
+    K.set_conv_precision(args.conv)
     from nets_common import seeded_weights
     from oracle import flow_oracle as FO
     from oracle import stage2_oracle as SO
@@ -51,7 +53,7 @@ def main():
     dev = "cuda"
     H, W = (272, 480) if args.small else (1080, 1920)
     h8, w8 = (H + 7) // 8, (W + 7) // 8
-    out = {"config": {"raft_frame": [H, W], "h8_w8": [h8, w8]}}
+    out = {"config": {"raft_frame": [H, W], "h8_w8": [h8, w8], "conv": args.conv}}
     g = torch.Generator(device="cpu").manual_seed(0)
     # ---------------- RAFT correlation
     f1 = torch.randn(1, 256, h8, w8, generator=g).to(dev)

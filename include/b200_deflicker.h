@@ -222,6 +222,15 @@ typedef struct B200ConvDesc {
 } B200ConvDesc;
 int b200_conv2d(const B200ConvDesc* d, const float* x, const float* w, const float* bias,
                 const float* residual, float* y, void* stream);
+/* Tensor-core (tcgen05, fp16 operands / fp32 accumulate) variant of b200_conv2d for the layers the reference
+ * itself runs with 10-bit-mantissa operands (RAFT under fp16 autocast, core/raft.py:131; stage-2 cuDNN
+ * convolutions with TF32 allowed).  Weights are first packed into K-major swizzled fp16 images:
+ *   bytes = b200_conv_weight_image_bytes(d);  b200_conv_weight_images(d, w, images, stream);
+ * then b200_conv2d_tc takes `images` in place of w.  Same descriptor semantics as b200_conv2d. */
+int64_t b200_conv_weight_image_bytes(const B200ConvDesc* d);
+int b200_conv_weight_images(const B200ConvDesc* d, const float* w, void* images, void* stream);
+int b200_conv2d_tc(const B200ConvDesc* d, const float* x, const void* w_images, const float* bias,
+                   const float* residual, float* y, void* stream);
 int b200_maxpool2(const float* x, float* y, int64_t planes, int32_t H, int32_t W, void* stream);
 int b200_upsample_bilinear2(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
                             int32_t out_c_total, int32_t out_c_off, void* stream);

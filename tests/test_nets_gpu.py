@@ -90,3 +90,111 @@ def test_full_raft_against_reference_fixture(golden_dir):
     scale = fx["flow_up"].abs().max().item()
     assert (low.cpu() - fx["flow_low"]).abs().max() <= 2e-3 * max(fx["flow_low"].abs().max().item(), 1.0)
     assert (up.cpu() - fx["flow_up"]).abs().max() <= 2e-3 * max(scale, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 convolution (fp16 operands, fp32 accumulation): the operand precision the reference runs these
+# layers in (fp16 autocast for RAFT, TF32 cuDNN for stage 2).  Per-layer tolerance 4e-3 * max|y| against an
+# fp64 convolution of the same fp32 inputs (operand rounding 2^-11 each, fp32 accumulation); whole-network
+# tolerances are stated per test.
+CONV_CASES = [
+    # n, cin, h, w, cout, kh, kw, stride, pad, pad_mode, act, upsample
+    (1, 128, 24, 40, 128, 3, 3, 1, (1, 1), "zeros", "relu", 1),
+    (2, 3, 33, 47, 32, 7, 7, 1, (3, 3), "reflect", "leaky", 1),
+    (1, 324, 17, 23, 256, 1, 1, 1, (0, 0), "zeros", "relu", 1),
+    (1, 384, 16, 24, 128, 1, 5, 1, (0, 2), "zeros", "sigmoid", 1),
+    (1, 384, 16, 24, 128, 5, 1, 1, (2, 0), "zeros", "tanh", 1),
+    (1, 64, 40, 56, 96, 3, 3, 2, (1, 1), "zeros", "none", 1),
+    (1, 64, 20, 28, 32, 3, 3, 1, (1, 1), "reflect", "relu", 2),
+    (1, 128, 16, 24, 2, 3, 3, 1, (1, 1), "zeros", "none", 1),
+    (1, 256, 16, 24, 576, 1, 1, 1, (0, 0), "zeros", "none", 1),
+    (3, 5, 9, 11, 7, 3, 3, 1, (1, 1), "zeros", "none", 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tc_single_layer(case):
+    from b200 import nn as K
+    import torch.nn.functional as F
+    n, cin, h, w, cout, kh, kw, stride, pad, mode, act, ups = case
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xd, wd, bd = x.to(DEV), wt.to(DEV), b.to(DEV)
+    y_tc = K.conv2d(xd, wd, bd, stride=stride, pad=pad, pad_mode=mode, act=act, upsample=ups, precision="tc")
+    y_32 = K.conv2d(xd, wd, bd, stride=stride, pad=pad, pad_mode=mode, act=act, upsample=ups, precision="fp32")
+    xx = x.double()
+    if ups == 2:
+        xx = F.interpolate(xx, scale_factor=2, mode="nearest")
+    if mode == "reflect":
+        xx = F.pad(xx, (pad[1], pad[1], pad[0], pad[0]), mode="reflect")
+        ref = F.conv2d(xx, wt.double(), b.double(), stride=stride)
+    else:
+        ref = F.conv2d(xx, wt.double(), b.double(), stride=stride, padding=pad)
+    ref = {"none": lambda t: t, "relu": torch.relu, "leaky": lambda t: F.leaky_relu(t, 0.2),
+           "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](ref)
+    assert y_tc.shape == ref.shape == y_32.shape
+    scale = ref.abs().max().item()
+    assert (y_32.cpu().double() - ref).abs().max() <= 2e-5 * scale
+    assert (y_tc.cpu().double() - ref).abs().max() <= 4e-3 * scale
+
+
+def test_conv_tc_slices_residual_and_scale():
+    from b200 import nn as K
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 96, 20, 28, generator=g).to(DEV)
+    wt = (torch.randn(40, 64, 3, 3, generator=g) / 24).to(DEV)
+    b = torch.randn(40, generator=g).to(DEV)
+    res = torch.randn(1, 50, 20, 28, generator=g).to(DEV)
+    outs = []
+    for prec in ("fp32", "tc"):
+        out = torch.full((1, 64, 20, 28), 7.0, device=DEV)
+        K.conv2d(x, wt, b, pad=1, act="tanh", out=out, out_c_off=8, in_slice=(16, 80), residual=res, res_c_off=10,
+                 out_scale=0.25, precision=prec)
+        outs.append(out)
+    assert torch.equal(outs[1][:, :8], torch.full_like(outs[1][:, :8], 7.0))
+    assert torch.equal(outs[1][:, 48:], torch.full_like(outs[1][:, 48:], 7.0))
+    assert (outs[0] - outs[1]).abs().max() <= 4e-3 * outs[0][:, 8:48].abs().max()
+
+
+def test_networks_with_tc_convolutions(golden_dir):
+    """Update block, UNet and TransformNet with every convolution on tcgen05: 2e-2 * max|oracle output|
+    (several dozen fp16-operand layers deep; the reference's own fp16/TF32 execution differs from an fp32
+    oracle by the same order)."""
+    from b200 import nn as K
+    from src.models.network_filter import UNet
+    from src.models.network_local import TransformNet
+    from src.models.stage_1.core.update import BasicUpdateBlock
+    prev = K.set_conv_precision("tc")
+    try:
+        fx = torch.load(os.path.join(golden_dir, "raft_update.pt"))
+        z = np.load(os.path.join(golden_dir, "raft_corr.npz"))
+        sd = seeded_weights(fx["shapes"], fx["seed"])
+        ub = BasicUpdateBlock(types.SimpleNamespace(corr_levels=4, corr_radius=4), hidden_dim=128)
+        ub.load_state_dict(sd)
+        ub = ub.to(DEV)
+        net, mask, delta = ub(fx["net"].to(DEV), fx["inp"].to(DEV), torch.from_numpy(z["lookup"]).to(DEV),
+                              fx["flow"].to(DEV))
+        o_net, o_mask, o_delta = FO.update_block(sd, fx["net"], fx["inp"], torch.from_numpy(z["lookup"]), fx["flow"])
+        errs = {"net": ((net.cpu() - o_net).abs().max() / o_net.abs().max()).item(),
+                "delta": ((delta.cpu() - o_delta).abs().max() / o_delta.abs().max()).item(),
+                "mask": ((mask.cpu() - o_mask).abs().max() / o_mask.abs().max()).item()}
+        fx = torch.load(os.path.join(golden_dir, "stage2_nets.pt"))
+        unet = UNet(in_channels=6, out_channels=3, init_features=32)
+        usd = seeded_weights(fx["unet_shapes"], fx["unet_seed"])
+        unet.load_state_dict(usd)
+        y = unet.to(DEV)(fx["unet_x"].to(DEV))
+        oy = SO.unet_forward(usd, fx["unet_x"])
+        errs["unet"] = ((y.cpu() - oy).abs().max() / oy.abs().max()).item()
+        tn = TransformNet(types.SimpleNamespace(nf=32, norm="IN", model="TransformNet", blocks=5), nc_in=12, nc_out=3)
+        tsd = seeded_weights(fx["tn_shapes"], fx["tn_seed"])
+        tn.load_state_dict(tsd, strict=False)
+        yy, (hid, cell) = tn.to(DEV)(fx["tn_x"].to(DEV), None)
+        oy, oh, oc = SO.transformnet_forward(tsd, fx["tn_x"])
+        errs["tn"] = ((yy.cpu() - oy).abs().max() / oy.abs().max()).item()
+        errs["tn_cell"] = ((cell.cpu() - oc).abs().max() / oc.abs().max()).item()
+        print("tc network errors (relative to max):", errs)
+        assert max(errs.values()) <= 2e-2, errs
+    finally:
+        K.set_conv_precision(prev)
