@@ -86,6 +86,10 @@ SIGNATURES = {
     "b200_conv_weight_image_bytes": (C.c_int64, [C.POINTER(ConvDesc)]),
     "b200_conv_weight_images": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P]),
     "b200_conv2d_tc": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "b200_conv_tma_workspace_bytes": (C.c_int64, [C.POINTER(ConvDesc)]),
+    "b200_conv_tma_weight_image_bytes": (C.c_int64, [C.POINTER(ConvDesc)]),
+    "b200_conv_tma_weight_images": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P]),
+    "b200_conv2d_tma": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "b200_maxpool2": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
     "b200_upsample_bilinear2": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "b200_instance_norm": (C.c_int, [_P, _P, _I64, _I64, _F, _I32, _P]),
@@ -118,6 +122,10 @@ def lib():
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def last_error() -> str:
+    return lib().b200_last_error().decode(errors="replace")
 
 
 def check(rc: int, what: str = ""):

@@ -16,9 +16,10 @@ _weight_images = {}        # (data_ptr, version, shape) -> packed fp16 images
 
 
 def set_conv_precision(mode):
-    """'fp32' or 'tc'.  Returns the previous mode."""
+    """'fp32', 'tc' (TMA-fed tcgen05; gather variant for strides it does not take) or 'tc_gather'.
+    Returns the previous mode."""
     global _conv_precision
-    if mode not in ("fp32", "tc"):
+    if mode not in ("fp32", "tc", "tc_gather"):
         raise N.B200Error(f"unknown convolution precision {mode!r}")
     prev, _conv_precision = _conv_precision, mode
     return prev
@@ -28,18 +29,20 @@ def conv_precision():
     return _conv_precision
 
 
-def _images_for(d, w):
-    key = (w.data_ptr(), w._version, tuple(w.shape))
+def _images_for(d, w, tma):
+    key = (w.data_ptr(), w._version, tuple(w.shape), tma)
     img = _weight_images.get(key)
     if img is None:
-        if len(_weight_images) > 512:
+        if len(_weight_images) > 1024:
             _weight_images.clear()
-        nbytes = N.lib().b200_conv_weight_image_bytes(C.byref(d))
+        L = N.lib()
+        size_fn, pack_fn = ((L.b200_conv_tma_weight_image_bytes, L.b200_conv_tma_weight_images) if tma else
+                            (L.b200_conv_weight_image_bytes, L.b200_conv_weight_images))
+        nbytes = size_fn(C.byref(d))
         if nbytes <= 0:
-            raise N.B200Error("b200_conv_weight_image_bytes: invalid descriptor")
+            raise N.B200Error("conv weight image size: invalid descriptor: " + N.last_error())
         img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-        N.check(N.lib().b200_conv_weight_images(C.byref(d), N.ptr(w), N.ptr(img), N.current_stream()),
-                "b200_conv_weight_images")
+        N.check(pack_fn(C.byref(d), N.ptr(w), N.ptr(img), N.current_stream()), "conv weight images")
         _weight_images[key] = img
     return img
 
@@ -69,8 +72,16 @@ def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", ups
     d = N.ConvDesc(n, cin, h, wd, c_total, c_off, cout, kh, kw, stride, ph, pw, 1 if pad_mode == "reflect" else 0,
                    upsample, out.shape[1], out_c_off, ACT[act], float(out_scale),
                    residual.shape[1] if residual is not None else 0, res_c_off)
-    if (_conv_precision if precision is None else precision) == "tc":
-        N.check(N.lib().b200_conv2d_tc(C.byref(d), N.ptr(x), N.ptr(_images_for(d, w)), N.ptr(b), N.ptr(residual),
+    mode = _conv_precision if precision is None else precision
+    if mode == "tc" and stride in (1, 2):
+        nbytes = N.lib().b200_conv_tma_workspace_bytes(C.byref(d))
+        if nbytes <= 0:
+            raise N.B200Error("b200_conv_tma_workspace_bytes: " + N.last_error())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        N.check(N.lib().b200_conv2d_tma(C.byref(d), N.ptr(x), N.ptr(_images_for(d, w, True)), N.ptr(b), N.ptr(residual),
+                                        N.ptr(out), N.ptr(ws), nbytes, N.current_stream()), "b200_conv2d_tma")
+    elif mode in ("tc", "tc_gather"):
+        N.check(N.lib().b200_conv2d_tc(C.byref(d), N.ptr(x), N.ptr(_images_for(d, w, False)), N.ptr(b), N.ptr(residual),
                                        N.ptr(out), N.current_stream()), "b200_conv2d_tc")
     else:
         N.check(N.lib().b200_conv2d(C.byref(d), N.ptr(x), N.ptr(w), N.ptr(b), N.ptr(residual), N.ptr(out),

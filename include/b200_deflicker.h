@@ -231,6 +231,15 @@ int64_t b200_conv_weight_image_bytes(const B200ConvDesc* d);
 int b200_conv_weight_images(const B200ConvDesc* d, const float* w, void* images, void* stream);
 int b200_conv2d_tc(const B200ConvDesc* d, const float* x, const void* w_images, const float* bias,
                    const float* residual, float* y, void* stream);
+/* TMA-fed variant (preferred): the input slice is first repacked to fp16 with padding / upsampling / stride
+ * phases materialised (workspace of b200_conv_tma_workspace_bytes(d) bytes), then every filter tap is a tiled
+ * TMA box load feeding tcgen05.mma directly — no im2col gather.  stride 1 or 2.  Weight images have their own
+ * layout (tap-major):  b200_conv_tma_weight_image_bytes / b200_conv_tma_weight_images. */
+int64_t b200_conv_tma_workspace_bytes(const B200ConvDesc* d);
+int64_t b200_conv_tma_weight_image_bytes(const B200ConvDesc* d);
+int b200_conv_tma_weight_images(const B200ConvDesc* d, const float* w, void* images, void* stream);
+int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images, const float* bias,
+                    const float* residual, float* y, void* workspace, int64_t workspace_bytes, void* stream);
 int b200_maxpool2(const float* x, float* y, int64_t planes, int32_t H, int32_t W, void* stream);
 int b200_upsample_bilinear2(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
                             int32_t out_c_total, int32_t out_c_off, void* stream);

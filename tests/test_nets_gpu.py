@@ -109,6 +109,10 @@ CONV_CASES = [
     (1, 128, 16, 24, 2, 3, 3, 1, (1, 1), "zeros", "none", 1),
     (1, 256, 16, 24, 576, 1, 1, 1, (0, 0), "zeros", "none", 1),
     (3, 5, 9, 11, 7, 3, 3, 1, (1, 1), "zeros", "none", 1),
+    (1, 32, 30, 44, 64, 3, 3, 2, (1, 1), "reflect", "leaky", 1),
+    (1, 3, 64, 96, 64, 7, 7, 2, (3, 3), "zeros", "relu", 1),
+    (1, 64, 12, 300, 3, 7, 7, 1, (3, 3), "reflect", "tanh", 1),
+    (2, 130, 11, 150, 40, 3, 3, 1, (1, 1), "zeros", "none", 2),
 ]
 
 
@@ -123,6 +127,7 @@ def test_conv_tc_single_layer(case):
     b = torch.randn(cout, generator=g)
     xd, wd, bd = x.to(DEV), wt.to(DEV), b.to(DEV)
     y_tc = K.conv2d(xd, wd, bd, stride=stride, pad=pad, pad_mode=mode, act=act, upsample=ups, precision="tc")
+    y_tg = K.conv2d(xd, wd, bd, stride=stride, pad=pad, pad_mode=mode, act=act, upsample=ups, precision="tc_gather")
     y_32 = K.conv2d(xd, wd, bd, stride=stride, pad=pad, pad_mode=mode, act=act, upsample=ups, precision="fp32")
     xx = x.double()
     if ups == 2:
@@ -137,7 +142,8 @@ def test_conv_tc_single_layer(case):
     assert y_tc.shape == ref.shape == y_32.shape
     scale = ref.abs().max().item()
     assert (y_32.cpu().double() - ref).abs().max() <= 2e-5 * scale
-    assert (y_tc.cpu().double() - ref).abs().max() <= 4e-3 * scale
+    assert (y_tc.cpu().double() - ref).abs().max() <= 4e-3 * scale        # TMA-fed kernel
+    assert (y_tg.cpu().double() - ref).abs().max() <= 4e-3 * scale        # gather kernel
 
 
 def test_conv_tc_slices_residual_and_scale():
