@@ -25,17 +25,17 @@
 namespace b200 {
 using namespace ptx;
 
-constexpr int TM_STAGES = 4;
-constexpr int TM_A_BYTES = 16384;               // 128 pixels x 64 channels x 2 B
-constexpr int TM_B_BYTES = 32768;               // <= 256 rows x 128 B
-constexpr int TM_STAGE_BYTES = TM_A_BYTES + TM_B_BYTES;
 constexpr int TM_THREADS = 320;
-constexpr int TM_SMEM = TM_STAGES * TM_STAGE_BYTES + 256;
+constexpr int TM_MAX_A = 8, TM_MAX_B = 16, TM_MAX_ACC = 8;
+constexpr int TM_BAR_BYTES = 1024;              // mbarriers + TMEM slot
+constexpr int TM_SMEM_BUDGET = 225 * 1024;
 
 struct ConvTmaArgs {
   B200ConvDesc d;
   const char* w_img; const float* bias; const float* res; float* y;
   int OH, OW, x_tiles, cchunks, n_chunks, n_tile, n_tiles_n, phases, shift, total_tiles;
+  int a_rows, a_stage, n_a, n_b, n_acc, acc_stride;   // box rows, bytes per A stage, ring depths, TMEM ring
+  int b_group, b_stage;                                // weight chunks (x taps) per B stage, bytes per B stage
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -46,31 +46,65 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-__device__ __forceinline__ float tm_act(float v, int act) {
-  switch (act) {
-    case 1: return fmaxf(v, 0.f);
-    case 2: return v > 0.f ? v : 0.2f * v;
-    case 3: return 1.0f / (1.0f + expf(-v));
-    case 4: return tanhf(v);
-    default: return v;
+template <int ACT>
+__device__ __forceinline__ float tm_act(float v) {
+  if (ACT == 1) return fmaxf(v, 0.f);
+  if (ACT == 2) return v > 0.f ? v : 0.2f * v;
+  if (ACT == 3) return 1.0f / (1.0f + expf(-v));
+  if (ACT == 4) return tanhf(v);
+  return v;
+}
+
+// 32 accumulator columns of one pixel -> bias, activation, scale, residual, NCHW stores (one channel plane apart)
+template <int ACT>
+__device__ __forceinline__ void tm_store32(const uint32_t (&raw)[32], const float* __restrict__ bias, float scale,
+                                           const float* __restrict__ resp, float* __restrict__ yq, int64_t oplane,
+                                           int ncols, bool live, int lane) {
+  const float bl = (bias && lane < ncols) ? __ldg(bias + lane) : 0.f;      // lane i holds bias[i] (ncols is warp-uniform)
+  const int nvalid = live ? ncols : 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float radd[16];
+    if (resp) {                                            // residual loads in flight before the first store
+      const float* rp = resp + (int64_t)(h * 16) * oplane;
+#pragma unroll
+      for (int i = 0; i < 16; ++i, rp += oplane) radd[i] = (h * 16 + i) < nvalid ? __ldg(rp) : 0.f;
+    }
+    float* p = yq + (int64_t)(h * 16) * oplane;
+#pragma unroll
+    for (int i = 0; i < 16; ++i, p += oplane) {
+      float val = __uint_as_float(raw[h * 16 + i]) + __shfl_sync(0xffffffffu, bl, h * 16 + i);
+      val = tm_act<ACT>(val) * scale;
+      if (resp) val += radd[i];
+      if (h * 16 + i < nvalid) *p = val;
+    }
   }
 }
 
+// Reduction order shared by the producer, the MMA issuer and the weight images:
+//   for ky, for xpar in [0, stride), for cc (64-channel block):   one activation box (all x shifts of that row)
+//     for kx = xpar, xpar + stride, ... < KW:                      one weight chunk, A start shifted by kx>>shift rows
 __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_constant__ ConvTmaArgs a,
                                                                    const __grid_constant__ CUtensorMap xmap) {
   extern __shared__ __align__(1024) char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TM_STAGES * TM_STAGE_BYTES);
-  uint64_t* full = bars;                     // [4] tx
-  uint64_t* empty = full + TM_STAGES;        // [4] commit
-  uint64_t* d_full = empty + TM_STAGES;      // [2] commit
-  uint64_t* d_empty = d_full + 2;            // [2] 256 epilogue arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+  const int b_bytes = a.n_tile * 128;
+  char* sA = smem;
+  char* sB = smem + a.n_a * a.a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + a.n_b * a.b_stage);
+  uint64_t* a_full = bars;                         // tx
+  uint64_t* a_empty = a_full + TM_MAX_A;           // commit
+  uint64_t* b_full = a_empty + TM_MAX_A;           // tx
+  uint64_t* b_empty = b_full + TM_MAX_B;           // commit
+  uint64_t* d_full = b_empty + TM_MAX_B;           // commit
+  uint64_t* d_empty = d_full + TM_MAX_ACC;         // 128 epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + TM_MAX_ACC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const B200ConvDesc& d = a.d;
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { printf("b200: conv smem not 1024-byte aligned\n"); __trap(); }
-    for (int i = 0; i < TM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 256); }
+    for (int i = 0; i < TM_MAX_A; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < TM_MAX_B; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < TM_MAX_ACC; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -78,64 +112,97 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int b_bytes = a.n_tile * 128;
+  const int s = d.stride;
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         const int nt = t % a.n_tiles_n;
         int r = t / a.n_tiles_n;
         const int xb = r % a.x_tiles; r /= a.x_tiles;
         const int oy = r % a.OH, n = r / a.OH;
         const char* wsrc = a.w_img + (int64_t)nt * a.n_chunks * b_bytes;
-        int tap = 0, cc = 0, ky = 0, kx = 0;
-        for (int j = 0; j < a.n_chunks; ++j, ++it) {
-          const int s = it % TM_STAGES;
-          mbar_wait(&empty[s], ((it / TM_STAGES) & 1) ^ 1);
-          char* sa = smem + s * TM_STAGE_BYTES;
-          mbar_expect_tx(&full[s], TM_A_BYTES + b_bytes);
-          const int ph = a.phases == 4 ? ((ky & 1) * 2 + (kx & 1)) : 0;
-          const int yy = oy + (ky >> a.shift), xx = xb * 128 + (kx >> a.shift);
-          tma_load_4d(sa, &xmap, cc * 64, xx, yy, n * a.phases + ph, &full[s]);
-          bulk_g2s(sa + TM_A_BYTES, wsrc + (int64_t)j * b_bytes, b_bytes, &full[s]);
-          if (++cc == a.cchunks) { cc = 0; ++tap; if (++kx == d.KW) { kx = 0; ++ky; } }
-        }
+        for (int ky = 0; ky < d.KH; ++ky)
+          for (int xpar = 0; xpar < s && xpar < d.KW; ++xpar) {
+            const int nsub = (d.KW - xpar + s - 1) / s;
+            const int ph = a.phases == 4 ? ((ky & 1) * 2 + xpar) : 0;
+            for (int cc = 0; cc < a.cchunks; ++cc) {
+              mbar_wait(&a_empty[sa], pha ^ 1);
+              mbar_expect_tx(&a_full[sa], a.a_rows * 128);
+              tma_load_4d(sA + sa * a.a_stage, &xmap, cc * 64, xb * 128, oy + (ky >> a.shift), n * a.phases + ph, &a_full[sa]);
+              if (++sa == a.n_a) { sa = 0; pha ^= 1; }
+              for (int i0 = 0; i0 < nsub; i0 += a.b_group) {
+                const int gn = nsub - i0 < a.b_group ? nsub - i0 : a.b_group;
+                mbar_wait(&b_empty[sb], phb ^ 1);
+                mbar_expect_tx(&b_full[sb], gn * b_bytes);
+                bulk_g2s(sB + sb * a.b_stage, wsrc, gn * b_bytes, &b_full[sb]);
+                wsrc += gn * b_bytes;
+                if (++sb == a.n_b) { sb = 0; phb ^= 1; }
+              }
+            }
+          }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, a.n_tile, 0, 0);
-      uint32_t it = 0, tile_i = 0;
-      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tile_i) {
-        const int acc = tile_i & 1;
-        mbar_wait(&d_empty[acc], ((tile_i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        int cc = 0;
-        for (int j = 0; j < a.n_chunks; ++j, ++it) {
-          const int s = it % TM_STAGES;
-          mbar_wait(&full[s], (it / TM_STAGES) & 1);
-          tc_fence_after();
-          const uint32_t pa = smem_u32(smem + s * TM_STAGE_BYTES), pb = pa + TM_A_BYTES;
-          const int left = d.Cin - cc * 64;
-          const int ksteps = ((left < 64 ? left : 64) + 15) >> 4;
-          for (int ks = 0; ks < ksteps; ++ks)
-            mma_ss(tmem + acc * 256, make_desc(pa + ks * 32, 16, 1024), make_desc(pb + ks * 32, 16, 1024), idesc,
-                   (j | ks) ? 1u : 0u);
-          mma_commit(&empty[s]);
-          if (++cc == a.cchunks) cc = 0;
+    // The whole warp runs the (uniform) loop control so that descriptors stay in uniform registers; one elected
+    // lane issues.  Ring positions are kept incrementally (no runtime divisions on this latency-critical path).
+    const uint32_t idesc = make_idesc(128, a.n_tile, 0, 0);
+    const uint64_t desc_hi = make_desc(0, 16, 1024);              // everything but the start address
+    const bool leader = elect_one();
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pha = 0, phb = 0, phd = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      mbar_wait(&d_empty[acc], phd ^ 1);
+      tc_fence_after();
+      const uint32_t dcol = tmem + acc * a.acc_stride;
+      uint32_t accum = 0;
+      for (int ky = 0; ky < d.KH; ++ky)
+        for (int xpar = 0; xpar < s && xpar < d.KW; ++xpar) {
+          const int nsub = (d.KW - xpar + s - 1) / s;
+          for (int cc = 0; cc < a.cchunks; ++cc) {
+            mbar_wait(&a_full[sa], pha);
+            const uint32_t pa = smem_u32(sA + sa * a.a_stage);
+            const int left = d.Cin - cc * 64;
+            const int ksteps = ((left < 64 ? left : 64) + 15) >> 4;
+            for (int i0 = 0; i0 < nsub; i0 += a.b_group) {
+              const int gn = nsub - i0 < a.b_group ? nsub - i0 : a.b_group;
+              mbar_wait(&b_full[sb], phb);
+              tc_fence_after();
+              const uint32_t pb = smem_u32(sB + sb * a.b_stage);
+              if (leader) {
+                for (int i = 0; i < gn; ++i) {
+                  const uint64_t da = desc_hi + (uint64_t)((pa + (i0 + i) * 128) >> 4);
+                  const uint64_t db = desc_hi + (uint64_t)((pb + i * b_bytes) >> 4);
+                  for (int ks = 0; ks < ksteps; ++ks, accum = 1u) mma_ss(dcol, da + 2 * ks, db + 2 * ks, idesc, accum);
+                }
+                mma_commit(&b_empty[sb]);
+              }
+              __syncwarp();
+              if (++sb == a.n_b) { sb = 0; phb ^= 1; }
+            }
+            if (leader) mma_commit(&a_empty[sa]);
+            __syncwarp();
+            if (++sa == a.n_a) { sa = 0; pha ^= 1; }
+          }
         }
-        mma_commit(&d_full[acc]);
-      }
+      if (leader) mma_commit(&d_full[acc]);
+      __syncwarp();
+      if (++acc == a.n_acc) { acc = 0; phd ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // ------------------------------------------------------------------ epilogue: two sets of 4 warps, alternate tiles
+    const int q = warp & 3, set = (warp - 2) >> 2;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const int64_t oplane = (int64_t)a.OH * a.OW;
     uint32_t tile_i = 0;
+    int acc = -1;
+    uint32_t phd = 1;
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++tile_i) {
-      const int acc = tile_i & 1;
+      if (++acc == a.n_acc) acc = 0;
+      if (acc == 0) phd ^= 1;
+      if ((int)(tile_i & 1) != set) continue;
       const int nt = t % a.n_tiles_n;
       int r = t / a.n_tiles_n;
       const int xb = r % a.x_tiles; r /= a.x_tiles;
@@ -143,23 +210,27 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
       const int x = xb * 128 + q * 32 + lane;
       const bool live = x < a.OW;
       const int64_t sp = (int64_t)oy * a.OW + x;
-      mbar_wait(&d_full[acc], (tile_i >> 1) & 1);
+      const float* resp = a.res ? a.res + ((int64_t)n * d.res_c_total + d.res_c_off) * oplane + sp : nullptr;
+      float* yp = a.y + ((int64_t)n * d.out_c_total + d.out_c_off) * oplane + sp;
+      mbar_wait(&d_full[acc], phd);
       tc_fence_after();
-      for (int c0 = half * 32; c0 < a.n_tile; c0 += 64) {
+      for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
         uint32_t raw[32];
-        tmem_ld32(tlane + acc * 256 + c0, raw);
+        tmem_ld32(tlane + acc * a.acc_stride + c0, raw);
         tmem_ld_wait();
-        if (!live) continue;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = nt * a.n_tile + c0 + i;
-          if (c0 + i < a.n_tile && j < d.Cout) {
-            float val = __uint_as_float(raw[i]);
-            if (a.bias) val += __ldg(a.bias + j);
-            val = tm_act(val, d.act) * d.out_scale;
-            if (a.res) val += __ldg(a.res + ((int64_t)n * d.res_c_total + d.res_c_off + j) * oplane + sp);
-            a.y[((int64_t)n * d.out_c_total + d.out_c_off + j) * oplane + sp] = val;
-          }
+        const int jb = nt * a.n_tile + c0;
+        int nvalid = a.n_tile - c0;
+        if (nvalid > d.Cout - jb) nvalid = d.Cout - jb;
+        if (nvalid > 32) nvalid = 32;
+        const float* bq = a.bias ? a.bias + jb : nullptr;
+        const float* rq = resp ? resp + (int64_t)jb * oplane : nullptr;
+        float* yq = yp + (int64_t)jb * oplane;
+        switch (d.act) {
+          case 1: tm_store32<1>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
+          case 2: tm_store32<2>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
+          case 3: tm_store32<3>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
+          case 4: tm_store32<4>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
+          default: tm_store32<0>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
         }
       }
       tc_fence_before();
@@ -222,13 +293,23 @@ __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __res
 // weights [Cout][Cin][KH][KW] fp32 -> per cout tile, per (tap, channel block): [n_tile rows x 64 channels] fp16,
 // K-major, 128-byte swizzle, zero padded
 __global__ void conv_tma_weight_images_kernel(const float* __restrict__ w, char* __restrict__ img, int Cout, int Cin,
-                                              int KHW, int n_tile, int n_tiles_n, int cchunks) {
-  const int n_chunks = KHW * cchunks;
+                                              int KH, int KW, int stride, int n_tile, int n_tiles_n, int cchunks) {
+  const int KHW = KH * KW, n_chunks = KHW * cchunks;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk each
   if (e >= (int64_t)n_tiles_n * n_tile * n_chunks * 8) return;
   const int c8 = (int)(e % 8), j = (int)((e / 8) % n_chunks), grow = (int)(e / (8 * n_chunks));
   const int nt = grow / n_tile, lrow = grow % n_tile, row = nt * n_tile + lrow;
-  const int tap = j / cchunks, cc = j % cchunks;
+  // chunk j -> (ky, xpar, cc, kx) in the kernel's reduction order
+  int tap = 0, cc = 0;
+  {
+    int cnt = 0;
+    bool found = false;
+    for (int ky = 0; ky < KH && !found; ++ky)
+      for (int xpar = 0; xpar < stride && xpar < KW && !found; ++xpar)
+        for (int c = 0; c < cchunks && !found; ++c)
+          for (int kx = xpar; kx < KW; kx += stride, ++cnt)
+            if (cnt == j) { tap = ky * KW + kx; cc = c; found = true; break; }
+  }
   float v[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -310,7 +391,7 @@ int b200_conv_tma_weight_images(const B200ConvDesc* d, const float* w, void* ima
   if (int rc = tma_geometry(d, &g)) return rc;
   const int64_t total = (int64_t)g.n_tiles_n * g.n_tile * g.n_chunks * 8;
   conv_tma_weight_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      w, reinterpret_cast<char*>(images), d->Cout, d->Cin, d->KH * d->KW, g.n_tile, g.n_tiles_n, g.cchunks);
+      w, reinterpret_cast<char*>(images), d->Cout, d->Cin, d->KH, d->KW, d->stride, g.n_tile, g.n_tiles_n, g.cchunks);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -339,7 +420,9 @@ int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images,
   alignas(64) CUtensorMap map;
   const cuuint64_t dims[4] = {(cuuint64_t)g.Cp, (cuuint64_t)g.WP2, (cuuint64_t)g.HP2, (cuuint64_t)d->N * g.phases};
   const cuuint64_t strides[3] = {(cuuint64_t)g.Cp * 2, (cuuint64_t)g.WP2 * g.Cp * 2, (cuuint64_t)g.HP2 * g.WP2 * g.Cp * 2};
-  const cuuint32_t box[4] = {64, 128, 1, 1};
+  const int a_rows = 128 + ((d->KW - 1) >> g.shift);
+  B200_REQUIRE(a_rows <= 256, "filter too wide");
+  const cuuint32_t box[4] = {64, (cuuint32_t)a_rows, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -347,20 +430,40 @@ int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images,
 
   static bool attr_done = false;
   if (!attr_done) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv2d_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv2d_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET));
     attr_done = true;
   }
   ConvTmaArgs a{};
   a.d = *d; a.w_img = reinterpret_cast<const char*>(w_images); a.bias = bias; a.res = residual; a.y = y;
   a.OH = g.OH; a.OW = g.OW; a.x_tiles = (g.OW + 127) / 128; a.cchunks = g.cchunks; a.n_chunks = g.n_chunks;
   a.n_tile = g.n_tile; a.n_tiles_n = g.n_tiles_n; a.phases = g.phases; a.shift = g.shift;
+  a.a_rows = a_rows;
+  a.a_stage = (a_rows * 128 + 1023) / 1024 * 1024;
+  const int b_bytes = g.n_tile * 128;
+  // x taps that share one activation box are fetched as one bulk copy while that stays <= 32 KB
+  const int nsub_max = (d->KW + d->stride - 1) / d->stride;
+  int b_group = 32768 / b_bytes; if (b_group < 1) b_group = 1; if (b_group > nsub_max) b_group = nsub_max;
+  a.b_group = b_group; a.b_stage = b_group * b_bytes;
+  // shared memory: at least 3 B stages (2 for the widest tiles), up to 6 A stages, the rest goes to the B ring
+  const int avail = TM_SMEM_BUDGET - TM_BAR_BYTES;
+  int n_a = (avail - 3 * a.b_stage) / a.a_stage;
+  if (n_a > 6) n_a = 6;
+  if (n_a < 2) n_a = 2;
+  int n_b = (avail - n_a * a.a_stage) / a.b_stage;
+  if (n_b > TM_MAX_B) n_b = TM_MAX_B;
+  B200_REQUIRE(n_a >= 2 && n_b >= 2, "tile does not fit in shared memory");
+  a.n_a = n_a; a.n_b = n_b;
+  const int cols = (g.n_tile + 31) / 32 * 32;
+  a.n_acc = 512 / cols; if (a.n_acc > TM_MAX_ACC) a.n_acc = TM_MAX_ACC; a.n_acc &= ~1;
+  a.acc_stride = 512 / a.n_acc;
+  const int smem_bytes = n_a * a.a_stage + n_b * a.b_stage + TM_BAR_BYTES;
   const int64_t tiles = (int64_t)d->N * g.OH * a.x_tiles * g.n_tiles_n;
   B200_REQUIRE(tiles < (1ll << 31), "too many tiles");
   a.total_tiles = (int)tiles;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  conv2d_tma_kernel<<<(unsigned)(tiles < sms ? tiles : sms), TM_THREADS, TM_SMEM, st>>>(a, map);
+  conv2d_tma_kernel<<<(unsigned)(tiles < sms ? tiles : sms), TM_THREADS, smem_bytes, st>>>(a, map);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -13,7 +13,8 @@ K.set_conv_precision("tc")
 g = torch.Generator().manual_seed(0)
 cases = [(6, 32, 3, 1088, 1920, "zeros", 1), (32, 32, 3, 1088, 1920, "zeros", 1), (128, 128, 3, 272, 480, "zeros", 1),
          (128, 128, 3, 272, 480, "reflect", 1), (128, 32, 3, 544, 960, "reflect", 2), (64, 3, 7, 1088, 1920, "reflect", 1)]
-for cin, cout, k, h, w, mode, up in cases:
+sel = [int(v) for v in sys.argv[1:]] or range(len(cases))
+for cin, cout, k, h, w, mode, up in [cases[i] for i in sel]:
     x = torch.randn(1, cin, h, w, generator=g).cuda()
     wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
     b = torch.zeros(cout).cuda()
