@@ -1,7 +1,11 @@
 """`RAFT` (basic variant, the only one the reference's wrapper builds: raft_wrapper.py:17-20) with the
 reference's module tree / state_dict keys and forward signature (src/models/stage_1/core/raft.py:28-148).
-Inference only (the reference never trains it).  fp32 throughout — the reference autocasts the encoders
-and the update block to fp16, correlation is fp32 in both."""
+Inference only (the reference never trains it).  `args.mixed_precision` keeps the reference's meaning
+(core/raft.py:99,110,131: encoders and update block under fp16 autocast, correlation in fp32): the
+convolutions of those three sub-networks then run on the tcgen05 path (fp16 operands, fp32 accumulation,
+fp32 tensors between layers); without it every convolution is the fp32 CUDA-core kernel."""
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -29,6 +33,17 @@ class RAFT(nn.Module):
         self.cnet = BasicEncoder(output_dim=hdim + cdim, norm_fn='batch', dropout=args.dropout)
         self.update_block = BasicUpdateBlock(self.args, hidden_dim=hdim)
 
+    @contextlib.contextmanager
+    def _autocast(self):
+        if not getattr(self.args, "mixed_precision", False) or K.conv_precision() != "fp32":
+            yield                      # an explicit global choice (b200.nn.set_conv_precision) wins
+            return
+        prev = K.set_conv_precision("tc")
+        try:
+            yield
+        finally:
+            K.set_conv_precision(prev)
+
     def initialize_flow(self, img):
         n, _, h, w = img.shape
         c = coords_grid(n, h // 8, w // 8).to(img.device)
@@ -38,9 +53,11 @@ class RAFT(nn.Module):
     def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
-        fmap1, fmap2 = self.fnet([image1, image2])
+        with self._autocast():
+            fmap1, fmap2 = self.fnet([image1, image2])
         corr_fn = CorrBlock(fmap1.float(), fmap2.float(), radius=self.args.corr_radius)
-        cnet = self.cnet(image1)
+        with self._autocast():
+            cnet = self.cnet(image1)
         net, inp = torch.split(cnet, [self.hidden_dim, self.context_dim], dim=1)
         net, inp = torch.tanh(net).contiguous(), torch.relu(inp).contiguous()
         coords0, coords1 = self.initialize_flow(image1)
@@ -50,7 +67,8 @@ class RAFT(nn.Module):
         for _ in range(iters):
             corr = corr_fn(coords1)
             flow = (coords1 - coords0).contiguous()
-            net, up_mask, delta_flow = self.update_block(net, inp, corr, flow)
+            with self._autocast():
+                net, up_mask, delta_flow = self.update_block(net, inp, corr, flow)
             coords1 = coords1 + delta_flow
             flow_up = K.convex_upsample((coords1 - coords0).contiguous(), up_mask)
             preds.append(flow_up)

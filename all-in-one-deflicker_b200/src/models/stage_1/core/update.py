@@ -1,7 +1,8 @@
 """RAFT update operator with the reference's module tree / state_dict keys
 (src/models/stage_1/core/update.py:6-136): BasicMotionEncoder, SepConvGRU, FlowHead, mask head.
 Parameters live in nn.Conv2d modules (for checkpoints); arithmetic runs in b200_conv2d / b200_gru_gate.
-The reference runs this block under fp16 autocast; here it is fp32 (a superset of that precision)."""
+The reference runs this block under fp16 autocast; the convolution arithmetic here follows
+b200.nn.conv_precision() (RAFT.forward selects the tcgen05 fp16-operand path when args.mixed_precision)."""
 import torch
 import torch.nn as nn
 

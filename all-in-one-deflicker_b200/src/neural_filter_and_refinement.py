@@ -26,6 +26,9 @@ parser.add_argument("--ckpt_local", default="./pretrained_weights/local_refineme
 parser.add_argument("--fps", default=10, type=int)
 parser.add_argument("--video_name", default=None, type=str)
 parser.add_argument('--gpu', type=int, default=0)
+# not in the reference: convolution arithmetic.  "tc" = tcgen05 with fp16 operands / fp32 accumulation — the same
+# operand width as the TF32 cuDNN convolutions the reference runs by default; "fp32" = CUDA-core FFMA.
+parser.add_argument('--conv_precision', choices=["tc", "fp32"], default="tc")
 
 
 def main(opts):
@@ -34,6 +37,8 @@ def main(opts):
     if not torch.cuda.is_available():
         raise Exception("No GPU found, run with cpu")
     device = torch.device("cuda:{}".format(opts.gpu))
+    from b200 import nn as K
+    K.set_conv_precision(opts.conv_precision)
     filter_net = net.UNet(in_channels=6, out_channels=3, init_features=32)
     filter_net.load_state_dict(torch.load(opts.ckpt_filter, map_location="cpu"))
     filter_net.to(device).eval()
