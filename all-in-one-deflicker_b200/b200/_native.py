@@ -81,6 +81,9 @@ SIGNATURES = {
     "b200_render": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, C.c_int, _P, _I64, _P]),
     "b200_corr_pyramid_floats": (_I64, [_I32, _I32]),
     "b200_corr_build": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "b200_corr_pool_levels": (C.c_int, [_P, _I32, _I32, _P]),
+    "b200_corr_build_tc_workspace_bytes": (C.c_int64, [_I32, _I32, _I32]),
+    "b200_corr_build_tc": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, C.c_int64, _P]),
     "b200_corr_lookup": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "b200_conv2d": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "b200_conv_weight_image_bytes": (C.c_int64, [C.POINTER(ConvDesc)]),

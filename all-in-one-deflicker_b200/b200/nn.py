@@ -138,15 +138,27 @@ def convex_upsample(flow, mask):
     return out
 
 
-def corr_build(fmap1, fmap2):
-    """fmaps (1, C, H8, W8) -> flat pyramid tensor (level 0 [HW][H8][W8] then 3 pooled levels)."""
+def corr_build(fmap1, fmap2, impl="tc"):
+    """fmaps (1, C, H8, W8) -> flat pyramid tensor (level 0 [HW][H8][W8] then 3 pooled levels).
+    impl 'tc': tcgen05 with (hi, lo) fp16 operand pairs (fp32-grade, like the reference's fp32 matmul);
+    'simt': fp32 CUDA-core GEMM."""
     _check(fmap1); _check(fmap2)
     b, c, h, w = fmap1.shape
     if b != 1:
         raise N.B200Error("correlation kernels take batch 1 (the reference runs one frame pair at a time)")
     pyr = torch.empty(int(N.lib().b200_corr_pyramid_floats(h, w)), dtype=torch.float32, device=fmap1.device)
-    N.check(N.lib().b200_corr_build(N.ptr(fmap1), N.ptr(fmap2), c, h, w, N.ptr(pyr), N.current_stream()),
-            "b200_corr_build")
+    if impl == "tc":
+        nbytes = N.lib().b200_corr_build_tc_workspace_bytes(c, h, w)
+        if nbytes <= 0:
+            raise N.B200Error("b200_corr_build_tc_workspace_bytes: bad arguments")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=fmap1.device)
+        N.check(N.lib().b200_corr_build_tc(N.ptr(fmap1), N.ptr(fmap2), c, h, w, N.ptr(pyr), N.ptr(ws), nbytes,
+                                           N.current_stream()), "b200_corr_build_tc")
+    elif impl == "simt":
+        N.check(N.lib().b200_corr_build(N.ptr(fmap1), N.ptr(fmap2), c, h, w, N.ptr(pyr), N.current_stream()),
+                "b200_corr_build")
+    else:
+        raise N.B200Error(f"unknown correlation builder {impl!r}")
     return pyr
 
 

@@ -36,6 +36,7 @@ struct ConvTmaArgs {
   int OH, OW, x_tiles, cchunks, n_chunks, n_tile, n_tiles_n, phases, shift, total_tiles;
   int a_rows, a_stage, n_a, n_b, n_acc, acc_stride;   // box rows, bytes per A stage, ring depths, TMEM ring
   int b_group, b_stage;                                // weight chunks (x taps) per B stage, bytes per B stage
+  int split;                                           // 1: both operands are (hi, lo) fp16 pairs, 3 MMAs per product
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -85,9 +86,12 @@ __device__ __forceinline__ void tm_store32(const uint32_t (&raw)[32], const floa
 //   for ky, for xpar in [0, stride), for cc (64-channel block):   one activation box (all x shifts of that row)
 //     for kx = xpar, xpar + stride, ... < KW:                      one weight chunk, A start shifted by kx>>shift rows
 __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_constant__ ConvTmaArgs a,
-                                                                   const __grid_constant__ CUtensorMap xmap) {
+                                                                   const __grid_constant__ CUtensorMap xmap,
+                                                                   const __grid_constant__ CUtensorMap xmap_lo) {
   extern __shared__ __align__(1024) char smem[];
-  const int b_bytes = a.n_tile * 128;
+  const int b_half = a.n_tile * 128;                    // one term of one weight chunk
+  const int b_bytes = a.split ? 2 * b_half : b_half;
+  const int a_half = a.a_stage >> 1;                    // split: hi box at +0, lo box at +a_half
   char* sA = smem;
   char* sB = smem + a.n_a * a.a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + a.n_b * a.b_stage);
@@ -130,8 +134,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
             const int ph = a.phases == 4 ? ((ky & 1) * 2 + xpar) : 0;
             for (int cc = 0; cc < a.cchunks; ++cc) {
               mbar_wait(&a_empty[sa], pha ^ 1);
-              mbar_expect_tx(&a_full[sa], a.a_rows * 128);
+              mbar_expect_tx(&a_full[sa], a.a_rows * 128 * (1 + a.split));
               tma_load_4d(sA + sa * a.a_stage, &xmap, cc * 64, xb * 128, oy + (ky >> a.shift), n * a.phases + ph, &a_full[sa]);
+              if (a.split)
+                tma_load_4d(sA + sa * a.a_stage + a_half, &xmap_lo, cc * 64, xb * 128, oy + (ky >> a.shift), n * a.phases + ph,
+                            &a_full[sa]);
               if (++sa == a.n_a) { sa = 0; pha ^= 1; }
               for (int i0 = 0; i0 < nsub; i0 += a.b_group) {
                 const int gn = nsub - i0 < a.b_group ? nsub - i0 : a.b_group;
@@ -175,7 +182,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
                 for (int i = 0; i < gn; ++i) {
                   const uint64_t da = desc_hi + (uint64_t)((pa + (i0 + i) * 128) >> 4);
                   const uint64_t db = desc_hi + (uint64_t)((pb + i * b_bytes) >> 4);
-                  for (int ks = 0; ks < ksteps; ++ks, accum = 1u) mma_ss(dcol, da + 2 * ks, db + 2 * ks, idesc, accum);
+                  if (!a.split) {
+                    for (int ks = 0; ks < ksteps; ++ks, accum = 1u) mma_ss(dcol, da + 2 * ks, db + 2 * ks, idesc, accum);
+                  } else {                                 // (hi + lo)(hi + lo) without the lo*lo term
+                    const uint64_t da_lo = da + (uint64_t)(a_half >> 4), db_lo = db + (uint64_t)(b_half >> 4);
+                    for (int ks = 0; ks < ksteps; ++ks, accum = 1u) {
+                      mma_ss(dcol, da + 2 * ks, db + 2 * ks, idesc, accum);
+                      mma_ss(dcol, da + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+                      mma_ss(dcol, da_lo + 2 * ks, db + 2 * ks, idesc, 1u);
+                    }
+                  }
                 }
                 mma_commit(&b_empty[sb]);
               }
@@ -251,7 +267,8 @@ __device__ __forceinline__ int tm_reflect(int i, int n) {
 // fp32 NCHW slice -> fp16 [N*phases][HP2][WP2][Cp] (Cp = channels padded to 64) with padding / upsampling /
 // phase split applied.  One block = 32 pixels of one row x 64 channels, transposed through shared memory.
 __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __restrict__ x, __half* __restrict__ xp,
-                                                              B200ConvDesc d, int HP2, int WP2, int Cp, int phases) {
+                                                              B200ConvDesc d, int HP2, int WP2, int Cp, int phases,
+                                                              float scale, int64_t lo_off) {
   __shared__ float tile[64][33];
   const int cblocks = Cp / 64;
   const int cb = blockIdx.z % cblocks, nph = blockIdx.z / cblocks;
@@ -283,17 +300,22 @@ __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __res
   if (bx + px < WP2) {
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = tile[c8 * 8 + q][px];
-    const uint4 pk = make_uint4(cvt_pack_f16x2(v[0], v[1]), cvt_pack_f16x2(v[2], v[3]), cvt_pack_f16x2(v[4], v[5]),
-                                cvt_pack_f16x2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(xp + (((int64_t)nph * HP2 + yy) * WP2 + bx + px) * Cp + cb * 64 + c8 * 8) = pk;
+    for (int q = 0; q < 8; ++q) v[q] = tile[c8 * 8 + q][px] * scale;
+    uint4 hi, lo;
+    split2_f16(v[0], v[1], hi.x, lo.x); split2_f16(v[2], v[3], hi.y, lo.y);
+    split2_f16(v[4], v[5], hi.z, lo.z); split2_f16(v[6], v[7], hi.w, lo.w);
+    const int64_t o = (((int64_t)nph * HP2 + yy) * WP2 + bx + px) * Cp + cb * 64 + c8 * 8;
+    *reinterpret_cast<uint4*>(xp + o) = hi;
+    if (lo_off) *reinterpret_cast<uint4*>(xp + lo_off + o) = lo;
   }
 }
 
 // weights [Cout][Cin][KH][KW] fp32 -> per cout tile, per (tap, channel block): [n_tile rows x 64 channels] fp16,
 // K-major, 128-byte swizzle, zero padded
+// (w_co, w_ci, w_tap = element strides of the weight tensor; split: chunk = [hi rows | lo rows], values pre-scaled)
 __global__ void conv_tma_weight_images_kernel(const float* __restrict__ w, char* __restrict__ img, int Cout, int Cin,
-                                              int KH, int KW, int stride, int n_tile, int n_tiles_n, int cchunks) {
+                                              int KH, int KW, int stride, int n_tile, int n_tiles_n, int cchunks,
+                                              int64_t w_co, int64_t w_ci, int64_t w_tap, float scale, int split) {
   const int KHW = KH * KW, n_chunks = KHW * cchunks;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk each
   if (e >= (int64_t)n_tiles_n * n_tile * n_chunks * 8) return;
@@ -314,13 +336,16 @@ __global__ void conv_tma_weight_images_kernel(const float* __restrict__ w, char*
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int ci = cc * 64 + c8 * 8 + q;
-    v[q] = (row < Cout && ci < Cin) ? w[((int64_t)row * Cin + ci) * KHW + tap] : 0.f;
+    v[q] = (row < Cout && ci < Cin) ? w[row * w_co + ci * w_ci + tap * w_tap] * scale : 0.f;
   }
-  const uint4 pk = make_uint4(cvt_pack_f16x2(v[0], v[1]), cvt_pack_f16x2(v[2], v[3]), cvt_pack_f16x2(v[4], v[5]),
-                              cvt_pack_f16x2(v[6], v[7]));
+  uint4 hi, lo;
+  split2_f16(v[0], v[1], hi.x, lo.x); split2_f16(v[2], v[3], hi.y, lo.y);
+  split2_f16(v[4], v[5], hi.z, lo.z); split2_f16(v[6], v[7], hi.w, lo.w);
   const int rr = lrow & 7;
-  char* dst = img + ((int64_t)nt * n_chunks + j) * n_tile * 128 + (lrow >> 3) * 1024 + rr * 128 + ((c8 ^ rr) << 4);
-  *reinterpret_cast<uint4*>(dst) = pk;
+  const int64_t chunk_bytes = (int64_t)n_tile * 128 * (1 + split);
+  char* dst = img + ((int64_t)nt * n_chunks + j) * chunk_bytes + (lrow >> 3) * 1024 + rr * 128 + ((c8 ^ rr) << 4);
+  *reinterpret_cast<uint4*>(dst) = hi;
+  if (split) *reinterpret_cast<uint4*>(dst + (int64_t)n_tile * 128) = lo;
 }
 
 struct TmaGeom {
@@ -367,66 +392,40 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-}  // namespace b200
-
-using namespace b200;
-
-extern "C" {
-
-int64_t b200_conv_tma_workspace_bytes(const B200ConvDesc* d) {
-  TmaGeom g;
-  if (tma_geometry(d, &g) != B200_OK) return -1;
-  return g.pack_bytes + 256;
-}
-
-int64_t b200_conv_tma_weight_image_bytes(const B200ConvDesc* d) {
-  TmaGeom g;
-  if (tma_geometry(d, &g) != B200_OK) return -1;
-  return (int64_t)g.n_tiles_n * g.n_chunks * g.n_tile * 128;
-}
-
-int b200_conv_tma_weight_images(const B200ConvDesc* d, const float* w, void* images, void* stream) {
-  B200_REQUIRE(w && images, "null pointer");
-  TmaGeom g;
-  if (int rc = tma_geometry(d, &g)) return rc;
+static int launch_weight_images(const B200ConvDesc* d, const TmaGeom& g, const float* w, int64_t w_co, int64_t w_ci,
+                                int64_t w_tap, float scale, int split, void* images, cudaStream_t st) {
   const int64_t total = (int64_t)g.n_tiles_n * g.n_tile * g.n_chunks * 8;
-  conv_tma_weight_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      w, reinterpret_cast<char*>(images), d->Cout, d->Cin, d->KH, d->KW, d->stride, g.n_tile, g.n_tiles_n, g.cchunks);
+  conv_tma_weight_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      w, reinterpret_cast<char*>(images), d->Cout, d->Cin, d->KH, d->KW, d->stride, g.n_tile, g.n_tiles_n, g.cchunks, w_co,
+      w_ci, w_tap, scale, split);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
-int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images, const float* bias,
-                    const float* residual, float* y, void* workspace, int64_t workspace_bytes, void* stream) {
-  B200_REQUIRE(x && w_images && y && workspace, "null pointer");
-  TmaGeom g;
-  if (int rc = tma_geometry(d, &g)) return rc;
-  B200_REQUIRE(d->in_c_off >= 0 && d->in_c_off + d->Cin <= d->in_c_total && d->out_c_off >= 0 &&
-               d->out_c_off + d->Cout <= d->out_c_total, "channel slice out of range");
-  if (!b200_device_supports_tc()) { set_error("b200_conv2d_tma needs a compute-capability 10.x device"); return B200_ERR_UNSUPPORTED; }
-  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  if (base + g.pack_bytes > reinterpret_cast<char*>(workspace) + workspace_bytes) {
-    set_error("b200_conv2d_tma: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(g.pack_bytes + 256));
-    return B200_ERR_WORKSPACE;
-  }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// repack x into `base` (fp16, hi then lo when split) and run the convolution
+static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float* x, char* base, const void* w_images,
+                           const float* bias, const float* residual, float* y, int split, float in_scale, cudaStream_t st) {
   B200_REQUIRE(g.HP2 <= 65535 && (int64_t)d->N * g.phases * g.cchunks <= 65535, "input too large for the repack grid");
   conv_pack_input_kernel<<<dim3((g.WP2 + 31) / 32, g.HP2, d->N * g.phases * g.cchunks), 256, 0, st>>>(
-      x, reinterpret_cast<__half*>(base), *d, g.HP2, g.WP2, g.Cp, g.phases);
+      x, reinterpret_cast<__half*>(base), *d, g.HP2, g.WP2, g.Cp, g.phases, in_scale, split ? g.pack_bytes / 2 : 0);
   B200_CHECK_LAUNCH();
 
   EncodeTiledFn enc = encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200_ERR_UNSUPPORTED; }
-  alignas(64) CUtensorMap map;
+  alignas(64) CUtensorMap map, map_lo;
   const cuuint64_t dims[4] = {(cuuint64_t)g.Cp, (cuuint64_t)g.WP2, (cuuint64_t)g.HP2, (cuuint64_t)d->N * g.phases};
   const cuuint64_t strides[3] = {(cuuint64_t)g.Cp * 2, (cuuint64_t)g.WP2 * g.Cp * 2, (cuuint64_t)g.HP2 * g.WP2 * g.Cp * 2};
   const int a_rows = 128 + ((d->KW - 1) >> g.shift);
   B200_REQUIRE(a_rows <= 256, "filter too wide");
   const cuuint32_t box[4] = {64, (cuuint32_t)a_rows, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return B200_ERR_CUDA; }
+  for (int term = 0; term <= split; ++term) {
+    const CUresult cr = enc(term ? &map_lo : &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base + term * g.pack_bytes, dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return B200_ERR_CUDA; }
+  }
+  if (!split) map_lo = map;
 
   static bool attr_done = false;
   if (!attr_done) {
@@ -437,9 +436,9 @@ int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images,
   a.d = *d; a.w_img = reinterpret_cast<const char*>(w_images); a.bias = bias; a.res = residual; a.y = y;
   a.OH = g.OH; a.OW = g.OW; a.x_tiles = (g.OW + 127) / 128; a.cchunks = g.cchunks; a.n_chunks = g.n_chunks;
   a.n_tile = g.n_tile; a.n_tiles_n = g.n_tiles_n; a.phases = g.phases; a.shift = g.shift;
-  a.a_rows = a_rows;
-  a.a_stage = (a_rows * 128 + 1023) / 1024 * 1024;
-  const int b_bytes = g.n_tile * 128;
+  a.a_rows = a_rows; a.split = split;
+  a.a_stage = (a_rows * 128 + 1023) / 1024 * 1024 * (1 + split);
+  const int b_bytes = g.n_tile * 128 * (1 + split);
   // x taps that share one activation box are fetched as one bulk copy while that stays <= 32 KB
   const int nsub_max = (d->KW + d->stride - 1) / d->stride;
   int b_group = 32768 / b_bytes; if (b_group < 1) b_group = 1; if (b_group > nsub_max) b_group = nsub_max;
@@ -463,9 +462,91 @@ int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  conv2d_tma_kernel<<<(unsigned)(tiles < sms ? tiles : sms), TM_THREADS, smem_bytes, st>>>(a, map);
+  conv2d_tma_kernel<<<(unsigned)(tiles < sms ? tiles : sms), TM_THREADS, smem_bytes, st>>>(a, map, map_lo);
   B200_CHECK_LAUNCH();
   return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int64_t b200_conv_tma_workspace_bytes(const B200ConvDesc* d) {
+  TmaGeom g;
+  if (tma_geometry(d, &g) != B200_OK) return -1;
+  return g.pack_bytes + 256;
+}
+
+int64_t b200_conv_tma_weight_image_bytes(const B200ConvDesc* d) {
+  TmaGeom g;
+  if (tma_geometry(d, &g) != B200_OK) return -1;
+  return (int64_t)g.n_tiles_n * g.n_chunks * g.n_tile * 128;
+}
+
+int b200_conv_tma_weight_images(const B200ConvDesc* d, const float* w, void* images, void* stream) {
+  B200_REQUIRE(w && images, "null pointer");
+  TmaGeom g;
+  if (int rc = tma_geometry(d, &g)) return rc;
+  const int KHW = d->KH * d->KW;
+  return launch_weight_images(d, g, w, (int64_t)d->Cin * KHW, KHW, 1, 1.0f, 0, images, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images, const float* bias,
+                    const float* residual, float* y, void* workspace, int64_t workspace_bytes, void* stream) {
+  B200_REQUIRE(x && w_images && y && workspace, "null pointer");
+  TmaGeom g;
+  if (int rc = tma_geometry(d, &g)) return rc;
+  B200_REQUIRE(d->in_c_off >= 0 && d->in_c_off + d->Cin <= d->in_c_total && d->out_c_off >= 0 &&
+               d->out_c_off + d->Cout <= d->out_c_total, "channel slice out of range");
+  if (!b200_device_supports_tc()) { set_error("b200_conv2d_tma needs a compute-capability 10.x device"); return B200_ERR_UNSUPPORTED; }
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  if (base + g.pack_bytes > reinterpret_cast<char*>(workspace) + workspace_bytes) {
+    set_error("b200_conv2d_tma: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(g.pack_bytes + 256));
+    return B200_ERR_WORKSPACE;
+  }
+  return launch_conv_tma(d, g, x, base, w_images, bias, residual, y, 0, 1.0f, reinterpret_cast<cudaStream_t>(stream));
+}
+
+/* ---- all-pairs correlation (RAFT CorrBlock level 0, src/models/stage_1/core/corr.py:56-64) as a 1x1 "convolution":
+ * input = fmap2 (pixels p2), weights[co = p1][ci] = fmap1[ci][p1], output [p1][p2].  The reference computes it in
+ * fp32 (fmaps are cast with .float() and TF32 matmul is off by default), so both operands are split into
+ * (hi, lo) fp16 pairs, pre-scaled by 2^4: 3 tensor-core products per element, fp32 accumulation — the same
+ * fp32-grade emulation as the stage-1 MLPs. */
+static void corr_desc(int dim, int H8, int W8, B200ConvDesc* d) {
+  *d = B200ConvDesc{};
+  d->N = 1; d->Cin = dim; d->H = H8; d->W = W8; d->in_c_total = dim; d->in_c_off = 0;
+  d->Cout = H8 * W8; d->KH = 1; d->KW = 1; d->stride = 1; d->pad_h = 0; d->pad_w = 0; d->pad_mode = 0; d->upsample = 1;
+  d->out_c_total = H8 * W8; d->out_c_off = 0; d->act = 0;
+  d->out_scale = 1.0f / sqrtf((float)dim) / 256.0f;       // undo the two 2^4 operand scales
+  d->res_c_total = 0; d->res_c_off = 0;
+}
+
+int64_t b200_corr_build_tc_workspace_bytes(int32_t dim, int32_t H8, int32_t W8) {
+  if (dim <= 0 || H8 < 8 || W8 < 8) return -1;
+  B200ConvDesc d; corr_desc(dim, H8, W8, &d);
+  TmaGeom g;
+  if (tma_geometry(&d, &g) != B200_OK) return -1;
+  return 2 * g.pack_bytes + 2 * (int64_t)g.n_tiles_n * g.n_chunks * g.n_tile * 128 + 1024;
+}
+
+int b200_corr_build_tc(const float* fmap1, const float* fmap2, int32_t dim, int32_t H8, int32_t W8, float* pyramid,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+  B200_REQUIRE(fmap1 && fmap2 && pyramid && workspace && dim > 0 && H8 >= 8 && W8 >= 8, "bad arguments");
+  if (!b200_device_supports_tc()) { set_error("b200_corr_build_tc needs a compute-capability 10.x device"); return B200_ERR_UNSUPPORTED; }
+  B200ConvDesc d; corr_desc(dim, H8, W8, &d);
+  TmaGeom g;
+  if (int rc = tma_geometry(&d, &g)) return rc;
+  const int64_t need = b200_corr_build_tc_workspace_bytes(dim, H8, W8);
+  B200_REQUIRE(workspace_bytes >= need, "b200_corr_build_tc: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  char* images = base + 2 * g.pack_bytes;                  // pack_bytes is a multiple of 128
+  const int HW = H8 * W8;
+  if (int rc = launch_weight_images(&d, g, fmap1, /*co*/ 1, /*ci*/ HW, /*tap*/ 0, 16.0f, 1, images, st)) return rc;
+  if (int rc = launch_conv_tma(&d, g, fmap2, base, images, nullptr, nullptr, pyramid, 1, 16.0f, st)) return rc;
+  return b200_corr_pool_levels(pyramid, H8, W8, stream);
 }
 
 }  // extern "C"

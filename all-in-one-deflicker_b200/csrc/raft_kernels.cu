@@ -81,6 +81,14 @@ int b200_corr_build(const float* fmap1, const float* fmap2, int32_t dim, int32_t
   const int HW = H8 * W8;
   // level 0: corr[p1][p2] = <f1[:, p1], f2[:, p2]> / sqrt(dim)        (corr.py:56-64)
   B200_PROPAGATE(simt_gemm_nn_scaled(fmap1, fmap2, pyramid, HW, HW, dim, 1.0f / sqrtf((float)dim), st));
+  return b200_corr_pool_levels(pyramid, H8, W8, stream);
+}
+
+/* levels 1..3 of the pyramid from level 0: 2x2 average pooling over the target image (corr.py:22-25) */
+int b200_corr_pool_levels(float* pyramid, int32_t H8, int32_t W8, void* stream) {
+  B200_REQUIRE(pyramid && H8 >= 8 && W8 >= 8, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int HW = H8 * W8;
   float* cur = pyramid;
   int h = H8, w = W8;
   for (int l = 1; l < 4; ++l) {

@@ -193,6 +193,14 @@ int64_t b200_corr_pyramid_floats(int32_t H8, int32_t W8);
 int b200_corr_build(const float* fmap1, const float* fmap2, int32_t dim, int32_t H8, int32_t W8,
                     float* pyramid, void* stream);
 /* CorrBlock.__call__ (corr.py:33-54): coords [1][2][H8][W8] (x, y) -> out [1][4*(2r+1)^2][H8][W8] */
+/* levels 1..3 from level 0 (2x2 average pooling over the target image, corr.py:22-25); called by both builders */
+int b200_corr_pool_levels(float* pyramid, int32_t H8, int32_t W8, void* stream);
+/* Tensor-core builder: level 0 on tcgen05 with both feature maps split into (hi, lo) fp16 pairs (3 products per
+ * element, fp32 accumulation: fp32-grade like the reference's fp32 matmul), operands fed by TMA; then the pooling.
+ * workspace: b200_corr_build_tc_workspace_bytes(dim, H8, W8) bytes. */
+int64_t b200_corr_build_tc_workspace_bytes(int32_t dim, int32_t H8, int32_t W8);
+int b200_corr_build_tc(const float* fmap1, const float* fmap2, int32_t dim, int32_t H8, int32_t W8, float* pyramid,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 int b200_corr_lookup(const float* pyramid, const float* coords, float* out, int32_t batch,
                      int32_t H8, int32_t W8, int32_t radius, void* stream);
 

@@ -26,6 +26,19 @@ def test_corr_build_and_lookup(golden_dir):
     got = blk.pyramid.cpu()
     assert got.numel() == flat.numel()
     assert (got - flat).abs().max() <= 1e-4 * flat.abs().max()
+    # both builders (tcgen05 with split fp16 operands = default, fp32 CUDA-core GEMM) to the same fp32-grade bound
+    for impl in ("tc", "simt"):
+        alt = K.corr_build(f1.to(DEV), f2.to(DEV), impl=impl).cpu()
+        err = ((alt - flat).abs().max() / flat.abs().max()).item()
+        print(f"corr_build[{impl}] relative error {err:.2e}")
+        assert err <= 1e-4
+    # a feature map that is not a multiple of the 128-pixel tile, with large and tiny magnitudes
+    g = torch.Generator().manual_seed(3)
+    a1 = torch.randn(1, 256, 19, 37, generator=g) * torch.logspace(-3, 1.5, 256).view(1, 256, 1, 1)
+    a2 = torch.randn(1, 256, 19, 37, generator=g)
+    want = torch.cat([p.reshape(-1) for p in FO.corr_pyramid(a1, a2)])
+    have = K.corr_build(a1.to(DEV), a2.to(DEV), impl="tc").cpu()
+    assert ((have - want).abs().max() / want.abs().max()).item() <= 1e-4
     look = blk(coords.to(DEV)).cpu()
     ref = FO.corr_lookup(pyr, coords)
     assert look.shape == ref.shape == (1, 324, 16, 24)
