@@ -44,7 +44,7 @@ class ConvDesc(C.Structure):
                 ("KW", C.c_int32), ("stride", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
                 ("pad_mode", C.c_int32), ("upsample", C.c_int32), ("out_c_total", C.c_int32),
                 ("out_c_off", C.c_int32), ("act", C.c_int32), ("out_scale", C.c_float),
-                ("res_c_total", C.c_int32), ("res_c_off", C.c_int32)]
+                ("res_c_total", C.c_int32), ("res_c_off", C.c_int32), ("upsample_mode", C.c_int32)]
 
 
 class AtlasConfig(C.Structure):

@@ -1,6 +1,7 @@
 """Thin torch-tensor wrappers over the convolution / RAFT entry points of libb200deflicker.so
 (include/b200_deflicker.h).  CUDA tensors only; every call runs on the current stream."""
 import ctypes as C
+import weakref
 
 import torch
 
@@ -12,7 +13,7 @@ ACT = {"none": 0, "relu": 1, "leaky": 2, "sigmoid": 3, "tanh": 4}
 # summation order), "tc" = tcgen05 with fp16 operands and fp32 accumulation — the operand precision the
 # reference itself uses for these layers (fp16 autocast in RAFT, TF32 cuDNN in stage 2).
 _conv_precision = "fp32"
-_weight_images = {}        # (data_ptr, version, shape) -> packed fp16 images
+_weight_images = {}        # id(weight tensor) -> (weakref to it, {(version, layout): packed fp16 images})
 
 
 def set_conv_precision(mode):
@@ -30,11 +31,17 @@ def conv_precision():
 
 
 def _images_for(d, w, tma):
-    key = (w.data_ptr(), w._version, tuple(w.shape), tma)
-    img = _weight_images.get(key)
+    """Packed weight images, cached per weight TENSOR OBJECT (not per address: a freed tensor's address is reused)
+    and per in-place version.  Pass module parameters themselves (conv.weight) to benefit from the cache."""
+    key = id(w)
+    ent = _weight_images.get(key)
+    if ent is None or ent[0]() is not w:
+        ent = (weakref.ref(w, lambda _r, k=key: _weight_images.pop(k, None)), {})
+        _weight_images[key] = ent
+    sub = (w._version, tma, d.stride)
+    img = ent[1].get(sub)
     if img is None:
-        if len(_weight_images) > 1024:
-            _weight_images.clear()
+        ent[1].clear()
         L = N.lib()
         size_fn, pack_fn = ((L.b200_conv_tma_weight_image_bytes, L.b200_conv_tma_weight_images) if tma else
                             (L.b200_conv_weight_image_bytes, L.b200_conv_weight_images))
@@ -43,7 +50,7 @@ def _images_for(d, w, tma):
             raise N.B200Error("conv weight image size: invalid descriptor: " + N.last_error())
         img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         N.check(pack_fn(C.byref(d), N.ptr(w), N.ptr(img), N.current_stream()), "conv weight images")
-        _weight_images[key] = img
+        ent[1][sub] = img
     return img
 
 
@@ -54,10 +61,24 @@ def _check(t):
 
 
 def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", upsample=1, out=None, out_c_off=0,
-           in_slice=None, residual=None, res_c_off=0, out_scale=1.0, precision=None):
+           in_slice=None, residual=None, res_c_off=0, out_scale=1.0, precision=None, upsample_mode="nearest"):
     """y = act(conv(pad(upsample(x[:, in_slice]))) + b) * out_scale (+ residual[:, res slice]) written into
     out[:, out_c_off:out_c_off+Cout] (allocated when None).  Restates nn.Conv2d / ReflectionPad2d / Upsample."""
     _check(x); _check(w); _check(b); _check(residual)
+    mode = _conv_precision if precision is None else precision
+    bilinear = 0
+    if upsample_mode == "bilinear":
+        if upsample != 2:
+            raise N.B200Error("bilinear upsampling is x2 only")
+        if mode == "tc" and stride in (1, 2):
+            bilinear = 1                                  # fused into the fp16 repack of b200_conv2d_tma
+        else:                                             # explicit nn.Upsample kernel, then a plain convolution
+            if in_slice is not None:
+                x = x[:, in_slice[0]:in_slice[1]].contiguous()
+                in_slice = None
+            x, upsample = upsample_bilinear2(x), 1
+    elif upsample_mode != "nearest":
+        raise N.B200Error(f"unknown upsample mode {upsample_mode!r}")
     n, c_total, h, wd = x.shape
     c_off, cin = (0, c_total) if in_slice is None else (in_slice[0], in_slice[1] - in_slice[0])
     cout, cin_w, kh, kw = w.shape
@@ -71,8 +92,7 @@ def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", ups
     _check(out)
     d = N.ConvDesc(n, cin, h, wd, c_total, c_off, cout, kh, kw, stride, ph, pw, 1 if pad_mode == "reflect" else 0,
                    upsample, out.shape[1], out_c_off, ACT[act], float(out_scale),
-                   residual.shape[1] if residual is not None else 0, res_c_off)
-    mode = _conv_precision if precision is None else precision
+                   residual.shape[1] if residual is not None else 0, res_c_off, bilinear)
     if mode == "tc" and stride in (1, 2):
         nbytes = N.lib().b200_conv_tma_workspace_bytes(C.byref(d))
         if nbytes <= 0:

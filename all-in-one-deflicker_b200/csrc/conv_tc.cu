@@ -310,6 +310,7 @@ int b200_conv_weight_images(const B200ConvDesc* d, const float* w, void* images,
 
 int b200_conv2d_tc(const B200ConvDesc* d, const float* x, const void* w_images, const float* bias,
                    const float* residual, float* y, void* stream) {
+  B200_REQUIRE(d && d->upsample_mode == 0, "bilinear upsampling is fused only by b200_conv2d_tma");
   B200_REQUIRE(d && x && w_images && y, "null pointer");
   B200_REQUIRE(d->N > 0 && d->Cin > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0 && d->stride > 0 &&
                (d->upsample == 1 || d->upsample == 2) && (d->pad_mode == 0 || d->pad_mode == 1) && d->act >= 0 && d->act <= 4,

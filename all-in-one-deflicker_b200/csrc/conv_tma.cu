@@ -276,23 +276,46 @@ __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __res
   const int yy = blockIdx.y, bx = blockIdx.x * 32;
   const int s = d.stride, HU = d.H * d.upsample, WU = d.W * d.upsample;
   {
-    const int lx = threadIdx.x & 31, crow = threadIdx.x >> 5;
+    const int lx_ = threadIdx.x & 31, crow = threadIdx.x >> 5;
     const int Y = yy * s + (phases == 4 ? (ph >> 1) : 0) - d.pad_h;
-    const int X = (bx + lx) * s + (phases == 4 ? (ph & 1) : 0) - d.pad_w;
+    const int X = (bx + lx_) * s + (phases == 4 ? (ph & 1) : 0) - d.pad_w;
     int u = Y, w = X;
     bool ok;
     if (d.pad_mode == 1) {
-      ok = Y >= -d.pad_h && Y < HU + d.pad_h && X >= -d.pad_w && X < WU + d.pad_w && bx + lx < WP2;
+      ok = Y >= -d.pad_h && Y < HU + d.pad_h && X >= -d.pad_w && X < WU + d.pad_w && bx + lx_ < WP2;
       u = tm_reflect(Y, HU); w = tm_reflect(X, WU);
     } else {
       ok = Y >= 0 && Y < HU && X >= 0 && X < WU;
     }
-    if (d.upsample > 1) { u >>= 1; w >>= 1; }
-    const float* src = x + ((int64_t)n * d.in_c_total + d.in_c_off) * d.H * d.W + (int64_t)u * d.W + w;
+    const int64_t plane = (int64_t)d.H * d.W;
+    const float* src0 = x + ((int64_t)n * d.in_c_total + d.in_c_off) * plane;
+    if (d.upsample > 1 && d.upsample_mode == 1) {
+      // bilinear x2, align_corners=True (ATen area_pixel_compute_source_index): src = dst * (in-1)/(out-1)
+      const float sh = HU > 1 ? (float)(d.H - 1) / (float)(HU - 1) : 0.f;
+      const float sw = WU > 1 ? (float)(d.W - 1) / (float)(WU - 1) : 0.f;
+      const float fy = sh * u, fx = sw * w;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < d.H - 1 ? 1 : 0), x1 = x0 + (x0 < d.W - 1 ? 1 : 0);
+      const float ly = fy - y0, lx = fx - x0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = cb * 64 + crow + 8 * i;
-      tile[crow + 8 * i][lx] = (ok && c < d.Cin) ? __ldg(src + (int64_t)c * d.H * d.W) : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int c = cb * 64 + crow + 8 * i;
+        float v = 0.f;
+        if (ok && c < d.Cin) {
+          const float* s = src0 + (int64_t)c * plane;
+          v = (1.f - ly) * ((1.f - lx) * __ldg(s + y0 * d.W + x0) + lx * __ldg(s + y0 * d.W + x1)) +
+              ly * ((1.f - lx) * __ldg(s + y1 * d.W + x0) + lx * __ldg(s + y1 * d.W + x1));
+        }
+        tile[crow + 8 * i][lx_] = v;
+      }
+    } else {
+      if (d.upsample > 1) { u >>= 1; w >>= 1; }
+      const float* src = src0 + (int64_t)u * d.W + w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cb * 64 + crow + 8 * i;
+        tile[crow + 8 * i][lx_] = (ok && c < d.Cin) ? __ldg(src + (int64_t)c * plane) : 0.f;
+      }
     }
   }
   __syncthreads();
@@ -357,7 +380,8 @@ static int tma_geometry(const B200ConvDesc* d, TmaGeom* g) {
   B200_REQUIRE(d, "null descriptor");
   B200_REQUIRE(d->N > 0 && d->Cin > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0 &&
                (d->stride == 1 || d->stride == 2) && (d->upsample == 1 || d->upsample == 2) &&
-               (d->pad_mode == 0 || d->pad_mode == 1) && d->act >= 0 && d->act <= 4 && d->pad_h >= 0 && d->pad_w >= 0,
+               (d->pad_mode == 0 || d->pad_mode == 1) && d->act >= 0 && d->act <= 4 && d->pad_h >= 0 && d->pad_w >= 0 &&
+               (d->upsample_mode == 0 || (d->upsample_mode == 1 && d->upsample == 2)),
                "invalid convolution descriptor (b200_conv2d_tma supports stride 1 and 2)");
   g->HU = d->H * d->upsample; g->WU = d->W * d->upsample;
   B200_REQUIRE(d->pad_mode == 0 || (d->pad_h < g->HU && d->pad_w < g->WU), "reflection padding larger than the input");

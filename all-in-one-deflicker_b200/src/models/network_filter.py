@@ -34,8 +34,8 @@ class UNet(nn.Module):
     @staticmethod
     def _run_block(block, x, out=None, out_c_off=0):
         convs = [m for m in block if isinstance(m, nn.Conv2d)]
-        t = K.conv2d(x, convs[0].weight.detach(), None, pad=1, act="relu")
-        return K.conv2d(t, convs[1].weight.detach(), None, pad=1, act="relu", out=out, out_c_off=out_c_off)
+        t = K.conv2d(x, convs[0].weight, None, pad=1, act="relu")
+        return K.conv2d(t, convs[1].weight, None, pad=1, act="relu", out=out, out_c_off=out_c_off)
 
     @torch.no_grad()
     def forward(self, x):
@@ -54,7 +54,7 @@ class UNet(nn.Module):
         cur = UNet._run_block(self.bottleneck, cur)
         for i, cat in zip((4, 3, 2, 1), reversed(cats)):
             up = getattr(self, f"upconv{i}")[1]
-            big = K.upsample_bilinear2(cur)
-            K.conv2d(big, up.weight.detach(), up.bias.detach(), pad=1, out=cat, out_c_off=0)
+            K.conv2d(cur, up.weight, up.bias.detach(), pad=1, out=cat, out_c_off=0, upsample=2,
+                     upsample_mode="bilinear")
             cur = UNet._run_block(getattr(self, f"decoder{i}"), cat)
-        return K.conv2d(cur, self.conv.weight.detach(), self.conv.bias.detach())
+        return K.conv2d(cur, self.conv.weight, self.conv.bias.detach())

@@ -25,7 +25,7 @@ class ConvLayer(nn.Module):
         if self.norm == "BN":
             raise NotImplementedError("norm='BN' (the only value for which the reference applies a norm) is unused")
         c = self.conv2d
-        return K.conv2d(x, c.weight.detach(), c.bias.detach() if c.bias is not None else None, stride=c.stride[0],
+        return K.conv2d(x, c.weight, c.bias.detach() if c.bias is not None else None, stride=c.stride[0],
                         pad=c.kernel_size[0] // 2, pad_mode="reflect", act=act, upsample=self.upsample or 1, **kw)
 
 
@@ -58,7 +58,11 @@ class ConvLSTM(nn.Module):
             raise NotImplementedError("the stage-2 script always passes prev_state=None "
                                       "(src/neural_filter_and_refinement.py:106)")
         # zero previous hidden state: only the input half of the gate weights contributes
-        w = self.Gates.weight.detach()[:, :self.input_size].contiguous()
+        gw = self.Gates.weight
+        if getattr(self, "_w_in_key", None) != (gw.data_ptr(), gw._version):       # input half, sliced once
+            self._w_in = gw.detach()[:, :self.input_size].contiguous()
+            self._w_in_key = (gw.data_ptr(), gw._version)
+        w = self._w_in
         gates = K.conv2d(x, w, self.Gates.bias.detach(), pad=self.Gates.padding)
         return K.convlstm_zero_state(gates)
 

@@ -9,7 +9,7 @@ from b200 import nn as K
 
 def _folded(conv, norm):
     """conv followed by eval-mode BatchNorm2d == conv with scaled weights / shifted bias."""
-    w, b = conv.weight.detach(), conv.bias.detach()
+    w, b = conv.weight, conv.bias.detach()      # the parameter itself: b200.nn caches its packed images
     if isinstance(norm, nn.BatchNorm2d):
         s = norm.weight.detach() / torch.sqrt(norm.running_var + norm.eps)
         w = (w * s.view(-1, 1, 1, 1)).contiguous()
@@ -88,7 +88,7 @@ class BasicEncoder(nn.Module):
         for layer in (self.layer1, self.layer2, self.layer3):
             for blk in layer:
                 x = blk(x)
-        x = K.conv2d(x, self.conv2.weight.detach(), self.conv2.bias.detach())
+        x = K.conv2d(x, self.conv2.weight, self.conv2.bias.detach())
         if is_list:
             x = torch.split(x, [batch_dim, batch_dim], dim=0)
         return x

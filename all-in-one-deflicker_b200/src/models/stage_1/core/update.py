@@ -10,7 +10,7 @@ from b200 import nn as K
 
 
 def _c(conv, x, act="none", **kw):
-    return K.conv2d(x, conv.weight.detach(), conv.bias.detach() if conv.bias is not None else None,
+    return K.conv2d(x, conv.weight, conv.bias.detach() if conv.bias is not None else None,
                     pad=conv.padding, act=act, **kw)
 
 

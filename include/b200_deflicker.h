@@ -217,6 +217,8 @@ int b200_corr_lookup(const float* pyramid, const float* coords, float* out, int3
 #define B200_ACT_TANH 4
 #define B200_PAD_ZEROS 0
 #define B200_PAD_REFLECT 1
+#define B200_UP_NEAREST 0
+#define B200_UP_BILINEAR_AC 1
 typedef struct B200ConvDesc {
   int32_t N, Cin, H, W;            /* input extent (before the optional nearest upsample)            */
   int32_t in_c_total, in_c_off;    /* input = channels [in_c_off, in_c_off+Cin) of an in_c_total tensor */
@@ -227,6 +229,9 @@ typedef struct B200ConvDesc {
   int32_t act;                     /* B200_ACT_*                                                      */
   float out_scale;
   int32_t res_c_total, res_c_off;  /* residual tensor slice (same spatial size as the output)         */
+  int32_t upsample_mode;           /* with upsample == 2: B200_UP_NEAREST or B200_UP_BILINEAR_AC
+                                      (nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                                      network_filter.py:22 — b200_conv2d_tma only)                     */
 } B200ConvDesc;
 int b200_conv2d(const B200ConvDesc* d, const float* x, const float* w, const float* bias,
                 const float* residual, float* y, void* stream);

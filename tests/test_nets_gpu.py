@@ -223,3 +223,22 @@ def test_networks_with_tc_convolutions(golden_dir):
         assert max(errs.values()) <= 2e-2, errs
     finally:
         K.set_conv_precision(prev)
+
+
+def test_conv_tc_fused_bilinear_upsample():
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) + Conv2d (UNet upconv, network_filter.py:22):
+    fused into the fp16 repack on the tcgen05 path, explicit kernel + fp32 convolution otherwise."""
+    from b200 import nn as K
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 70, 17, 29, generator=g)
+    wt = torch.randn(40, 70, 3, 3, generator=g) / 25.0
+    b = torch.randn(40, generator=g)
+    ref = F.conv2d(F.interpolate(x.double(), scale_factor=2, mode="bilinear", align_corners=True), wt.double(), b.double(),
+                   padding=1)
+    scale = ref.abs().max().item()
+    y32 = K.conv2d(x.to(DEV), wt.to(DEV), b.to(DEV), pad=1, upsample=2, upsample_mode="bilinear", precision="fp32")
+    ytc = K.conv2d(x.to(DEV), wt.to(DEV), b.to(DEV), pad=1, upsample=2, upsample_mode="bilinear", precision="tc")
+    assert y32.shape == ytc.shape == ref.shape
+    assert (y32.cpu().double() - ref).abs().max() <= 2e-5 * scale
+    assert (ytc.cpu().double() - ref).abs().max() <= 4e-3 * scale
