@@ -63,6 +63,69 @@ __global__ void corr_lookup_kernel(LookupArgs a) {
   a.out[((int64_t)b * 4 * taps + l * taps + tap) * plane + pix] = v;
 }
 
+// Tiled variant used for the standard radius 4: one block = 32 consecutive pixels x one level.  The 10x10
+// neighbourhood the 81 bilinear taps of a pixel touch is staged once in shared memory (12x12 with margin) instead
+// of 324 scattered loads; per-tap arithmetic is unchanged (same expressions as corr_lookup_kernel), taps that
+// fall outside the staged window (non-finite or absurd coordinates) read global memory as before.
+constexpr int LKW = 12;
+__global__ void __launch_bounds__(256) corr_lookup_tiled_kernel(LookupArgs a) {
+  __shared__ float win[32][LKW * LKW + 1];
+  __shared__ int s_ox[32], s_oy[32];
+  const int l = blockIdx.y, b = blockIdx.z, r = a.radius, wn = 2 * r + 1, taps = wn * wn;
+  const int64_t plane = (int64_t)a.H1 * a.W1, pix0 = (int64_t)blockIdx.x * 32;
+  const int W = a.LW[l], H = a.LH[l];
+  const float inv = 1.0f / (float)(1 << l);
+  if (threadIdx.x < 32) {
+    const int64_t pix = pix0 + threadIdx.x;
+    float cx = 0.f, cy = 0.f;
+    if (pix < plane) { cx = a.coords[((int64_t)b * 2 + 0) * plane + pix]; cy = a.coords[((int64_t)b * 2 + 1) * plane + pix]; }
+    const float fx = fminf(fmaxf(floorf(cx * inv), -1.0e6f), 1.0e6f), fy = fminf(fmaxf(floorf(cy * inv), -1.0e6f), 1.0e6f);
+    s_ox[threadIdx.x] = (fx == fx ? (int)fx : 0) - r - 1;
+    s_oy[threadIdx.x] = (fy == fy ? (int)fy : 0) - r - 1;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * LKW * LKW; e += 256) {
+    const int p = e / (LKW * LKW), k = e % (LKW * LKW);
+    const int yy = s_oy[p] + k / LKW, xx = s_ox[p] + k % LKW;
+    const int64_t pix = pix0 + p;
+    float v = 0.f;
+    if (pix < plane && xx >= 0 && xx < W && yy >= 0 && yy < H)
+      v = __ldg(a.level[l] + ((int64_t)b * plane + pix) * H * W + (int64_t)yy * W + xx);
+    win[p][k] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * taps; e += 256) {
+    const int p = e & 31, tap = e >> 5;
+    const int64_t pix = pix0 + p;
+    if (pix >= plane) continue;
+    const int i = tap / wn, j = tap % wn;
+    const float cx = a.coords[((int64_t)b * 2 + 0) * plane + pix];
+    const float cy = a.coords[((int64_t)b * 2 + 1) * plane + pix];
+    const float x = cx * inv + (float)(i - r);
+    const float y = cy * inv + (float)(j - r);
+    const float gx = 2.0f * x / (float)(W - 1) - 1.0f, gy = 2.0f * y / (float)(H - 1) - 1.0f;
+    const float ix = ((gx + 1.0f) / 2.0f) * (float)(W - 1), iy = ((gy + 1.0f) / 2.0f) * (float)(H - 1);
+    float* dst = a.out + ((int64_t)b * 4 * taps + l * taps + tap) * plane + pix;
+    if (!isfinite(ix) || !isfinite(iy)) { *dst = nanf(""); continue; }
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float tx = ix - fx0, ty = iy - fy0;
+    float nw, ne, sw, se;
+    const float rx = fx0 - (float)s_ox[p], ry = fy0 - (float)s_oy[p];
+    if (rx >= 0.f && rx <= (float)(LKW - 2) && ry >= 0.f && ry <= (float)(LKW - 2)) {
+      const float* wp = &win[p][(int)ry * LKW + (int)rx];
+      nw = wp[0]; ne = wp[1]; sw = wp[LKW]; se = wp[LKW + 1];
+    } else if (fabsf(fx0) < 1.0e9f && fabsf(fy0) < 1.0e9f) {
+      const int x0 = (int)fx0, y0 = (int)fy0;
+      const float* src = a.level[l] + ((int64_t)b * plane + pix) * H * W;
+      auto at = [&](int yy, int xx) -> float { return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(src + (int64_t)yy * W + xx) : 0.f; };
+      nw = at(y0, x0); ne = at(y0, x0 + 1); sw = at(y0 + 1, x0); se = at(y0 + 1, x0 + 1);
+    } else {
+      nw = ne = sw = se = 0.f;
+    }
+    *dst = nw * ((1.f - tx) * (1.f - ty)) + ne * (tx * (1.f - ty)) + sw * ((1.f - tx) * ty) + se * (tx * ty);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -114,7 +177,11 @@ int b200_corr_lookup(const float* pyramid, const float* coords, float* out, int3
   a.coords = coords; a.out = out; a.B = batch; a.H1 = H8; a.W1 = W8; a.radius = radius;
   const int win = 2 * radius + 1;
   const int64_t total = (int64_t)batch * H8 * W8 * 4 * win * win;
-  corr_lookup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  if (radius <= 4) {
+    corr_lookup_tiled_kernel<<<dim3((unsigned)(((int64_t)H8 * W8 + 31) / 32), 4, batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  } else {
+    corr_lookup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  }
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -64,14 +64,15 @@ class RAFT(nn.Module):
         if flow_init is not None:
             coords1 = coords1 + flow_init
         flow_up, preds = None, []
-        for _ in range(iters):
+        for it in range(iters):
             corr = corr_fn(coords1)
             flow = (coords1 - coords0).contiguous()
             with self._autocast():
                 net, up_mask, delta_flow = self.update_block(net, inp, corr, flow)
             coords1 = coords1 + delta_flow
-            flow_up = K.convex_upsample((coords1 - coords0).contiguous(), up_mask)
-            preds.append(flow_up)
+            if not test_mode or it == iters - 1:          # test mode returns only the last upsampled flow
+                flow_up = K.convex_upsample((coords1 - coords0).contiguous(), up_mask)
+                preds.append(flow_up)
         if test_mode:
             return coords1 - coords0, flow_up
         return preds
