@@ -37,6 +37,7 @@ struct ConvTmaArgs {
   int a_rows, a_stage, n_a, n_b, n_acc, acc_stride;   // box rows, bytes per A stage, ring depths, TMEM ring
   int b_group, b_stage;                                // weight chunks (x taps) per B stage, bytes per B stage
   int split;                                           // 1: both operands are (hi, lo) fp16 pairs, 3 MMAs per product
+  int resident;                                        // 1: the whole weight image stays in shared memory (narrow layers)
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -122,6 +123,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
+      if (a.resident) {                                    // one cout tile, all chunks: loaded once per CTA
+        mbar_expect_tx(&b_full[0], a.n_chunks * b_bytes);
+        for (int j = 0; j < a.n_chunks; ++j) bulk_g2s(sB + j * b_bytes, a.w_img + (int64_t)j * b_bytes, b_bytes, &b_full[0]);
+      }
       for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         const int nt = t % a.n_tiles_n;
         int r = t / a.n_tiles_n;
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
                 tma_load_4d(sA + sa * a.a_stage + a_half, &xmap_lo, cc * 64, xb * 128, oy + (ky >> a.shift), n * a.phases + ph,
                             &a_full[sa]);
               if (++sa == a.n_a) { sa = 0; pha ^= 1; }
+              if (a.resident) continue;
               for (int i0 = 0; i0 < nsub; i0 += a.b_group) {
                 const int gn = nsub - i0 < a.b_group ? nsub - i0 : a.b_group;
                 mbar_wait(&b_empty[sb], phb ^ 1);
@@ -160,11 +166,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
     const bool leader = elect_one();
     int sa = 0, sb = 0, acc = 0;
     uint32_t pha = 0, phb = 0, phd = 0;
+    if (a.resident) mbar_wait(&b_full[0], 0);
+    const uint64_t db_res = desc_hi + (uint64_t)(smem_u32(sB) >> 4);
+    const uint64_t db_step = (uint64_t)(b_bytes >> 4);
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       mbar_wait(&d_empty[acc], phd ^ 1);
       tc_fence_after();
       const uint32_t dcol = tmem + acc * a.acc_stride;
       uint32_t accum = 0;
+      uint64_t db_run = db_res;                            // resident mode: descriptor of the next weight chunk
       for (int ky = 0; ky < d.KH; ++ky)
         for (int xpar = 0; xpar < s && xpar < d.KW; ++xpar) {
           const int nsub = (d.KW - xpar + s - 1) / s;
@@ -173,6 +183,20 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
             const uint32_t pa = smem_u32(sA + sa * a.a_stage);
             const int left = d.Cin - cc * 64;
             const int ksteps = ((left < 64 ? left : 64) + 15) >> 4;
+            if (a.resident) {
+              tc_fence_after();
+              if (leader) {
+                uint64_t da = desc_hi + (uint64_t)(pa >> 4);
+                for (int i = 0; i < nsub; ++i, da += 8, db_run += db_step)
+                  for (int ks = 0; ks < ksteps; ++ks, accum = 1u) mma_ss(dcol, da + 2 * ks, db_run + 2 * ks, idesc, accum);
+                mma_commit(&a_empty[sa]);
+              } else {
+                db_run += db_step * nsub;
+              }
+              __syncwarp();
+              if (++sa == a.n_a) { sa = 0; pha ^= 1; }
+              continue;
+            }
             for (int i0 = 0; i0 < nsub; i0 += a.b_group) {
               const int gn = nsub - i0 < a.b_group ? nsub - i0 : a.b_group;
               mbar_wait(&b_full[sb], phb);
@@ -467,14 +491,24 @@ static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float*
   const int nsub_max = (d->KW + d->stride - 1) / d->stride;
   int b_group = 32768 / b_bytes; if (b_group < 1) b_group = 1; if (b_group > nsub_max) b_group = nsub_max;
   a.b_group = b_group; a.b_stage = b_group * b_bytes;
-  // shared memory: at least 3 B stages (2 for the widest tiles), up to 6 A stages, the rest goes to the B ring
+  // shared memory: at least 3 B stages (2 for the widest tiles), up to 6 A stages, the rest goes to the B ring;
+  // narrow layers keep the whole weight image resident instead (no per-chunk weight traffic or barriers)
   const int avail = TM_SMEM_BUDGET - TM_BAR_BYTES;
-  int n_a = (avail - 3 * a.b_stage) / a.a_stage;
-  if (n_a > 6) n_a = 6;
-  if (n_a < 2) n_a = 2;
-  int n_b = (avail - n_a * a.a_stage) / a.b_stage;
-  if (n_b > TM_MAX_B) n_b = TM_MAX_B;
-  B200_REQUIRE(n_a >= 2 && n_b >= 2, "tile does not fit in shared memory");
+  a.resident = (!split && g.n_tiles_n == 1 && (int64_t)g.n_chunks * b_bytes <= 100 * 1024) ? 1 : 0;
+  int n_a, n_b;
+  if (a.resident) {
+    a.b_group = 1; a.b_stage = b_bytes;
+    n_b = g.n_chunks;                                      // "ring" = the resident image
+    n_a = (avail - n_b * a.b_stage) / a.a_stage;
+    if (n_a > TM_MAX_A) n_a = TM_MAX_A;
+  } else {
+    n_a = (avail - 3 * a.b_stage) / a.a_stage;
+    if (n_a > 6) n_a = 6;
+    if (n_a < 2) n_a = 2;
+    n_b = (avail - n_a * a.a_stage) / a.b_stage;
+    if (n_b > TM_MAX_B) n_b = TM_MAX_B;
+  }
+  B200_REQUIRE(n_a >= 2 && (a.resident || n_b >= 2), "tile does not fit in shared memory");
   a.n_a = n_a; a.n_b = n_b;
   const int cols = (g.n_tile + 31) / 32 * 32;
   a.n_acc = 512 / cols; if (a.n_acc > TM_MAX_ACC) a.n_acc = TM_MAX_ACC; a.n_acc &= ~1;
