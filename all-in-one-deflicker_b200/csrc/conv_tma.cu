@@ -292,7 +292,7 @@ __device__ __forceinline__ int tm_reflect(int i, int n) {
 // phase split applied.  One block = 32 pixels of one row x 64 channels, transposed through shared memory.
 __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __restrict__ x, __half* __restrict__ xp,
                                                               B200ConvDesc d, int HP2, int WP2, int Cp, int phases,
-                                                              float scale, int64_t lo_off) {
+                                                              float scale, int64_t lo_off, int fold_cf) {
   __shared__ float tile[64][33];
   const int cblocks = Cp / 64;
   const int cb = blockIdx.z % cblocks, nph = blockIdx.z / cblocks;
@@ -301,6 +301,20 @@ __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __res
   const int s = d.stride, HU = d.H * d.upsample, WU = d.W * d.upsample;
   {
     const int lx_ = threadIdx.x & 31, crow = threadIdx.x >> 5;
+    if (fold_cf) {
+      // channel slot k = kx * fold_cf + c holds input channel c at x + kx (stride 1, nearest sampling only)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = crow + 8 * i, kx = k / fold_cf, c = k - kx * fold_cf;
+        const int Y = yy - d.pad_h, X = bx + lx_ + kx - d.pad_w;
+        int u = Y, w = X;
+        bool ok = kx < d.KW && c < d.Cin && bx + lx_ < WP2;
+        if (d.pad_mode == 1) { u = tm_reflect(Y, HU); w = tm_reflect(X, WU); ok = ok && Y >= -d.pad_h && Y < HU + d.pad_h; }
+        else ok = ok && Y >= 0 && Y < HU && X >= 0 && X < WU;
+        if (d.upsample > 1) { u >>= 1; w >>= 1; }
+        tile[k][lx_] = ok ? __ldg(x + ((int64_t)n * d.in_c_total + d.in_c_off + c) * d.H * d.W + (int64_t)u * d.W + w) : 0.f;
+      }
+    } else {
     const int Y = yy * s + (phases == 4 ? (ph >> 1) : 0) - d.pad_h;
     const int X = (bx + lx_) * s + (phases == 4 ? (ph & 1) : 0) - d.pad_w;
     int u = Y, w = X;
@@ -341,6 +355,7 @@ __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __res
         tile[crow + 8 * i][lx_] = (ok && c < d.Cin) ? __ldg(src + (int64_t)c * plane) : 0.f;
       }
     }
+    }
   }
   __syncthreads();
   const int px = threadIdx.x >> 3, c8 = threadIdx.x & 7;
@@ -362,15 +377,16 @@ __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __res
 // (w_co, w_ci, w_tap = element strides of the weight tensor; split: chunk = [hi rows | lo rows], values pre-scaled)
 __global__ void conv_tma_weight_images_kernel(const float* __restrict__ w, char* __restrict__ img, int Cout, int Cin,
                                               int KH, int KW, int stride, int n_tile, int n_tiles_n, int cchunks,
-                                              int64_t w_co, int64_t w_ci, int64_t w_tap, float scale, int split) {
-  const int KHW = KH * KW, n_chunks = KHW * cchunks;
+                                              int64_t w_co, int64_t w_ci, int64_t w_tap, float scale, int split,
+                                              int fold_cf) {
+  const int KHW = KH * KW, n_chunks = fold_cf ? KH : KHW * cchunks;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk each
   if (e >= (int64_t)n_tiles_n * n_tile * n_chunks * 8) return;
   const int c8 = (int)(e % 8), j = (int)((e / 8) % n_chunks), grow = (int)(e / (8 * n_chunks));
   const int nt = grow / n_tile, lrow = grow % n_tile, row = nt * n_tile + lrow;
   // chunk j -> (ky, xpar, cc, kx) in the kernel's reduction order
   int tap = 0, cc = 0;
-  {
+  if (!fold_cf) {
     int cnt = 0;
     bool found = false;
     for (int ky = 0; ky < KH && !found; ++ky)
@@ -382,8 +398,13 @@ __global__ void conv_tma_weight_images_kernel(const float* __restrict__ w, char*
   float v[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int ci = cc * 64 + c8 * 8 + q;
-    v[q] = (row < Cout && ci < Cin) ? w[row * w_co + ci * w_ci + tap * w_tap] * scale : 0.f;
+    int ci = cc * 64 + c8 * 8 + q, tp = tap;
+    bool ok = row < Cout;
+    if (fold_cf) {                                         // chunk j = filter row, slot k = kx * fold_cf + c
+      const int kx = ci / fold_cf;
+      ci -= kx * fold_cf; tp = j * KW + kx; ok = ok && kx < KW;
+    }
+    v[q] = (ok && ci < Cin) ? w[row * w_co + ci * w_ci + tp * w_tap] * scale : 0.f;
   }
   uint4 hi, lo;
   split2_f16(v[0], v[1], hi.x, lo.x); split2_f16(v[2], v[3], hi.y, lo.y);
@@ -397,6 +418,7 @@ __global__ void conv_tma_weight_images_kernel(const float* __restrict__ w, char*
 
 struct TmaGeom {
   int HU, WU, OH, OW, phases, shift, HP2, WP2, Cp, cchunks, n_chunks, n_tile, n_tiles_n;
+  int fold_cf;      // > 0: the KW x taps are folded into the channel dimension, fold_cf channels per tap (narrow inputs)
   int64_t pack_bytes;
 };
 
@@ -418,6 +440,15 @@ static int tma_geometry(const B200ConvDesc* d, TmaGeom* g) {
   g->cchunks = (d->Cin + 63) / 64;
   g->n_chunks = d->KH * d->KW * g->cchunks;
   g->Cp = g->cchunks * 64;
+  // narrow inputs (Cin <= 8 for 7-wide filters, <= 16 for 3-wide ...): pack the KW horizontally shifted copies of a
+  // pixel next to each other in its 64-channel vector; the convolution then has KW = 1 and one chunk per filter row
+  g->fold_cf = 0;
+  const int cf = (d->Cin + 7) / 8 * 8;
+  if (d->stride == 1 && d->KW > 1 && cf * d->KW <= 64 && d->upsample_mode == 0) {
+    g->fold_cf = cf;
+    g->WP2 = g->OW;
+    g->n_chunks = d->KH;
+  }
   g->n_tiles_n = (d->Cout + 255) / 256;
   g->n_tile = ((d->Cout + g->n_tiles_n - 1) / g->n_tiles_n + 15) / 16 * 16;
   g->pack_bytes = (int64_t)d->N * g->phases * g->HP2 * g->WP2 * g->Cp * 2;
@@ -445,7 +476,7 @@ static int launch_weight_images(const B200ConvDesc* d, const TmaGeom& g, const f
   const int64_t total = (int64_t)g.n_tiles_n * g.n_tile * g.n_chunks * 8;
   conv_tma_weight_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       w, reinterpret_cast<char*>(images), d->Cout, d->Cin, d->KH, d->KW, d->stride, g.n_tile, g.n_tiles_n, g.cchunks, w_co,
-      w_ci, w_tap, scale, split);
+      w_ci, w_tap, scale, split, g.fold_cf);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -455,7 +486,7 @@ static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float*
                            const float* bias, const float* residual, float* y, int split, float in_scale, cudaStream_t st) {
   B200_REQUIRE(g.HP2 <= 65535 && (int64_t)d->N * g.phases * g.cchunks <= 65535, "input too large for the repack grid");
   conv_pack_input_kernel<<<dim3((g.WP2 + 31) / 32, g.HP2, d->N * g.phases * g.cchunks), 256, 0, st>>>(
-      x, reinterpret_cast<__half*>(base), *d, g.HP2, g.WP2, g.Cp, g.phases, in_scale, split ? g.pack_bytes / 2 : 0);
+      x, reinterpret_cast<__half*>(base), *d, g.HP2, g.WP2, g.Cp, g.phases, in_scale, split ? g.pack_bytes / 2 : 0, g.fold_cf);
   B200_CHECK_LAUNCH();
 
   EncodeTiledFn enc = encode_tiled();
@@ -463,7 +494,8 @@ static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float*
   alignas(64) CUtensorMap map, map_lo;
   const cuuint64_t dims[4] = {(cuuint64_t)g.Cp, (cuuint64_t)g.WP2, (cuuint64_t)g.HP2, (cuuint64_t)d->N * g.phases};
   const cuuint64_t strides[3] = {(cuuint64_t)g.Cp * 2, (cuuint64_t)g.WP2 * g.Cp * 2, (cuuint64_t)g.HP2 * g.WP2 * g.Cp * 2};
-  const int a_rows = 128 + ((d->KW - 1) >> g.shift);
+  const int kw_eff = g.fold_cf ? 1 : d->KW;               // folded: the x taps live in the channel dimension
+  const int a_rows = 128 + ((kw_eff - 1) >> g.shift);
   B200_REQUIRE(a_rows <= 256, "filter too wide");
   const cuuint32_t box[4] = {64, (cuuint32_t)a_rows, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -482,13 +514,14 @@ static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float*
   }
   ConvTmaArgs a{};
   a.d = *d; a.w_img = reinterpret_cast<const char*>(w_images); a.bias = bias; a.res = residual; a.y = y;
+  if (g.fold_cf) { a.d.KW = 1; a.d.Cin = g.fold_cf * d->KW; }
   a.OH = g.OH; a.OW = g.OW; a.x_tiles = (g.OW + 127) / 128; a.cchunks = g.cchunks; a.n_chunks = g.n_chunks;
   a.n_tile = g.n_tile; a.n_tiles_n = g.n_tiles_n; a.phases = g.phases; a.shift = g.shift;
   a.a_rows = a_rows; a.split = split;
   a.a_stage = (a_rows * 128 + 1023) / 1024 * 1024 * (1 + split);
   const int b_bytes = g.n_tile * 128 * (1 + split);
   // x taps that share one activation box are fetched as one bulk copy while that stays <= 32 KB
-  const int nsub_max = (d->KW + d->stride - 1) / d->stride;
+  const int nsub_max = (kw_eff + d->stride - 1) / d->stride;
   int b_group = 32768 / b_bytes; if (b_group < 1) b_group = 1; if (b_group > nsub_max) b_group = nsub_max;
   a.b_group = b_group; a.b_stage = b_group * b_bytes;
   // shared memory: at least 3 B stages (2 for the widest tiles), up to 6 A stages, the rest goes to the B ring;
