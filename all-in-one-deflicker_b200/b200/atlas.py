@@ -239,6 +239,9 @@ class AtlasTrainer:
         if self._ws is None:
             cfg = self._config(True)
             nbytes = int(self.lib.b200_atlas_workspace_bytes(C.byref(cfg)))
+            if cfg.batch < 10000:        # pre_train_mapping always draws 10000 pixels (unwrap_utils.py:183)
+                cfg.batch = 10000
+                nbytes = max(nbytes, int(self.lib.b200_atlas_workspace_bytes(C.byref(cfg))))
             if nbytes < 0:
                 raise N.B200Error(self.lib.b200_last_error().decode())
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -319,12 +322,8 @@ class AtlasTrainer:
         pixels of one frame per step, its own Adam(lr=1e-4) on the mapping block only.  Index draws
         come from the CPU generator in the reference's order (rows, then columns)."""
         larger = max(W, H)
-        B = int(self.cfg["samples_batch"])
-        assert B == 10000 or True
         cfg = self._config(False)
-        cfg.batch = 10000                      # unwrap_utils.py:183 hard-codes 10000
-        if cfg.batch > self.cfg["samples_batch"]:
-            raise N.B200Error("workspace planned for a smaller batch than the pre-training batch of 10000")
+        cfg.batch = 10000                      # unwrap_utils.py:183 hard-codes 10000, whatever samples_batch is
         ws = self._workspace()
         n = self.map_total
         m = torch.zeros(n, dtype=torch.float32, device=self.device)
