@@ -282,7 +282,11 @@ def main():
                 "launches_per_step": {"with_global": per_step[True], "without": per_step[False]},
                 "roofline": {"bound": "tensor", "kernel": kern_name, "achieved": achieved, "peak": peak_tf,
                              "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                             "kernel_ms": k_ms, "peak_source": f"{how} bf16_tflops_sustained", "traffic": None,
+                             "kernel_ms": k_ms, "peak_source": f"{how} bf16_tflops_sustained",
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one tc_fwd_kernel<mapping> launch, from the
+                             # ncu --set full capture in profiles/r1_tc_v1_ncu_full_summary.csv (4.9 MB + 314.1 MB: the fp16
+                             # activation images written for the backward pass; algorithmic image bytes = rows*256*4*5 B)
+                             "traffic": (319.0e6 if precision != N.PREC_FP32 and world == 1 else None),
                              "step_algorithmic_gflop": flop_step / 1e9,
                              "step_tflops": flop_step * value / 1e12},
                 "clocks": sampler.summary() if sampler else None,
