@@ -5,9 +5,10 @@
             one update-block iteration, and a whole frame pair (20 iterations, both kernels + encoders)
   config 5  stage 2 at 1088 x 1920: UNet neural filter and TransformNet local refinement, frames/s
 
-Each number is CUDA-event time of OUR kernels through the C ABI; `torch_eager` is the oracle restatement
-(plain torch ops = cuBLAS/cuDNN) on the same GPU for orientation.  One JSON line.
-    python bench_aux.py [--small]
+Each number is CUDA-event time of OUR kernels through the C ABI.  With --with-eager the same operators are also
+timed as plain torch ops (cuBLAS/cuDNN) on the same GPU for orientation: that leg runs the oracle restatement
+and therefore lives under tests/ (tests/perf/eager_aux.py).  One JSON line.
+    python bench_aux.py [--small] [--conv tc|fp32] [--with-eager]
 """
 import argparse
 import json
@@ -20,7 +21,6 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "all-in-one-deflicker_b200"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def timed(fn, iters=3, warm=1):
@@ -40,12 +40,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--small", action="store_true", help="quarter resolution (quick check)")
     ap.add_argument("--conv", choices=["fp32", "tc"], default="tc", help="convolution arithmetic (b200.nn)")
+    ap.add_argument("--with-eager", action="store_true", help="also time torch-eager restatements (tests/perf/eager_aux.py)")
     args = ap.parse_args()
     from b200 import nn as K
     K.set_conv_precision(args.conv)
-    from nets_common import seeded_weights
-    from oracle import flow_oracle as FO
-    from oracle import stage2_oracle as SO
+    eager = None
+    if args.with_eager:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "perf"))
+        import eager_aux as eager
     from src.models.network_filter import UNet
     from src.models.network_local import TransformNet
     from src.models.stage_1.core.raft import RAFT
@@ -69,16 +71,8 @@ def main():
     coords = (torch.stack([xs, ys])[None] + torch.randn(1, 2, h8, w8, generator=g)).to(dev)
     ms = timed(lambda: K.corr_lookup(pyr[0], coords), iters=5)
     out["corr_lookup"] = {"ms": ms, "taps_per_s": hw * 324 * 4 / ms * 1e3}
-    # torch eager reference for the same two operators
-    def ref_build(): return FO.corr_pyramid(f1, f2)
-    try:
-        ms_ref = timed(ref_build, iters=2)
-        rp = FO.corr_pyramid(f1, f2)
-        ms_ref_l = timed(lambda: FO.corr_lookup([p.to(dev) for p in rp], coords), iters=3)
-        out["torch_eager_corr"] = {"build_ms": ms_ref, "lookup_ms": ms_ref_l}
-        del rp
-    except Exception as e:      # noqa: BLE001
-        out["torch_eager_corr"] = {"error": str(e)[:100]}
+    if eager:
+        out["torch_eager_corr"] = eager.corr(timed, f1, f2, coords)
     # ---------------- update block, one iteration
     ub = BasicUpdateBlock(types.SimpleNamespace(corr_levels=4, corr_radius=4), hidden_dim=128).to(dev)
     net = torch.tanh(torch.randn(1, 128, h8, w8, generator=g)).to(dev)
@@ -87,10 +81,8 @@ def main():
     corr = K.corr_lookup(pyr[0], coords)
     ms = timed(lambda: ub(net, inp, corr, flow), iters=3)
     out["update_block_iter"] = {"ms": ms, "tflops": 2 * 3.118e6 * hw / ms / 1e9}
-    sd = {k: v.detach() for k, v in ub.state_dict().items()}
-    with torch.no_grad():
-        ms_ref = timed(lambda: FO.update_block(sd, net, inp, corr, flow), iters=3)
-    out["torch_eager_update_block_iter_ms"] = ms_ref
+    if eager:
+        out["torch_eager_update_block_iter_ms"] = eager.update_block(timed, ub, net, inp, corr, flow)
     del pyr, corr
     torch.cuda.empty_cache()
     # ---------------- whole pair
@@ -113,11 +105,8 @@ def main():
     out["stage2"] = {"unet_ms": ms_u, "transformnet_ms": ms_t, "frames_per_s": 1000.0 / (ms_u + ms_t),
                      "unet_tflops": 2 * 524e9 * (Hp * Wp) / (1088 * 1920) / ms_u / 1e9,
                      "transformnet_tflops": 2 * 559e9 * (Hp * Wp) / (1088 * 1920) / ms_t / 1e9}
-    usd = {k: v.detach() for k, v in unet.state_dict().items()}
-    tsd = {k: v.detach() for k, v in tn.state_dict().items()}
-    with torch.no_grad():
-        out["torch_eager_stage2"] = {"unet_ms": timed(lambda: SO.unet_forward(usd, x6), iters=2),
-                                     "transformnet_ms": timed(lambda: SO.transformnet_forward(tsd, x12), iters=2)}
+    if eager:
+        out["torch_eager_stage2"] = eager.stage2(timed, unet, tn, x6, x12)
     print(json.dumps(out))
 
 

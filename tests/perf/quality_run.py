@@ -3,7 +3,7 @@ tensor-core path and with the fp32 CUDA-core path from identical initial weights
 streams, render every frame, PSNR(input, reconstruction) as evaluate.py:740-743; plus a short
 side-by-side of the loss trajectory against the oracle on the CPU starting from the same state.
 
-    python tools/quality_run.py [--iters 3000] [--oracle-iters 120]
+    python tests/perf/quality_run.py [--iters 3000] [--oracle-iters 120]
 """
 import argparse
 import json
@@ -14,7 +14,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "all-in-one-deflicker_b200"))
 from b200 import _native as N, atlas as A, synth          # noqa: E402
 from oracle import atlas_oracle as O                         # noqa: E402

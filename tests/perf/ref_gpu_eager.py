@@ -3,7 +3,7 @@ ops as the reference, bit-identical on CPU) with the networks on cuda and the vi
 CPU exactly as the reference keeps them (gathers on the host, ~10 H2D copies per iteration).
 Baseline measurement only; not part of the product.
 
-    python tools/ref_gpu_eager.py [--iters 100]
+    python tests/perf/ref_gpu_eager.py [--iters 100]
 """
 import argparse
 import json
@@ -13,7 +13,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "all-in-one-deflicker_b200"))
 from b200 import synth                                   # noqa: E402
 from oracle import atlas_oracle as O                     # noqa: E402
