@@ -55,6 +55,22 @@ class RAFT(nn.Module):
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         with self._autocast():
             fmap1, fmap2 = self.fnet([image1, image2])
+        return self._refine(fmap1, fmap2, image1, iters, flow_init, test_mode)
+
+    @torch.no_grad()
+    def forward_both(self, image1, image2, iters=12):
+        """Flow 1->2 and 2->1 of one frame pair with the feature encoder run once (the
+        reference's pre-pass, preprocess_optical_flow.py:29-30, calls the model twice and re-encodes both frames).
+        Each direction is exactly `forward(a, b, iters, test_mode=True)`: same feature maps, same arithmetic."""
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        with self._autocast():
+            fmap1, fmap2 = self.fnet([image1, image2])
+        out12 = self._refine(fmap1, fmap2, image1, iters, None, True)
+        out21 = self._refine(fmap2, fmap1, image2, iters, None, True)
+        return out12, out21
+
+    def _refine(self, fmap1, fmap2, image1, iters, flow_init, test_mode):
         corr_fn = CorrBlock(fmap1.float(), fmap2.float(), radius=self.args.corr_radius)
         with self._autocast():
             cnet = self.cnet(image1)

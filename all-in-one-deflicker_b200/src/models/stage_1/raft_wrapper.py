@@ -44,3 +44,10 @@ class RAFTWrapper():
         im1, im2 = padder.pad(im1, im2)
         _, flow12 = self.model(im1, im2, iters=20, test_mode=True)
         return flow12[0].permute(1, 2, 0).detach().cpu().numpy()
+
+    def compute_flow_both(self, im1, im2):
+        """(flow 1->2, flow 2->1), identical to two compute_flow calls but with the feature encoder run once."""
+        padder = InputPadder(im1.shape)
+        im1, im2 = padder.pad(im1, im2)
+        (_, f12), (_, f21) = self.model.forward_both(im1, im2, iters=20)
+        return tuple(f[0].permute(1, 2, 0).detach().cpu().numpy() for f in (f12, f21))

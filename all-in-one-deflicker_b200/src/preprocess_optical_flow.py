@@ -23,8 +23,9 @@ def preprocess(args):
         o12, o21 = out_dir / f'{f1.name}_{f2.name}.npy', out_dir / f'{f2.name}_{f1.name}.npy'
         if not o12.exists() and not o21.exists():
             im1, im2 = wrapper.load_images(str(f1), str(f2))
-            np.save(o12, wrapper.compute_flow(im1, im2))
-            np.save(o21, wrapper.compute_flow(im2, im1))
+            flow12, flow21 = wrapper.compute_flow_both(im1, im2)      # one feature-encoder pass for both directions
+            np.save(o12, flow12)
+            np.save(o21, flow21)
 
 
 if __name__ == '__main__':

@@ -242,3 +242,19 @@ def test_conv_tc_fused_bilinear_upsample():
     assert y32.shape == ytc.shape == ref.shape
     assert (y32.cpu().double() - ref).abs().max() <= 2e-5 * scale
     assert (ytc.cpu().double() - ref).abs().max() <= 4e-3 * scale
+
+
+def test_raft_both_directions_share_the_encoder(golden_dir):
+    """forward_both (one fnet pass) == two independent forward calls, bit for bit."""
+    import argparse
+    from src.models.stage_1.core.raft import RAFT
+    fx = torch.load(os.path.join(golden_dir, "raft_full.pt"))
+    model = RAFT(argparse.Namespace(small=False, mixed_precision=True))
+    model.load_state_dict(seeded_weights(fx["shapes"], fx["seed"]), strict=False)
+    model = model.to(DEV).eval()
+    a, b = fx["im1"].to(DEV), fx["im2"].to(DEV)
+    (lo12, up12), (lo21, up21) = model.forward_both(a, b, iters=3)
+    r12 = model(a, b, iters=3, test_mode=True)
+    r21 = model(b, a, iters=3, test_mode=True)
+    assert torch.equal(up12, r12[1]) and torch.equal(lo12, r12[0])
+    assert torch.equal(up21, r21[1]) and torch.equal(lo21, r21[0])
