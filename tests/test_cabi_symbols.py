@@ -61,3 +61,39 @@ def test_frame_ranges_partition_the_video():
             assert spans[0][0] == 0 and spans[-1][1] == T
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _conv_desc(n, cin, h, w, cout, kh, kw, stride=1, pad=(0, 0), pad_mode=0, upsample=1, up_mode=0):
+    return N.ConvDesc(n, cin, h, w, cin, 0, cout, kh, kw, stride, pad[0], pad[1], pad_mode, upsample, cout, 0, 0, 1.0, 0, 0,
+                      up_mode)
+
+
+def test_conv_tma_geometry_host_side():
+    """Workspace / weight-image sizes of the TMA convolution are closed-form functions of the descriptor
+    (conv_tma.cu tma_geometry): fp16 NHWC repack with channels padded to 64, padding / upsampling / stride-2
+    phases materialised; images = cout tiles x chunks x n_tile rows x 128 B."""
+    lib = N.lib()
+    # 3x3, pad 1, 128 -> 128 at 24x40: HP=26, WP=42, Cp=128; chunks = 3*3*2, n_tile = 128
+    d = _conv_desc(1, 128, 24, 40, 128, 3, 3, pad=(1, 1))
+    assert lib.b200_conv_tma_workspace_bytes(C.byref(d)) == 26 * 42 * 128 * 2 + 256
+    assert lib.b200_conv_tma_weight_image_bytes(C.byref(d)) == 18 * 128 * 128
+    # stride 2 (4 pixel phases): HP2 = ceil(32/2), WP2 = ceil(46/2), Cp = 64; 9 chunks, n_tile = 64
+    d = _conv_desc(1, 32, 30, 44, 64, 3, 3, stride=2, pad=(1, 1), pad_mode=1)
+    assert lib.b200_conv_tma_workspace_bytes(C.byref(d)) == 4 * 16 * 23 * 64 * 2 + 256
+    assert lib.b200_conv_tma_weight_image_bytes(C.byref(d)) == 9 * 64 * 128
+    # narrow input, 7x7: x taps folded into the channels (8 per tap): packed width = OW, one chunk per filter row
+    d = _conv_desc(2, 6, 33, 47, 32, 7, 7, pad=(3, 3), pad_mode=1)
+    assert lib.b200_conv_tma_workspace_bytes(C.byref(d)) == 2 * 39 * 47 * 64 * 2 + 256
+    assert lib.b200_conv_tma_weight_image_bytes(C.byref(d)) == 7 * 32 * 128
+    # Cout 576 -> 3 cout tiles of 192; x2 nearest upsampling doubles the repacked extent
+    d = _conv_desc(1, 256, 16, 24, 576, 1, 1)
+    assert lib.b200_conv_tma_weight_image_bytes(C.byref(d)) == 3 * 4 * 192 * 128
+    d = _conv_desc(1, 64, 20, 28, 32, 3, 3, pad=(1, 1), pad_mode=1, upsample=2)
+    assert lib.b200_conv_tma_workspace_bytes(C.byref(d)) == 42 * 58 * 64 * 2 + 256
+    # invalid descriptors are refused on the host
+    for bad in (_conv_desc(1, 8, 8, 8, 8, 3, 3, stride=3), _conv_desc(1, 8, 8, 8, 8, 3, 3, pad=(9, 9), pad_mode=1),
+                _conv_desc(1, 8, 8, 8, 8, 3, 3, upsample=1, up_mode=1), _conv_desc(0, 8, 8, 8, 8, 3, 3)):
+        assert lib.b200_conv_tma_workspace_bytes(C.byref(bad)) == -1
+    assert lib.b200_corr_build_tc_workspace_bytes(256, 135, 240) > 2 * 135 * 240 * 256 * 2
+    assert lib.b200_corr_build_tc_workspace_bytes(256, 4, 240) == -1
+    assert lib.b200_corr_pyramid_floats(16, 24) == 384 * (384 + 96 + 24 + 6)
