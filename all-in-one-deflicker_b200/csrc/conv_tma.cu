@@ -546,7 +546,9 @@ static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float*
   const int cols = (g.n_tile + 31) / 32 * 32;
   a.n_acc = 512 / cols; if (a.n_acc > TM_MAX_ACC) a.n_acc = TM_MAX_ACC; a.n_acc &= ~1;
   a.acc_stride = 512 / a.n_acc;
-  const int smem_bytes = n_a * a.a_stage + n_b * a.b_stage + TM_BAR_BYTES;
+  int smem_bytes = n_a * a.a_stage + n_b * a.b_stage + TM_BAR_BYTES;
+  // each CTA allocates all 512 TMEM columns: never let two CTAs share an SM (a second tcgen05.alloc would wait forever)
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   const int64_t tiles = (int64_t)d->N * g.OH * a.x_tiles * g.n_tiles_n;
   B200_REQUIRE(tiles < (1ll << 31), "too many tiles");
   a.total_tiles = (int)tiles;
