@@ -14,6 +14,20 @@ def _c(conv, x, act="none", **kw):
                     pad=conv.padding, act=act, **kw)
 
 
+def _merged(owner, name, convs):
+    """Weights / biases of convolutions that read the SAME input with the same geometry and activation, stacked
+    along Cout so that they run as one launch (each output channel is still its own dot product: results are
+    unchanged).  Cached on the module, rebuilt when a source parameter is replaced or modified in place."""
+    key = tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+    cache = owner.__dict__.setdefault("_merged_cache", {})
+    ent = cache.get(name)
+    if ent is None or ent[0] != key:
+        ent = (key, torch.cat([c.weight.detach() for c in convs], 0).contiguous(),
+               torch.cat([c.bias.detach() for c in convs], 0).contiguous())
+        cache[name] = ent
+    return ent[1], ent[2]
+
+
 class FlowHead(nn.Module):
     def __init__(self, input_dim=128, hidden_dim=256):
         super().__init__()
@@ -38,8 +52,10 @@ class SepConvGRU(nn.Module):
         hx[:, c:] = x                                           # the x half of both concats never changes
         for tag in ("1", "2"):
             hx[:, :c] = h
-            z = _c(getattr(self, "convz" + tag), hx, "sigmoid")
-            r = _c(getattr(self, "convr" + tag), hx, "sigmoid")
+            cz, cr = getattr(self, "convz" + tag), getattr(self, "convr" + tag)
+            w, b = _merged(self, "zr" + tag, (cz, cr))          # z and r gates: one convolution, Cout = 2c
+            zr = K.conv2d(hx, w, b, pad=cz.padding, act="sigmoid")
+            z, r = zr[:, :c].contiguous(), zr[:, c:].contiguous()   # views for batch 1
             K.gru_gate(r, h, out=hx, mode=0)                    # [r*h, x]
             q = _c(getattr(self, "convq" + tag), hx, "tanh")
             h = K.gru_gate(z, h, q, mode=1)                     # (1-z)*h + z*q
@@ -80,6 +96,9 @@ class BasicUpdateBlock(nn.Module):
     def forward(self, net, inp, corr, flow, upsample=True):
         motion = self.encoder(flow, corr)
         net = self.gru(net, torch.cat([inp, motion], dim=1))
-        delta_flow = self.flow_head(net)
-        mask = _c(self.mask[2], _c(self.mask[0], net, "relu"), out_scale=0.25)     # .25 * mask head
+        # flow head and mask head both start with a 3x3 128->256 ReLU convolution of `net`: one launch, Cout = 512
+        w, b = _merged(self, "heads", (self.flow_head.conv1, self.mask[0]))
+        hm = K.conv2d(net, w, b, pad=self.mask[0].padding, act="relu")
+        delta_flow = _c(self.flow_head.conv2, hm, in_slice=(0, 256))
+        mask = _c(self.mask[2], hm, in_slice=(256, 512), out_scale=0.25)           # .25 * mask head
         return net, mask, delta_flow
