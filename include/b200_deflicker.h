@@ -14,6 +14,9 @@
  *     capturable: no allocation, no synchronisation, no host read-back inside any call;
  *   - return value 0 = success, otherwise a B200_ERR_* code; b200_last_error() returns a
  *     thread-local message; no exceptions cross the ABI;
+ *   - one host thread per GPU / process drives the library (the reference's own model: one Python
+ *     process per device); the small host-side caches (device tables, kernel attributes, the TMA
+ *     descriptor encoder) are not synchronised;
  *   - floating point is fp32 in memory everywhere.  `precision` selects how the 256-wide Linear
  *     layers are contracted: B200_PREC_FP32 = CUDA-core FFMA (bit-for-bit an fp32 GEMM),
  *     B200_PREC_TC = tcgen05 tensor cores on a 2-term fp16 split of both operands (22-bit
