@@ -41,10 +41,14 @@ class RAFTWrapper():
             pixels = cv2.resize(pixels, (int(cols // shrink), int(rows // shrink)), interpolation=cv2.INTER_AREA)
         return torch.from_numpy(pixels).permute(2, 0, 1).float()
 
+    def load_image_list(self, image_files):
+        """Sorted file names -> one (N, 3, H, W) batch on the device, padded to multiples of 8."""
+        batch = torch.stack([self.load_image(f) for f in sorted(image_files)], dim=0).to(device)
+        batch, = InputPadder(batch.shape).pad(batch)
+        return batch
+
     def load_images(self, fn1, fn2):
-        first, second = sorted([fn1, fn2])
-        pair = torch.stack([self.load_image(first), self.load_image(second)], dim=0).to(device)
-        pair, = InputPadder(pair.shape).pad(pair)
+        pair = self.load_image_list([fn1, fn2])
         return pair[0:1], pair[1:2]
 
     def _padded(self, im1, im2):
