@@ -336,3 +336,27 @@ def test_full_size_properties(golden_dir, T, H, W):
         del part
     assert (acc[:-8] - g1).norm() <= 2e-4 * g1.norm()
     np.testing.assert_allclose(acc[-8:-2].cpu().numpy(), l1[:6], rtol=1e-4)
+
+
+def test_empty_flow_sets_give_nan_loss_values(golden_dir):
+    """No valid flow sample in the batch: the reference takes the mean of an empty tensor (loss_utils.py:299-356),
+    so the flow term and the total are NaN as VALUES (the oracle's gradients stay finite: no element carries the
+    0/0).  Same here: NaN in the loss vector, zero counts, the other four terms equal to the oracle's.
+    (Gradients are not compared on this video: its random flows make the rigidity terms ~1e3 per sample and the
+    bias sums cancel to ~1e-2 of their addends, so fp32 summation order dominates any per-entry bound.)"""
+    H, W, T, B = 24, 40, 6, 200
+    data = synth.throughput_set(H, W, T, seed=2)
+    data["mask_fwd"].zero_(); data["mask_bwd"].zero_()
+    inds = torch.randint(H * W * T, (B, 1), generator=torch.Generator().manual_seed(5))
+    tr = _trainer(data, golden_dir, B)
+    tr.indices.copy_(inds.reshape(-1))
+    tr.loss_grad(True)
+    torch.cuda.synchronize()
+    mp, ap = _params(golden_dir)
+    with torch.no_grad():
+        terms = O.iteration_losses(O.Video(**data), mp, ap, inds, 0)
+    assert np.isnan(float(terms["flow"])) and np.isnan(float(terms["total"]))
+    losses = tr.losses.cpu().numpy()
+    assert np.isnan(losses[0]) and np.isnan(losses[5]) and losses[6] == 0 and losses[7] == 0
+    ref = [float(terms[k]) for k in ("rgb", "gradient", "rigidity", "rigidity_global")]
+    np.testing.assert_allclose(losses[1:5], ref, rtol=5e-4)

@@ -52,6 +52,11 @@ def test_workspace_sizes_are_positive_and_monotone():
     assert 0 < a < b
     assert lib.b200_render_workspace_bytes(1000) > 0
     assert lib.b200_render_workspace_bytes(0) == -1
+    # the plan takes at most 16384 samples per iteration; one more is refused with a message, not truncated
+    edge = N.AtlasConfig(16384, 1, N.PREC_TC, 768, 0.8, 1, 100, 5000, 1000, 1, 5, 500)
+    over = N.AtlasConfig(16385, 1, N.PREC_TC, 768, 0.8, 1, 100, 5000, 1000, 1, 5, 500)
+    assert lib.b200_atlas_workspace_bytes(C.byref(edge)) > b
+    assert lib.b200_atlas_workspace_bytes(C.byref(over)) == -1 and b"16384" in lib.b200_last_error()
 
 
 def test_frame_ranges_partition_the_video():
