@@ -1,4 +1,4 @@
-"""N>1 host logic on CPU (gloo, world_size 2): the frame-sharded formulation — every rank sees the
+"""N>1 host logic on CPU (gloo, world_size 2 and 4): the frame-sharded formulation — every rank sees the
 same index batch, keeps the samples whose frame it owns, normalises by the GLOBAL batch / GLOBAL
 flow-row counts, and one SUM all-reduce of (gradients ‖ loss vector) reproduces the unsharded
 iteration.  The per-rank arithmetic here is the oracle; the CUDA path implements the same
@@ -80,11 +80,13 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_frame_sharding_reproduces_single_rank():
+@pytest.mark.parametrize("world", [2, 4])
+def test_frame_sharding_reproduces_single_rank(world):
+    """world 4 on the 6-frame golden video gives ragged frame blocks (2, 2, 1, 1 frames)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + 7 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs: p.start()
     got = q.get(timeout=240)
     for p in procs: p.join(60)
