@@ -21,12 +21,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "all-in-one-deflicker_b200"))
 REF = "/root/reference"
-sys.path.insert(0, REF)
 sys.modules.setdefault("imageio", types.ModuleType("imageio"))
 
-from src.models.stage_1.implicit_neural_networks import IMLP, positionalEncoding_vec  # noqa: E402
-from src.models.stage_1 import loss_utils as ref_loss  # noqa: E402
-from src.models.stage_1 import unwrap_utils as ref_unwrap  # noqa: E402
+
+def _load_reference(name, rel):
+    """Reference modules are loaded BY FILE PATH: the repo's own mirror package is also called `src`, and a
+    regular package on sys.path would shadow the reference's namespace package.  The three modules have no
+    intra-package imports, so this is exactly the code the reference runs."""
+    import importlib.util
+    path = os.path.join(REF, rel)
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert os.path.realpath(mod.__file__).startswith(REF + os.sep), mod.__file__
+    return mod
+
+
+_ref_inn = _load_reference("ref_implicit_neural_networks", "src/models/stage_1/implicit_neural_networks.py")
+ref_loss = _load_reference("ref_loss_utils", "src/models/stage_1/loss_utils.py")
+ref_unwrap = _load_reference("ref_unwrap_utils", "src/models/stage_1/unwrap_utils.py")
+IMLP, positionalEncoding_vec = _ref_inn.IMLP, _ref_inn.positionalEncoding_vec
 
 from oracle import atlas_oracle as O  # noqa: E402
 from b200 import synth  # noqa: E402
