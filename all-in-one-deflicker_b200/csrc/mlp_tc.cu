@@ -25,6 +25,10 @@
 // Restates nn.Linear/ReLU/tanh/skip-concat forward+autograd of
 //   src/models/stage_1/implicit_neural_networks.py:62-81 for the two networks of
 //   src/stage1_neural_atlas.py:112-128.
+#include <memory>
+#include <mutex>
+#include <vector>
+
 #include "tc_api.cuh"
 #include "tc_ptx.cuh"
 #include "loss_math.h"
@@ -1059,7 +1063,12 @@ static int sm_count() {
 }
 
 static int ensure_attrs() {
-  static bool done = false;
+  // cudaFuncSetAttribute is per device: remember which devices of this process have been configured
+  static bool done_dev[64] = {};
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  B200_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  bool& done = done_dev[dev];
   if (done) return B200_OK;
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
@@ -1073,20 +1082,27 @@ static int ensure_attrs() {
 // Job / item tables depend only on pointers and geometry: built by one eager call per (workspace, row
 // geometry, parameter buffers), kept in device memory, reused inside captured graphs.
 struct HostTables {
+  int key_dev = -1;
   const void* key_base = nullptr; int key_cap = 0, key_groups = 0; const void* key_params = nullptr;
   const void* key_grads = nullptr; bool key_atlas = false;
   PrepJobs* d_prep = nullptr; WgradItems* d_wg = nullptr;
   int n_wg = 0, n_prep = 0;
 };
-constexpr int MAX_TABLES = 16;
-static HostTables g_tabs[MAX_TABLES];
-static int g_n_tabs = 0;
+// Captured graphs bake a slot's device pointers in, so a slot is NEVER recycled: the list only grows (each entry
+// is ~50 KB of device memory; one entry per (device, workspace, row geometry, parameter buffers)).
+constexpr int MAX_TABLES = 4096;
+static std::vector<HostTables*> g_tabs;
+static std::mutex g_tabs_mutex;
+
+static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 
 static HostTables* find_tables(const TcStep& s) {
   const bool atlas = s.y_atlas != nullptr;
-  for (int i = 0; i < g_n_tabs; ++i) {
-    HostTables& t = g_tabs[i];
-    if (t.key_base == s.plan->base && t.key_cap == s.cap && t.key_groups == s.n_groups && t.key_params == s.params &&
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_tabs_mutex);
+  for (size_t i = 0; i < g_tabs.size(); ++i) {
+    HostTables& t = *g_tabs[i];
+    if (t.key_dev == dev && t.key_base == s.plan->base && t.key_cap == s.cap && t.key_groups == s.n_groups && t.key_params == s.params &&
         t.key_grads == s.grads && t.key_atlas == atlas)
       return &t;
   }
@@ -1109,13 +1125,17 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
   }
   B200_REQUIRE(s.as->L == 8 && s.ms->L == 6 && s.as->skip[4] && s.as->skip[7] && s.as->pe == 10 && s.ms->pe == 0 &&
                s.as->hidden == HID && s.ms->hidden == HID, "tensor-core path is specialised to the two stage-1 networks");
-  if (g_n_tabs == MAX_TABLES) g_n_tabs = 0;          // recycle (device buffers are reused)
-  HostTables& tab = g_tabs[g_n_tabs];
-  if (!tab.d_prep) {
-    B200_CHECK_CUDA(cudaMalloc(&tab.d_prep, sizeof(PrepJobs)));
-    B200_CHECK_CUDA(cudaMalloc(&tab.d_wg, sizeof(WgradItems)));
+  {
+    std::lock_guard<std::mutex> lock(g_tabs_mutex);
+    B200_REQUIRE((int)g_tabs.size() < MAX_TABLES, "too many distinct tensor-core workspaces in one process (%d)",
+                 MAX_TABLES);
   }
-  static PrepJobs pj; static WgradItems wi;
+  std::unique_ptr<HostTables> tab_owner(new HostTables());
+  HostTables& tab = *tab_owner;
+  B200_CHECK_CUDA(cudaMalloc(&tab.d_prep, sizeof(PrepJobs)));
+  B200_CHECK_CUDA(cudaMalloc(&tab.d_wg, sizeof(WgradItems)));
+  std::unique_ptr<PrepJobs> pj_owner(new PrepJobs()); std::unique_ptr<WgradItems> wi_owner(new WgradItems());
+  PrepJobs& pj = *pj_owner; WgradItems& wi = *wi_owner;
   pj.n = 0; wi.n = 0;
   const float* pm = s.params;
   const float* pa = s.params + s.ms->total;
@@ -1217,9 +1237,12 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
   B200_CHECK_CUDA(cudaStreamSynchronize(st));
   tab.n_wg = wi.n; tab.n_prep = pj.n;
   tab.key_base = s.plan->base; tab.key_cap = s.cap; tab.key_groups = s.n_groups; tab.key_params = s.params;
-  tab.key_grads = s.grads; tab.key_atlas = atlas;
-  ++g_n_tabs;
-  *out = &tab;
+  tab.key_grads = s.grads; tab.key_atlas = atlas; tab.key_dev = current_device();
+  {
+    std::lock_guard<std::mutex> lock(g_tabs_mutex);
+    g_tabs.push_back(tab_owner.release());
+    *out = g_tabs.back();
+  }
   return B200_OK;
 }
 

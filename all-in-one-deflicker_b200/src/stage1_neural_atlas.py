@@ -83,10 +83,12 @@ if __name__ == "__main__":
     args = parser.parse_args()
     os.environ["CUDA_VISIBLE_DEVICES"] = "%d" % args.gpu
     args.vid_path = os.path.join(args.root, args.vid_name)
-    flow_dir = args.vid_path.rstrip("/") + "_flow"
-    if not os.path.isdir(flow_dir):
-        cmd = "python %s --vid-path %s --gpu %d " % (os.path.join(HERE, "preprocess_optical_flow.py"), args.vid_path, args.gpu)
-        print(cmd)
-        subprocess.call(cmd, shell=True)
+    # always run the pre-pass (reference :276-278): it skips the pairs whose files already exist, so a partially
+    # written flow folder is completed instead of crashing later in load_input_data_single
+    cmd = "%s %s --vid-path %s --gpu %d " % (sys.executable, os.path.join(HERE, "preprocess_optical_flow.py"),
+                                             args.vid_path, args.gpu)
+    print(cmd)
+    if subprocess.call(cmd, shell=True) != 0:
+        raise RuntimeError("optical-flow pre-pass failed")
     with open(os.path.join(HERE, "config", args.config)) as f:
         main(json.load(f), args)

@@ -41,15 +41,33 @@ def split_video(path, out_dir, fps):
 
 if __name__ == "__main__":
     args = parser.parse_args()
+    # The reference (test.py:17-31) always works on ./data/test/<name>: a video is split into that folder, a frame
+    # folder is moved there.  Stage 1 (--root data/test/) and stage 2 (hard-coded ./data/test/<name>) both read it.
     if args.video_name is not None:
-        name = os.path.splitext(os.path.basename(args.video_name))[0]
-        root = os.path.dirname(args.video_name) or "."
-        split_video(args.video_name, os.path.join(root, name), args.fps)
+        name = os.path.basename(args.video_name)[:-4]
+        frames_dir = os.path.join(".", "data", "test", name)
+        split_video(args.video_name, frames_dir, args.fps)
     else:
         name = os.path.basename(os.path.normpath(args.video_frame_folder))
-        root = os.path.dirname(os.path.normpath(args.video_frame_folder)) or "."
-    rc = subprocess.call([sys.executable, os.path.join(HERE, "src", "stage1_neural_atlas.py"), "--vid_name", name,
-                          "--root", root + "/", "--gpu", str(args.gpu)])
-    stage2 = os.path.join(HERE, "src", "neural_filter_and_refinement.py")
-    if rc == 0 and os.path.exists(stage2):
-        subprocess.call([sys.executable, stage2, "--video_name", name, "--fps", str(args.fps)])
+        frames_dir = os.path.join(".", "data", "test", name)
+        if os.path.isdir(frames_dir):
+            print("input folder {} exist".format(frames_dir))
+        else:
+            os.makedirs(os.path.dirname(frames_dir), exist_ok=True)
+            print("mv {} {}".format(args.video_frame_folder, frames_dir))
+            shutil.move(args.video_frame_folder, frames_dir)
+    if args.class_name is None:
+        stage1 = [sys.executable, os.path.join(HERE, "src", "stage1_neural_atlas.py"), "--vid_name", name,
+                  "--gpu", str(args.gpu)]
+    else:
+        seg = os.path.join(HERE, "src", "stage1_neural_atlas_seg.py")
+        if not os.path.exists(seg):
+            raise NotImplementedError("--class_name selects the segmentation variant (src/stage1_neural_atlas_seg.py), "
+                                      "which this build does not ship (SURVEY.md §8f rank 3)")
+        stage1 = [sys.executable, seg, "--vid_name", name, "--class_name", args.class_name, "--gpu", str(args.gpu)]
+    rc = subprocess.call(stage1)
+    if rc != 0:
+        sys.exit(rc)
+    sys.exit(subprocess.call([sys.executable, os.path.join(HERE, "src", "neural_filter_and_refinement.py"),
+                              "--video_name", name, "--fps", str(args.fps), "--ckpt_filter", args.ckpt_filter,
+                              "--ckpt_local", args.ckpt_local]))

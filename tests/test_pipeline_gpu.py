@@ -44,7 +44,7 @@ def test_scripts_end_to_end(tmp_path):
     cfg.update(iters_num=301, evaluate_every=300, pretrain_iter_number=3, samples_batch=2000, stop_global_rigidity=150)
     cfg_path = str(work / "cfg.json")
     json.dump(cfg, open(cfg_path, "w"))
-    env = dict(os.environ, PYTHONPATH=PKG)
+    env = dict(os.environ, PYTHONPATH=PKG, B200_ALLOW_RANDOM_RAFT="1")    # no pretrained RAFT offline
     r = subprocess.run([sys.executable, os.path.join(PKG, "src", "stage1_neural_atlas.py"), "--vid_name", vid, "--root",
                         "data/test/", "--down", "1", "--config", cfg_path], cwd=str(work), env=env, capture_output=True,
                        text=True, timeout=900)
