@@ -166,6 +166,32 @@ int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int3
                             int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Stand-alone loss heads — the arithmetic of the reference's three loss FUNCTIONS
+ *   get_gradient_loss_single  src/models/stage_1/loss_utils.py:134-170
+ *   get_rigidity_loss         src/models/stage_1/loss_utils.py:227-278
+ *   get_optical_flow_loss     src/models/stage_1/loss_utils.py:299-322 (one flow direction per call)
+ * for callers that keep the reference's function-level structure (all-in-one-deflicker_b200/src/
+ * models/stage_1/loss_utils.py wraps them as autograd Functions).  Each call writes the scalar the
+ * reference function returns (*loss, a mean) and the gradient of that scalar with respect to every
+ * network output it consumes.  Inputs are the *network outputs* (rgb = (atlas+1)/2, uv = mapping);
+ * evaluating the networks stays with the caller's IMLP objects.  rows n; all arrays row-major.
+ * ------------------------------------------------------------------------------------------ */
+/* rgb, rgb_xp, rgb_yp, dx_gt, dy_gt: [n][3]; d_*: [n][3] */
+int b200_gradient_loss_head(const float* rgb, const float* rgb_xp, const float* rgb_yp,
+                            const float* dx_gt, const float* dy_gt, int64_t n, float* loss,
+                            float* d_rgb, float* d_rgb_xp, float* d_rgb_yp, void* stream);
+/* uv: [n][2]; uv_p: [2n][2] = mapping at (x, y-d, t) for all rows, then at (x-d, y, t) (the
+ * concatenation order of loss_utils.py:230-233); per_sample (optional, [n]) receives the
+ * un-averaged values (`return_all=True`) */
+int b200_rigidity_loss_head(const float* uv, const float* uv_p, int64_t n, float resx,
+                            float uv_mapping_scale, float derivative_amount, float* per_sample,
+                            float* loss, float* d_uv, float* d_uv_p, void* stream);
+/* uv_rel, uv_match: [n][2] (rows with a valid flow only); n == 0 writes NaN like torch's mean */
+int b200_flow_loss_head(const float* uv_rel, const float* uv_match, int64_t n, float resx,
+                        float uv_mapping_scale, float* loss, float* d_uv_rel, float* d_uv_match,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimiser — replaces torch.optim.Adam.step() (src/stage1_neural_atlas.py:132-134,231) on a
  * flat buffer.  `step` is a device int64 counter (steps already taken); it is incremented by
  * the kernel so the call can sit inside a replayed CUDA graph.  lr/betas/eps are doubles because

@@ -1,0 +1,107 @@
+"""The three loss functions of the drop-in boundary (all-in-one-deflicker_b200/src/models/stage_1/loss_utils.py,
+signatures of the reference's loss_utils.py:134,227,299) against the oracle: same CPU video tensors, same `jif`,
+the repo's IMLP objects on the GPU versus the oracle networks with the same parameters.
+
+Tolerances: loss value rtol 2e-5 (fp32 sums in a different order); gradient of the returned scalar with respect
+to every network parameter |err| <= 2e-4 * max|g| per tensor (fp32 path of the IMLP kernels)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from b200 import synth
+from oracle import atlas_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _nets(golden_dir):
+    from src.models.stage_1.implicit_neural_networks import IMLP
+    z = np.load(os.path.join(golden_dir, "params_seed1234.npz"))
+    mp = [torch.from_numpy(z[f"map{i}"]).clone().requires_grad_(True) for i in range(12)]
+    ap = [torch.from_numpy(z[f"atl{i}"]).clone().requires_grad_(True) for i in range(16)]
+    m = IMLP(input_dim=3, output_dim=2, hidden_dim=256, use_positional=False, positional_dim=4, num_layers=6,
+             skip_layers=[], verbose=False)
+    a = IMLP(input_dim=2, output_dim=3, hidden_dim=256, use_positional=True, positional_dim=10, num_layers=8,
+             skip_layers=[4, 7], verbose=False)
+    m.load_state_dict(O.state_dict_of([p.detach() for p in mp]))
+    a.load_state_dict(O.state_dict_of([p.detach() for p in ap]))
+    return mp, ap, m.to(DEV), a.to(DEV)
+
+
+def _setup(golden_dir, B=700, mask_density=0.7):
+    H, W, T = 40, 56, 7
+    data = synth.throughput_set(H, W, T, seed=11, mask_density=mask_density)
+    video = O.Video(**data)
+    inds = torch.randint(H * W * T, (B, 1), generator=torch.Generator().manual_seed(5))
+    jif = O.pixel_table(T, H, W)[:, inds]
+    mp, ap, m, a = _nets(golden_dir)
+    o_map = lambda x: O.mlp_forward(O.MAPPING_SPEC, mp, x)
+    o_atl = lambda x: O.mlp_forward(O.ATLAS_SPEC, ap, x)
+    xyt = O.normalise_xyt(jif, max(H, W), T)
+    return data, video, jif, xyt, (mp, ap, o_map, o_atl), (m, a), (H, W, T)
+
+
+def _check_grads(ref_params, module, what):
+    views = module._views(module.flat.grad)
+    for i in range(len(ref_params) // 2):
+        for kind, p in (("weight", ref_params[2 * i]), ("bias", ref_params[2 * i + 1])):
+            got = views[f"hidden.{i}.{kind}"].cpu()
+            want = p.grad if p.grad is not None else torch.zeros_like(p)
+            tol = 2e-4 * float(want.abs().max()) + 1e-9
+            assert float((got - want).abs().max()) <= tol, (what, i, kind, float((got - want).abs().max()), tol)
+
+
+def test_gradient_loss_single(golden_dir):
+    from src.models.stage_1 import loss_utils as LU
+    data, video, jif, xyt, (mp, ap, o_map, o_atl), (m, a), (H, W, T) = _setup(golden_dir)
+    rgb_o = (o_atl(o_map(xyt) * 0.5 + 0.5) + 1.0) * 0.5
+    want = O.gradient_loss(video, jif, o_map, o_atl, rgb_o, W)
+    want.backward()
+    rgb = (a(m(xyt.to(DEV)) * 0.5 + 0.5) + 1.0) * 0.5
+    got = LU.get_gradient_loss_single(data["frames_dx"], data["frames_dy"], jif, m, a, rgb, DEV, W, T)
+    assert got.dim() == 0 and got.dtype == torch.float32 and got.requires_grad
+    np.testing.assert_allclose(float(got), float(want), rtol=2e-5)
+    got.backward()
+    _check_grads(mp, m, "gradient/mapping")
+    _check_grads(ap, a, "gradient/atlas")
+
+
+@pytest.mark.parametrize("d", [1, 100])
+def test_rigidity_loss(golden_dir, d):
+    from src.models.stage_1 import loss_utils as LU
+    data, video, jif, xyt, (mp, ap, o_map, o_atl), (m, a), (H, W, T) = _setup(golden_dir)
+    L = max(H, W)
+    want = O.rigidity_loss(jif, d, L, T, o_map, o_map(xyt), uv_scale=0.8)
+    want.backward()
+    got = LU.get_rigidity_loss(jif, d, L, T, m, m(xyt.to(DEV)), DEV, uv_mapping_scale=0.8)
+    np.testing.assert_allclose(float(got), float(want), rtol=2e-5)
+    got.backward()
+    _check_grads(mp, m, f"rigidity d={d}")
+    with torch.no_grad():
+        every = LU.get_rigidity_loss(jif, d, L, T, m, m(xyt.to(DEV)), DEV, uv_mapping_scale=0.8, return_all=True)
+        ref = O.rigidity_loss(jif, d, L, T, o_map, o_map(xyt), uv_scale=0.8, per_sample=True)
+    np.testing.assert_allclose(every.cpu().numpy(), ref.detach().numpy(), rtol=2e-4)
+
+
+def test_optical_flow_loss(golden_dir):
+    from src.models.stage_1 import loss_utils as LU
+    data, video, jif, xyt, (mp, ap, o_map, o_atl), (m, a), (H, W, T) = _setup(golden_dir)
+    L = max(H, W)
+    want = O.flow_loss(video, jif, o_map(xyt), L, o_map, 0.8)
+    want.backward()
+    got = LU.get_optical_flow_loss(jif, m(xyt.to(DEV)), data["flow_bwd"], data["mask_bwd"], L, T, m, data["flow_fwd"],
+                                   data["mask_fwd"], 0.8, DEV)
+    np.testing.assert_allclose(float(got), float(want), rtol=2e-5)
+    got.backward()
+    _check_grads(mp, m, "flow")
+
+
+def test_optical_flow_loss_empty_set_is_nan(golden_dir):
+    from src.models.stage_1 import loss_utils as LU
+    data, video, jif, xyt, _, (m, a), (H, W, T) = _setup(golden_dir, B=64, mask_density=0.0)
+    got = LU.get_optical_flow_loss(jif, m(xyt.to(DEV)), data["flow_bwd"], data["mask_bwd"], max(H, W), T, m,
+                                   data["flow_fwd"], data["mask_fwd"], 0.8, DEV)
+    assert torch.isnan(got)                      # mean over an empty set, as the reference (loss_utils.py:320-322)
