@@ -20,8 +20,8 @@ void set_error(const char* fmt, ...) {
 static long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
-static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
-static int g_timer_tag = 0;
+// one optional (start, stop) event pair per tagged launch site
+static cudaEvent_t g_t0[8] = {}, g_t1[8] = {};
 
 static void record_timer(cudaEvent_t ev, cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -29,8 +29,8 @@ static void record_timer(cudaEvent_t ev, cudaStream_t st) {
   if (cs == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
   else cudaEventRecord(ev, st);
 }
-void timer_begin(int tag, cudaStream_t st) { if (tag == g_timer_tag && g_t0) record_timer(g_t0, st); }
-void timer_end(int tag, cudaStream_t st) { if (tag == g_timer_tag && g_t1) record_timer(g_t1, st); }
+void timer_begin(int tag, cudaStream_t st) { if (tag > 0 && tag < 8 && g_t0[tag]) record_timer(g_t0[tag], st); }
+void timer_end(int tag, cudaStream_t st) { if (tag > 0 && tag < 8 && g_t1[tag]) record_timer(g_t1[tag], st); }
 
 int resolve_mlp(const B200MlpDesc* d, MlpShape* s) {
   if (!d || !s) { set_error("null descriptor"); return B200_ERR_INVALID; }
@@ -145,9 +145,13 @@ int b200_version(void) { return 100; }
 long long b200_launch_count(void) { return g_launches; }
 
 int b200_set_kernel_timer(void* ev_start, void* ev_stop, int tag) {
-  g_t0 = reinterpret_cast<cudaEvent_t>(ev_start);
-  g_t1 = reinterpret_cast<cudaEvent_t>(ev_stop);
-  g_timer_tag = (ev_start && ev_stop) ? tag : 0;
+  if (tag == 0 && !ev_start && !ev_stop) {               // switch every site off
+    for (int i = 0; i < 8; ++i) g_t0[i] = g_t1[i] = nullptr;
+    return B200_OK;
+  }
+  B200_REQUIRE(tag > 0 && tag < 8, "unknown kernel tag %d", tag);
+  g_t0[tag] = (ev_start && ev_stop) ? reinterpret_cast<cudaEvent_t>(ev_start) : nullptr;
+  g_t1[tag] = (ev_start && ev_stop) ? reinterpret_cast<cudaEvent_t>(ev_stop) : nullptr;
   return B200_OK;
 }
 

@@ -112,5 +112,206 @@ def main():
     print(json.dumps(out))
 
 
+# ------------------------------------------------------------------------------------------------------
+# driver-format lines for `bench.py --workload raft|stage2` (BASELINE.json configs[3] / configs[4])
+# ------------------------------------------------------------------------------------------------------
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def _event_ms(fn, iters, warm, world=1, dev=None):
+    import torch.distributed as dist
+    for _ in range(warm):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms / iters
+
+
+def _reference_line(args):
+    """--impl reference for the two secondary workloads: the oracle restatements (plain torch ops) on the host
+    cores, bounded sample."""
+    import time
+    from oracle import flow_oracle as FO, stage2_oracle as SO
+    cores = os.cpu_count() or 1
+    threads = min(cores, 32)
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    if args.workload == "stage2":
+        from src.models.network_filter import UNet
+        from src.models.network_local import TransformNet
+        Hp, Wp = 1088, 1920
+        sd_u = UNet(6, 3, 32).state_dict()
+        sd_t = TransformNet(types.SimpleNamespace(nf=32, norm="IN", model="TransformNet", blocks=5), 12, 3).state_dict()
+        x6, x12 = torch.rand(1, 6, Hp, Wp, generator=g), torch.rand(1, 12, Hp, Wp, generator=g)
+        with torch.no_grad():
+            t0 = time.perf_counter(); SO.unet_forward(sd_u, x6); SO.transformnet_forward(sd_t, x12)
+            dt = time.perf_counter() - t0
+        val, unit, metric = 1.0 / dt, "frames/s", "stage2_frames_per_sec"
+        sample = f"1 frame at 1088x1920 through the oracle UNet + TransformNet (torch CPU fp32), {threads} threads of {cores}"
+    else:
+        h8, w8 = 135, 240
+        f1, f2 = torch.randn(1, 256, h8, w8, generator=g), torch.randn(1, 256, h8, w8, generator=g)
+        ub_sd = {}
+        from src.models.stage_1.core.update import BasicUpdateBlock
+        ub_sd = BasicUpdateBlock(types.SimpleNamespace(corr_levels=4, corr_radius=4), hidden_dim=128).state_dict()
+        ys, xs = torch.meshgrid(torch.arange(h8).float(), torch.arange(w8).float(), indexing="ij")
+        coords = torch.stack([xs, ys])[None]
+        net, inp, flow = torch.randn(1, 128, h8, w8), torch.randn(1, 128, h8, w8), torch.zeros(1, 2, h8, w8)
+        with torch.no_grad():
+            t0 = time.perf_counter(); pyr = FO.corr_pyramid(f1, f2); t_c = time.perf_counter() - t0
+            t0 = time.perf_counter(); c = FO.corr_lookup(pyr, coords); FO.update_block(ub_sd, net, inp, c, flow)
+            t_i = time.perf_counter() - t0
+        dt = 2 * (t_c + 20 * t_i)
+        val, unit, metric = 1.0 / dt, "pairs/s", "raft_pairs_per_sec"
+        sample = (f"one direction: correlation pyramid ({t_c:.2f} s) + 1 of 20 lookup+update iterations ({t_i:.2f} s), "
+                  f"extrapolated to 2 directions x 20 iterations, encoders and upsampling NOT counted (favours the CPU); "
+                  f"oracle torch CPU fp32, {threads} threads of {cores}")
+    print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+                      "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / val, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                      "config": {"workload": args.workload},
+                      "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def driver_line(args, rank, world, local):
+    """`bench.py --workload raft|stage2`: a step = one 1080p frame pair (both flow directions, 20 refinement
+    iterations) / one 1088x1920 frame through UNet + TransformNet.  Pairs and neural-filter frames are independent
+    units: with N GPUs every rank runs its own (weak scaling, no collective)."""
+    if args.impl == "reference":
+        if rank == 0:
+            _reference_line(args)
+        return
+    import argparse as ap2
+    import torch.distributed as dist
+    from b200 import nn as K
+    from b200 import _native as N
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K.set_conv_precision("tc")
+    steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    g = torch.Generator().manual_seed(rank)
+    peaks, how = _peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    launches0 = N.lib().b200_launch_count()
+    if args.workload == "raft":
+        from src.models.stage_1.core.raft import RAFT
+        from src.models.stage_1.core.update import BasicUpdateBlock
+        Hh, Ww = 1080, 1920
+        h8, w8 = Hh // 8, Ww // 8
+        hw = h8 * w8
+        raft = RAFT(ap2.Namespace(small=False, mixed_precision=True)).to(dev).eval()
+        im1_h = (torch.rand(1, 3, Hh, Ww, generator=g) * 255).pin_memory()
+        im2_h = (torch.rand(1, 3, Hh, Ww, generator=g) * 255).pin_memory()
+        im1, im2 = im1_h.to(dev), im2_h.to(dev)
+        with torch.no_grad():
+            ms = _event_ms(lambda: raft.forward_both(im1, im2, iters=20), steps, warm, world, dev)
+            n_launch = (N.lib().b200_launch_count() - launches0) // (steps + warm)
+            res = {}
+            def e2e():
+                a, b = im1_h.to(dev, non_blocking=True), im2_h.to(dev, non_blocking=True)
+                (_, u12), (_, u21) = raft.forward_both(a, b, iters=20)
+                res["f"] = (u12[0].permute(1, 2, 0).cpu(), u21[0].permute(1, 2, 0).cpu())
+            ems = _event_ms(e2e, max(1, steps // 2), 1, world, dev)
+            # dominant component: the update block (20 x 2 calls per pair), timed alone
+            ub = raft.update_block
+            net = torch.tanh(torch.randn(1, 128, h8, w8, generator=g)).to(dev)
+            inp = torch.relu(torch.randn(1, 128, h8, w8, generator=g)).to(dev)
+            flow = torch.randn(1, 2, h8, w8, generator=g).to(dev)
+            corr = torch.randn(1, 324, h8, w8, generator=g).to(dev)
+            ub_ms = _event_ms(lambda: ub(net, inp, corr, flow), 10, 2)
+            f1 = torch.randn(1, 256, h8, w8, generator=g).to(dev)
+            pyr = [None]
+            def build():
+                pyr[0] = None
+                pyr[0] = K.corr_build(f1, f1)
+            cb_ms = _event_ms(build, 3, 1)
+        value, unit, metric = world * 1000.0 / ms, "pairs/s", "raft_pairs_per_sec"
+        e2e_v = world * 1000.0 / ems
+        h2d, d2h = 2 * 3 * Hh * Ww * 4, 2 * Hh * Ww * 2 * 4
+        ub_tf = 2 * 3.118e6 * hw / ub_ms / 1e9
+        vol = 4.0 * hw * hw * (1 + 0.25 + 0.0625 + 0.015625)
+        roof = {"bound": "tensor", "kernel": "conv2d_tma_kernel (BasicUpdateBlock, one refinement iteration)",
+                "achieved": ub_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ub_tf / peak_tf, "kernel_ms": ub_ms,
+                "share_of_step": 40 * ub_ms / ms, "traffic": None, "peak_source": how,
+                "hbm": {"kernel": "corr_build (conv2d_tma_kernel split + avgpool2_kernel)", "achieved": vol / cb_ms / 1e6,
+                        "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": vol / cb_ms / 1e6 / float(peaks["hbm_gbs"]),
+                        "kernel_ms": cb_ms, "share_of_step": 2 * cb_ms / ms}}
+        config = {"workload": "RAFT flow pre-pass, 1080x1920 synthetic frame pair, both directions, 20 refinement "
+                              "iterations, random-init RAFT-things weights (BASELINE.json configs[3])",
+                  "l2": "4.2 GB correlation volume per direction exceeds L2"}
+        dtype = "fp16 operands / fp32 accumulate convolutions (the reference's autocast), fp32-grade correlation"
+    else:
+        from src.models.network_filter import UNet
+        from src.models.network_local import TransformNet
+        Hp, Wp = 1088, 1920
+        unet = UNet(6, 3, 32).to(dev).eval()
+        tn = TransformNet(types.SimpleNamespace(nf=32, norm="IN", model="TransformNet", blocks=5), 12, 3).to(dev).eval()
+        c_h = torch.rand(1, 3, Hp, Wp, generator=g).pin_memory()
+        s_h = torch.rand(1, 3, Hp, Wp, generator=g).pin_memory()
+        content, style = c_h.to(dev), s_h.to(dev)
+        state = {"o1": torch.rand(1, 3, Hp, Wp, generator=g).to(dev), "p1": torch.rand(1, 3, Hp, Wp, generator=g).to(dev)}
+        def frame(c, s):
+            pred = unet(torch.cat([c, s], dim=1))
+            out, _ = tn(torch.cat((pred, state["o1"], pred, state["p1"]), dim=1), None)
+            o2 = pred + out
+            state["p1"], state["o1"] = pred, o2
+            return o2
+        with torch.no_grad():
+            ms = _event_ms(lambda: frame(content, style), steps, warm, world, dev)
+            n_launch = (N.lib().b200_launch_count() - launches0) // (steps + warm)
+            res = {}
+            def e2e():
+                o = frame(c_h.to(dev, non_blocking=True), s_h.to(dev, non_blocking=True))
+                res["o"] = o.cpu()
+            ems = _event_ms(e2e, max(1, steps // 2), 1, world, dev)
+            x6 = torch.rand(1, 6, Hp, Wp, generator=g).to(dev)
+            x12 = torch.rand(1, 12, Hp, Wp, generator=g).to(dev)
+            u_ms = _event_ms(lambda: unet(x6), 4, 1)
+            t_ms = _event_ms(lambda: tn(x12, None), 4, 1)
+        value, unit, metric = world * 1000.0 / ms, "frames/s", "stage2_frames_per_sec"
+        e2e_v = world * 1000.0 / ems
+        h2d, d2h = 2 * 3 * Hp * Wp * 4, 3 * Hp * Wp * 4
+        t_tf = 2 * 559e9 / t_ms / 1e9
+        roof = {"bound": "tensor", "kernel": "conv2d_tma_kernel (TransformNet forward)", "achieved": t_tf,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": t_tf / peak_tf, "kernel_ms": t_ms, "traffic": None,
+                "peak_source": how, "unet": {"ms": u_ms, "tflops": 2 * 524e9 / u_ms / 1e9}}
+        config = {"workload": "stage 2: UNet neural filter + TransformNet local refinement on 1088x1920 frames "
+                              "(1080p padded to /32), random-init weights (BASELINE.json configs[4])",
+                  "note": "the refinement chain is sequential over frames; with N GPUs each rank filters its own video "
+                          "(replicas)", "l2": "per-layer activations (up to 267 MB) exceed L2"}
+        dtype = "fp16 operands / fp32 accumulate (tcgen05), the operand width of the reference's TF32 cuDNN convolutions"
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warm,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": dtype, "data": "synthetic", "config": config,
+                          "e2e": {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                          "gpu_launches": int(n_launch * steps), "roofline": roof}), flush=True)
+    if world > 1:
+        torch.cuda.synchronize(); dist.barrier()
+        sys.stdout.flush(); os._exit(0)
+
+
 if __name__ == "__main__":
     main()

@@ -51,7 +51,8 @@ int b200_device_supports_tc(void);
 /* Diagnostics (no reference counterpart).  b200_launch_count: kernels this library has launched
  * (or captured into a CUDA graph) in this process.  b200_set_kernel_timer: record the two
  * cudaEvent_t around the launch site tagged `tag` (B200_TAG_*) on every following call, also
- * inside captured graphs; NULL events switch it off. */
+ * inside captured graphs; every tag has its own pair (all sites can be timed in one run); NULL
+ * events switch that site off, (NULL, NULL, 0) switches every site off. */
 #define B200_TAG_MAP_FWD 1
 #define B200_TAG_MAP_BWD 2
 #define B200_TAG_ATLAS_FWD 3
