@@ -225,6 +225,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the pre-training / render side measurements")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="profiling aid: ONE process does the work of rank 0 of an N-GPU run (frame shard 0, no "
+                         "collective), so that ncu can list the per-rank kernels of the sharded step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,6 +263,9 @@ def main():
 
     data = synth.throughput_set(H, W, T, seed=0)
     t0, t1 = A.frame_range(rank, world, T)
+    if args.emulate_world > 1:
+        assert world == 1
+        t0, t1 = A.frame_range(0, args.emulate_world, T)
     video = A.DeviceVideo.from_reference_layout(data, dev, t0, t1)
     trainer = A.AtlasTrainer(video, {"samples_batch": BATCH}, precision=precision, device=dev, process_group=pg)
     torch.manual_seed(0)
@@ -400,7 +406,8 @@ def main():
                 "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None,
                 "dtype": "fp32" if precision == N.PREC_FP32 else "fp32 (2-term fp16 split on tcgen05, fp32 accumulate)",
-                "data": "synthetic", "config": dict(ATLAS_CONFIG, parallelism=f"frame-sharded dp{world}",
+                "data": "synthetic", "config": dict(ATLAS_CONFIG, parallelism=f"frame-sharded dp{world}" if args.emulate_world < 2
+                                                    else f"PROFILING AID: rank 0 of an emulated dp{args.emulate_world} run, no collective",
                                                     precision=prec, cuda_graph=True),
                 "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": BATCH * 8,
                         "d2h_bytes_per_step": N.LOSS_FLOATS * 4, "steps": k_e2e},
