@@ -267,7 +267,8 @@ template <bool ATLAS> struct KCfg {
 template <int NST, bool ATLAS>
 struct SmemMap {
   char* stage; char* staging; char* aux; float* cst;
-  uint64_t* full; uint64_t* empty; uint64_t* a_ready; uint64_t* d_ready; uint64_t* misc; uint32_t* tmem_slot;
+  uint64_t* full; uint64_t* empty; uint64_t* a_ready; uint64_t* x_ready; uint64_t* d_ready; uint64_t* d_free;
+  uint64_t* misc; uint32_t* tmem_slot;
   __device__ __forceinline__ void init(char* raw) {
     char* p = raw;                                   // 1024-aligned (checked in setup_cta): keeps the
     stage = p; p += NST * STAGE_BYTES;               // shared address space visible to the compiler (LDS/STS)
@@ -276,9 +277,11 @@ struct SmemMap {
     cst = reinterpret_cast<float*>(p); p += SMEM_CONST_FLOATS * 4;
     full = reinterpret_cast<uint64_t*>(p);
     empty = full + NST;
-    a_ready = empty + NST;
-    d_ready = a_ready + 1;
-    misc = d_ready + 1;
+    a_ready = empty + NST;          // [4]: one per 64-column k chunk of the next layer's A operand
+    x_ready = a_ready + 4;          // layer-0 input of a tile is in place (atlas: positional-encoding tile)
+    d_ready = x_ready + 1;          // accumulator of the current layer pass is complete
+    d_free = d_ready + 1;           // ... and has been drained into registers by every epilogue thread
+    misc = d_free + 1;
     tmem_slot = reinterpret_cast<uint32_t*>(misc + 2);
   }
 };
@@ -288,8 +291,10 @@ __device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp)
   if (threadIdx.x == 0) {
     if (smem_u32(sm.stage) & 1023u) { printf("b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-    mbar_init(sm.a_ready, EPI_THREADS);
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], EPI_THREADS / 2);
+    mbar_init(sm.x_ready, EPI_THREADS);
     mbar_init(sm.d_ready, 1);
+    mbar_init(sm.d_free, EPI_THREADS);
     mbar_init(&sm.misc[0], 1);
     mbar_init(&sm.misc[1], EPI_THREADS);
     fence_barrier_init();
@@ -350,11 +355,21 @@ struct FwdParams {
   int64_t w_off[B200_MAX_LAYERS], b_off[B200_MAX_LAYERS];
   NetImages img;
   int cap, n_groups; const int* n_valid;
+  float in_scale, in_shift;  // atlas: network input = x * in_scale + in_shift (0.5, 0.5 inside the loop: uv -> [0,1])
+  int store_images;          // 0: inference (render / IMLP.forward without grad): no activation images, no flags
+  int tanh_out;
 };
 
 // =============================================================================================
 // forward
 // =============================================================================================
+// Schedule of one layer pass (both fused kernels).  The accumulator D of pass n is drained into registers by the
+// 8 epilogue warps as soon as it is complete (d_ready -> 4 tcgen05.ld per thread -> d_free), which frees TMEM for
+// pass n+1 while the epilogue arithmetic of pass n is still running: the epilogue emits the next A operand one
+// 64-column k chunk at a time (a_ready[kc], chunks of the two column halves alternate: 0, 2, 1, 3) and the MMA
+// warp consumes the chunks in that order, so the tensor pipe works on layer l+1 underneath the epilogue of layer l.
+__device__ __constant__ int kChunkOrder[4] = {0, 2, 1, 3};
+
 template <bool ATLAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(1024) char smem_raw[];
@@ -383,26 +398,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (consumption order)
     if (lane == 0) {
       Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x)
-        for (int l = FIRST_TC; l <= LAST_TC; ++l)
-          produce_items(pp, P.img.w_fwd + P.img.w_fwd_layer[l], P.img.n_chunks_fwd[l] * 2);
+        for (int l = FIRST_TC; l <= LAST_TC; ++l) {
+          const char* base = P.img.w_fwd + P.img.w_fwd_layer[l];
+          if (ATLAS && l == 0) { produce_items(pp, base, 2); continue; }
+          if (ATLAS && l == 4) produce_items(pp, base + (int64_t)4 * 2 * STAGE_BYTES, 2);      // skip (PE) chunk first
+          for (int j = 0; j < 4; ++j) produce_items(pp, base + (int64_t)kChunkOrder[j] * 2 * STAGE_BYTES, 2);
+        }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
-      uint32_t a_par = 0;
+      uint32_t pass = 0, ts_pass = 0, x_par = 0;
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
         for (int l = FIRST_TC; l <= LAST_TC; ++l) {
-          mbar_wait(sm.a_ready, a_par); a_par ^= 1;
-          tc_fence_after();
+          if (pass > 0) mbar_wait(sm.d_free, (pass - 1) & 1);      // D of the previous pass is in registers
           bool first = true;
-          if (l > 0) for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, IDESC, first);
+          if (ATLAS && l == 0) { mbar_wait(sm.x_ready, x_par); x_par ^= 1; }
+          tc_fence_after();
           if (ATLAS && (l == 0 || l == 4)) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + ATOM_BYTES, IDESC, first);
+          if (l > 0) {
+            for (int j = 0; j < 4; ++j) {
+              const int kc = kChunkOrder[j];
+              mbar_wait(&sm.a_ready[kc], ts_pass & 1);
+              tc_fence_after();
+              mma_chunk_ts(pp, tmem, kc, IDESC, first);
+            }
+            ++ts_pass;
+          }
           mma_commit(sm.d_ready);
+          ++pass;
         }
       }
     }
@@ -422,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         // positional encoding of in = uv*0.5+0.5 (implicit_neural_networks.py:9-13) into the aux tile
         // (K-major SW128, columns k*4 + {sin x0, sin x1, cos x0, cos x1}); half 0 does k = 0..5, half 1 the rest
         const float2 uv = *reinterpret_cast<const float2*>(P.x + row * 2);
-        const float in[2] = {uv.x * 0.5f + 0.5f, uv.y * 0.5f + 0.5f};
+        const float in[2] = {uv.x * P.in_scale + P.in_shift, uv.y * P.in_scale + P.in_shift};
         char* a_hi = sm.aux;
         char* a_lo = sm.aux + ATOM_BYTES;
         char* g_hi = P.img.pe + (int64_t)gt * ATOM_BYTES;
@@ -449,12 +478,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(a_hi + off) = vh;
           *reinterpret_cast<uint4*>(a_lo + off) = vl;
-          *reinterpret_cast<uint4*>(g_hi + off) = vh;
-          *reinterpret_cast<uint4*>(g_lo + off) = vl;
+          if (P.store_images) {
+            *reinterpret_cast<uint4*>(g_hi + off) = vh;
+            *reinterpret_cast<uint4*>(g_lo + off) = vl;
+          }
         }
         fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the MMA
         tc_fence_before();
-        mbar_arrive(sm.a_ready);
+        mbar_arrive(sm.x_ready);
       } else {
         // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0), this thread's 128 columns
         const float4 xv = *reinterpret_cast<const float4*>(P.x + row * 4);
@@ -489,14 +520,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
             tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
             tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
           }
-          char* g = img + (hh * 2 + ab) * ATOM_BYTES;
-          stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&sm.a_ready[hh * 2 + ab]);       // k chunk hh*2+ab of A_1 is in TMEM
+          if (P.store_images) {
+            char* g = img + (hh * 2 + ab) * ATOM_BYTES;
+            stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+          }
         }
-        *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)0 * P.img.rows + row) * 8 + hh * 4) =
-            make_uint4(bits[0], bits[1], bits[2], bits[3]);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(sm.a_ready);
+        if (P.store_images)
+          *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)0 * P.img.rows + row) * 8 + hh * 4) =
+              make_uint4(bits[0], bits[1], bits[2], bits[3]);
       }
       // ---------------- tensor-core layers
       float outacc[OUT];
@@ -506,6 +540,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       for (int l = FIRST_TC; l <= LAST_TC; ++l) {
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
+        // drain this thread's 128 accumulator columns, then hand D back to the MMA warp
+        uint32_t raw[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sm.d_free);
         const bool last = (l == LAST_TC);
         char* img = P.img.act + (int64_t)l * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
         const float* bias = s_bias + l * 256 + hh * 128;
@@ -516,14 +557,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c = ab * 2 + cc;
-            uint32_t raw[32];
-            tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw);
-            tmem_ld_wait();
             uint32_t bw = 0;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float z0 = fmaf(__uint_as_float(raw[i]), inv_scale, bias[c * 32 + i]);
-              const float z1 = fmaf(__uint_as_float(raw[i + 1]), inv_scale, bias[c * 32 + i + 1]);
+              const float z0 = fmaf(__uint_as_float(raw[c][i]), inv_scale, bias[c * 32 + i]);
+              const float z1 = fmaf(__uint_as_float(raw[c][i + 1]), inv_scale, bias[c * 32 + i + 1]);
               bw |= (z0 > 0.f ? 1u : 0u) << i;
               bw |= (z1 > 0.f ? 1u : 0u) << (i + 1);
               const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
@@ -545,16 +583,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
               tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
             }
           }
-          char* g = img + (hh * 2 + ab) * ATOM_BYTES;
-          stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+          if (!last) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&sm.a_ready[hh * 2 + ab]);     // next layer's MMAs on this k chunk may start
+          }
+          if (P.store_images) {
+            char* g = img + (hh * 2 + ab) * ATOM_BYTES;
+            stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+          }
         }
-        *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8 + hh * 4) =
-            make_uint4(bits[0], bits[1], bits[2], bits[3]);
-        if (!last) {
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(sm.a_ready);
-        }
+        if (P.store_images)
+          *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8 + hh * 4) =
+              make_uint4(bits[0], bits[1], bits[2], bits[3]);
       }
       // ---------------- output layer (+ skip part for the atlas) and tanh; the two column halves of a row
       // combine through shared memory
@@ -576,7 +617,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       named_bar(3, EPI_THREADS);
       if (hh == 0) {
 #pragma unroll
-        for (int j = 0; j < OUT; ++j) P.y[row * OUT + j] = tanhf(outacc[j] + s_xch[m * 4 + j] + s_blast[j]);
+        for (int j = 0; j < OUT; ++j) {
+          const float o = outacc[j] + s_xch[m * 4 + j] + s_blast[j];
+          P.y[row * OUT + j] = P.tanh_out ? tanhf(o) : o;
+        }
       }
       named_bar(3, EPI_THREADS);                         // s_xch / aux tile reuse by the next tile
     }
@@ -601,6 +645,9 @@ struct BwdParams {
   NetImages img;
   int cap, n_groups; const int* n_valid;
   int* gmax_bits;            // [0] max |dL/dy| from the loss head, [1] max |dL/duv| after the atlas backward
+  float in_scale;            // atlas: d(network input)/d(x) (0.5 inside the loop)
+  int d_in_accumulate;       // atlas: 1 = d_in already holds the direct loss-head gradient (the loop), 0 = overwrite
+  int tanh_out;
 };
 
 // column sums over the 32 rows of a warp: lane j ends with sum_rows v[j]
@@ -688,22 +735,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
                    &sm.misc[0]);
           h_par ^= 1;
         }
-        for (int l = L - 2; l >= LOW; --l) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[l], 8);
-        if (ATLAS) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[0], 8);
+        for (int l = L - 2; l >= (ATLAS ? 0 : LOW); --l) {
+          const char* base = P.img.w_bwd + P.img.w_bwd_layer[l];
+          for (int j = 0; j < 4; ++j) produce_items(pp, base + (int64_t)kChunkOrder[j] * 2 * STAGE_BYTES, 2);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
-      uint32_t a_par = 0;
+      uint32_t pass = 0;
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
         for (int l = 0; l < N_DGRAD + (ATLAS ? 1 : 0); ++l) {
-          mbar_wait(sm.a_ready, a_par); a_par ^= 1;
+          if (pass > 0) mbar_wait(sm.d_free, (pass - 1) & 1);
           tc_fence_after();
           bool first = true;
           const uint32_t idesc = (ATLAS && l == N_DGRAD) ? IDESC64 : IDESC;
-          for (int kc = 0; kc < 4; ++kc) mma_chunk_ts(pp, tmem, kc, idesc, first);
+          for (int j = 0; j < 4; ++j) {
+            const int kc = kChunkOrder[j];
+            mbar_wait(&sm.a_ready[kc], pass & 1);        // every pass of this kernel is a TMEM-operand pass
+            tc_fence_after();
+            mma_chunk_ts(pp, tmem, kc, idesc, first);
+          }
           mma_commit(sm.d_ready);
+          ++pass;
         }
       }
     }
@@ -722,7 +777,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
 #pragma unroll
       for (int j = 0; j < OUT; ++j) {
         const float yv = P.y[row * OUT + j];
-        dzl[j] = P.dy[row * OUT + j] * (1.0f - yv * yv);
+        dzl[j] = P.dy[row * OUT + j] * (P.tanh_out ? (1.0f - yv * yv) : 1.0f);
       }
       if (hh == 0) {
 #pragma unroll
@@ -776,18 +831,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
             tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
             tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
           }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&sm.a_ready[hh * 2 + ab]);
           char* g = img + (hh * 2 + ab) * ATOM_BYTES;
           stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(sm.a_ready);
       }
       // ---------------- hidden layers: dA_l = dZ_l W_l  ->  dZ_{l-1}
 #pragma unroll 1
       for (int l = L - 2; l >= LOW; --l) {
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
+        uint32_t raw[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sm.d_free);
         const int slot = l - 1;                           // produces dZ_{l-1}
         const uint4 bb = *reinterpret_cast<const uint4*>(P.img.bits + ((int64_t)slot * P.img.rows + row) * 8 + hh * 4);
         const uint32_t bits[4] = {bb.x, bb.y, bb.z, bb.w};
@@ -802,12 +863,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c = ab * 2 + cc;
-            uint32_t raw[32];
-            tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw);
-            tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ((bits[c] >> i) & 1u) ? __uint_as_float(raw[i]) * inv_dgrad : 0.f;
+            for (int i = 0; i < 32; ++i) v[i] = ((bits[c] >> i) & 1u) ? __uint_as_float(raw[c][i]) * inv_dgrad : 0.f;
             atomicAdd(&s_bacc[slot * 256 + hh * 128 + c * 32 + lane], warp_colsum32(v, lane));
             if (!ATLAS && slot == 0) {
               // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
@@ -836,35 +894,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
               }
             }
           }
+          if (need_tmem) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&sm.a_ready[hh * 2 + ab]);
+          }
           if (need_img) {
             char* g = img + (hh * 2 + ab) * ATOM_BYTES;
             stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
           }
         }
-        if (need_tmem) {
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(sm.a_ready);
-        }
       }
       if (ATLAS) {
-        // ---------------- dPE = dZ_0 W_0 (64 columns, 40 real) -> d(in) -> d_uv += 0.5 * d(in)
+        // ---------------- dPE = dZ_0 W_0 (64 columns, 40 real) -> d(in) -> d_in += in_scale * d(in)
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
         mbar_wait(&sm.misc[0], aux_par);                  // PE tile of this row block
+        uint32_t raw[2][32];
+        if (hh == 0) {
+          tmem_ld32(et.tlane + TM_D, raw[0]);
+          tmem_ld32(et.tlane + TM_D + 32, raw[1]);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(sm.d_free);
         if (hh == 0) {
           float din[2] = {0.f, 0.f};
-#pragma unroll 1
+#pragma unroll
           for (int c = 0; c < 2; ++c) {
-            uint32_t raw[32];
-            tmem_ld32(et.tlane + TM_D + c * 32, raw);
-            tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int col = c * 32 + i;
               if (col < PE_COLS) {
                 const int k = col >> 2, e = col & 3;       // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
-                const float g = __uint_as_float(raw[i]) * inv_dgrad;
+                const float g = __uint_as_float(raw[c][i]) * inv_dgrad;
                 const int pcol = (e < 2) ? col + 2 : col - 2;   // d sin = cos * b,  d cos = -sin * b
                 const int off = atom_off(m, pcol);
                 const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
@@ -875,20 +938,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
               }
             }
           }
-          float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
-          float2 cur = *dst;
-          cur.x += 0.5f * din[0];
-          cur.y += 0.5f * din[1];
-          *dst = cur;
-          float mx = fmaxf(fabsf(cur.x), fabsf(cur.y));
+          if (P.d_in) {
+            float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
+            float2 cur = P.d_in_accumulate ? *dst : make_float2(0.f, 0.f);
+            cur.x += P.in_scale * din[0];
+            cur.y += P.in_scale * din[1];
+            *dst = cur;
+            float mx = fmaxf(fabsf(cur.x), fabsf(cur.y));
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          if (lane == 0 && mx > 0.f) atomicMax(P.gmax_bits + 1, __float_as_int(mx));
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0 && mx > 0.f) atomicMax(P.gmax_bits + 1, __float_as_int(mx));
+          }
         }
         tc_fence_before();
         mbar_arrive(&sm.misc[1]);                         // aux tile may be overwritten
         aux_par ^= 1;
-        named_bar(3, EPI_THREADS);                        // D of the dPE product fully read before the next tile
       }
     }
     if (issuer) bulk_wait_all0();
@@ -1249,6 +1313,7 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
 static void fill_fwd(FwdParams& P, const MlpShape& sh, const NetImages& im, const float* x, float* y,
                      const float* params, int cap, int groups, const int* n_valid) {
   P.x = x; P.y = y; P.params = params; P.img = im; P.cap = cap; P.n_groups = groups; P.n_valid = n_valid;
+  P.in_scale = 0.5f; P.in_shift = 0.5f; P.store_images = 1; P.tanh_out = 1;
   for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
 }
 
@@ -1287,6 +1352,7 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
                   const float* x, float* d_in, const float* params, float* grads, int groups) {
     P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = im;
     P.cap = s.cap; P.n_groups = groups; P.n_valid = s.counters; P.gmax_bits = gmax;
+    P.in_scale = 0.5f; P.d_in_accumulate = 1; P.tanh_out = 1;
     for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
   };
   if (with_atlas) {

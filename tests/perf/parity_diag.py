@@ -62,6 +62,55 @@ def main():
             print(f"{'G' if wg else 'N'} {r['t']:26s} gmax {r['gmax']:.3e} | TC max {r['tc_max']/r['gmax']:.2e} fro {r['tc_fro']/r['gfro']:.2e} q90 {r['tc_q90']/r['gmax']:.2e}"
                   f" | oracle32 max {r['o32_max']/r['gmax']:.2e} fro {r['o32_fro']/r['gfro']:.2e} q90 {r['o32_q90']/r['gmax']:.2e}")
         del tr
+    # ---- well-conditioned scenario: quality set, mapping pre-trained for 2 sweeps (J ~ 0.8 I), full size
+    dq = synth.quality_set(H, W, T, seed=0); dq.pop("clean")
+    vq = A.DeviceVideo.from_reference_layout(dq, DEV)
+    trq = A.AtlasTrainer(vq, {"samples_batch": B}, precision=N.PREC_TC, device=DEV)
+    trq.load_state(O.state_dict_of(mp), O.state_dict_of(ap))
+    torch.manual_seed(11)
+    trq.pretrain(T, H, W, 2)
+    mq = [v.detach().cpu().clone() for v in trq.param_views("mapping").values()]
+    aq = [v.detach().cpu().clone() for v in trq.param_views("atlas").values()]
+    for wg, it in ((True, 0), (False, 6000)):
+        trq.indices.copy_(inds.reshape(-1)); trq.loss_grad(wg); torch.cuda.synchronize()
+        g_tc = trq.grads.clone(); l_tc = trq.losses.cpu().numpy().copy()
+        video = O.Video(**dq)
+        m32 = [p.clone().requires_grad_(True) for p in mq]; a32 = [p.clone().requires_grad_(True) for p in aq]
+        t32 = O.iteration_losses(video, m32, a32, inds, it); t32["total"].backward()
+        video64 = O.Video(**{k: v.double() if v.dtype == torch.float32 else v for k, v in dq.items()})
+        m64 = [p.double().requires_grad_(True) for p in mq]; a64 = [p.double().requires_grad_(True) for p in aq]
+        t64 = O.iteration_losses(video64, m64, a64, inds, it); t64["total"].backward()
+        print("Q losses tc", [float(x) for x in l_tc[:6]], "o32", [float(t32[k]) if k in t32 else 0.0 for k in ("total", "rgb", "gradient", "rigidity", "rigidity_global", "flow")])
+        i = 0
+        for which in ("mapping", "atlas"):
+            views = trq._views(g_tc, which)
+            for k in views:
+                truth = (m64 + a64)[i].grad
+                e_tc = (views[k].cpu().double() - truth).abs(); e_32 = ((m32 + a32)[i].grad.double() - truth).abs(); i += 1
+                print(f"Q{'G' if wg else 'N'} {which}.{k:18s} gmax {float(truth.abs().max()):.3e} | TC max {float(e_tc.max()/truth.abs().max()):.2e} fro {float(e_tc.norm()/truth.norm()):.2e}"
+                      f" | oracle32 max {float(e_32.max()/truth.abs().max()):.2e} fro {float(e_32.norm()/truth.norm()):.2e}")
+    # trajectory on the well-conditioned state
+    video = O.Video(**dq)
+    for prec in (N.PREC_FP32, N.PREC_TC):
+        tr = A.AtlasTrainer(vq, {"samples_batch": B}, precision=prec, device=DEV)
+        tr.load_state(O.state_dict_of(mq), O.state_dict_of(aq))
+        rm = [p.clone().requires_grad_(True) for p in mq]; ra = [p.clone().requires_grad_(True) for p in aq]
+        opt = O.make_optimizer(rm, ra)
+        gi = torch.Generator().manual_seed(21)
+        for it in range(5):
+            ii = torch.randint(H * W * T, (B, 1), generator=gi)
+            ref = O.train_iteration(video, rm, ra, opt, ii, it)
+            got = tr.step_host(ii, it)
+            print("Qtraj", "tc" if prec == N.PREC_TC else "fp32", it, "loss rel diff", abs(got[0] - ref["total"]) / abs(ref["total"]))
+        for which, ref_p in (("mapping", rm), ("atlas", ra)):
+            m_views = tr._views(tr.exp_avg, which)
+            for (k, pv), r in zip(tr.param_views(which).items(), ref_p):
+                dd = (pv.cpu() - r.detach()).abs(); st = opt.state[r]
+                em = (m_views[k].cpu() - st["exp_avg"]).abs()
+                print(f"Qtraj {'tc' if prec == N.PREC_TC else 'fp32'} {which}.{k:18s} p_max={float(dd.max()):.2e} p_mean={float(dd.mean()):.2e} p_gt2e5={float((dd > 2e-5).float().mean()):.2e} "
+                      f"p_gt1e4={float((dd > 1e-4).float().mean()):.2e} m_rel_fro={float(em.norm() / st['exp_avg'].norm()):.2e} m_rel_max={float(em.max() / st['exp_avg'].abs().max()):.2e}")
+        del tr
+    del trq, vq
     # ---- trajectory: 5 steps, both precisions, small video (the size of the committed tests) and full size
     for (h, w, t, b) in ((24, 40, 6, 64), (H, W, T, B)):
         d = data if (h, w, t) == (H, W, T) else synth.throughput_set(h, w, t, seed=3)
