@@ -45,9 +45,9 @@ constexpr int ATOM_BYTES = TM * 128;    // one 64-column block of a tile image, 
 constexpr int TILE_IMG_BYTES = 4 * ATOM_BYTES;   // one term of one [128 x 256] activation tile image: 64 KB
 constexpr int PE_COLS = 40;
 
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TC_THREADS = 64 + EPI_THREADS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int TC_THREADS = 64 + EPI_THREADS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..17: epilogue
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_D = 0, TM_AHI = 256, TM_ALO = 384;
 
@@ -256,7 +256,7 @@ __device__ __forceinline__ void produce_items(Pipe<NST>& pp, const char* src, in
 // dynamic shared memory map: [weight stages][staging 2 x (hi 16K | lo 16K)][aux tile 32 KB (atlas)][consts][barriers]
 constexpr int SMEM_STAGING = 2 * 2 * ATOM_BYTES;             // 64 KB
 constexpr int SMEM_AUX = 2 * ATOM_BYTES;                     // 32 KB
-constexpr int SMEM_CONST_FLOATS = 3584;                      // 14 KB
+constexpr int SMEM_CONST_FLOATS = 4608;                      // 18 KB
 constexpr int SMEM_BARS = 256;
 template <bool ATLAS> struct KCfg {
   static constexpr int NST = ATLAS ? 3 : 4;
@@ -291,7 +291,7 @@ __device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp)
   if (threadIdx.x == 0) {
     if (smem_u32(sm.stage) & 1023u) { printf("b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], EPI_THREADS / 2);
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], EPI_THREADS / 2);   // 2 column slices x 4 quadrants x 32 lanes
     mbar_init(sm.x_ready, EPI_THREADS);
     mbar_init(sm.d_ready, 1);
     mbar_init(sm.d_free, EPI_THREADS);
@@ -306,47 +306,54 @@ __device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp)
   return *sm.tmem_slot;
 }
 
-// Epilogue thread geometry: 8 warps; warp e handles TMEM lanes of quadrant (warp_id & 3) and the column
-// half hh = e / 4 (128 columns = 2 atom blocks = 4 chunks of 32 columns).
+// Epilogue thread geometry: 16 warps.  A warp may only touch the TMEM lanes of quadrant (warp_id & 3); the four
+// warps of a quadrant split the 256 accumulator columns into slices j = 0..3, and every warp owns TWO 32-column
+// blocks: columns [32j, 32j+32) ("block 0", inside k chunk j>>1) and [128+32j, 128+32j+32) ("block 1", inside k
+// chunk 2 + (j>>1)).  All block-0 work of a layer finishes half-way through the epilogue, so the k chunks 0, 1 of
+// the next layer's A operand are released to the MMA warp while blocks 1 are still being computed.
 struct EpiThread {
-  int e, q, hh, lane, m, tid;       // epilogue warp, TMEM quadrant, column half, lane, tile row, 0..255
+  int e, q, j, lane, m, tid, pb;    // epilogue warp, TMEM quadrant, column slice, lane, tile row, 0..511, pair buffer
   uint32_t tlane;
   __device__ __forceinline__ void init(uint32_t tmem) {
     const int warp = threadIdx.x >> 5;
     lane = threadIdx.x & 31;
-    e = warp - 2; q = warp & 3; hh = e >> 2;
+    e = warp - 2; q = warp & 3; j = e >> 2;
     m = q * 32 + lane;
     tid = threadIdx.x - 64;
+    pb = q * 2 + (j >> 1);
     tlane = tmem + ((uint32_t)(q * 32) << 16);
   }
+  __device__ __forceinline__ int col0(int b) const { return b * 128 + j * 32; }     // first column of block b
+  __device__ __forceinline__ int kchunk(int b) const { return b * 2 + (j >> 1); }   // 64-column k chunk of block b
 };
 
-// Pushes one finished 64-column atom block (held as packed hi/lo words of this thread's row) to the HBM
-// image through the staging buffer of this column half.  Called by all 128 threads of the half.
-//   ph/pl: 32 packed words each (64 columns).   bar_id: named barrier of this half.
-__device__ __forceinline__ void stage_and_store(const EpiThread& t, char* staging, const uint32_t (&ph)[32],
-                                                const uint32_t (&pl)[32], char* g_hi, char* g_lo, bool issuer,
-                                                int bar_id) {
-  char* sh = staging + t.hh * (2 * ATOM_BYTES);
-  char* sl = sh + ATOM_BYTES;
-  if (issuer) bulk_wait_read0();                       // previous block of this half has left the buffer
-  named_bar(bar_id, 128);
+// Pushes one finished 32-column block (packed hi/lo words of this thread's row) to the HBM image.  The two warps
+// (q, 2p) and (q, 2p+1) fill one 32-row x 64-column piece of an atom block = 4 KB contiguous bytes of the image per
+// term, staged in their pair buffer and written with one bulk store per term.  Called by both warps of the pair.
+__device__ __forceinline__ void stage_pair(const EpiThread& t, char* staging, const uint32_t (&ph)[16],
+                                           const uint32_t (&pl)[16], char* g_hi_atom, char* g_lo_atom) {
+  char* sh = staging + t.pb * 8192;
+  char* sl = sh + 4096;
+  const bool issuer = ((t.j & 1) == 0) && t.lane == 0;
+  if (issuer) bulk_wait_read0();                         // the previous piece has left the buffer
+  named_bar(1 + t.pb, 64);
   const int r = t.m & 7;
-  const int base = (t.m >> 3) * 1024 + r * 128;
+  const int base = ((t.m & 31) >> 3) * 1024 + r * 128;
 #pragma unroll
-  for (int c16 = 0; c16 < 8; ++c16) {
-    const int off = base + ((c16 ^ r) << 4);
-    *reinterpret_cast<uint4*>(sh + off) = make_uint4(ph[4 * c16], ph[4 * c16 + 1], ph[4 * c16 + 2], ph[4 * c16 + 3]);
-    *reinterpret_cast<uint4*>(sl + off) = make_uint4(pl[4 * c16], pl[4 * c16 + 1], pl[4 * c16 + 2], pl[4 * c16 + 3]);
+  for (int c = 0; c < 4; ++c) {
+    const int off = base + ((((t.j & 1) * 4 + c) ^ r) << 4);
+    *reinterpret_cast<uint4*>(sh + off) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
+    *reinterpret_cast<uint4*>(sl + off) = make_uint4(pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
   }
   fence_proxy_async_smem();
-  named_bar(bar_id, 128);
+  named_bar(1 + t.pb, 64);
   if (issuer) {
-    bulk_s2g(g_hi, sh, ATOM_BYTES);
-    bulk_s2g(g_lo, sl, ATOM_BYTES);
+    bulk_s2g(g_hi_atom + t.q * 4096, sh, 4096);
+    bulk_s2g(g_lo_atom + t.q * 4096, sl, 4096);
     bulk_commit();
   }
 }
+constexpr int BAR_EPI = 9;                               // named barrier of all epilogue threads
 
 struct FwdParams {
   const float* x;            // mapping: [rows][4] (x, y, t, 0);  atlas: uv [rows][2]
@@ -364,12 +371,11 @@ struct FwdParams {
 // forward
 // =============================================================================================
 // Schedule of one layer pass (both fused kernels).  The accumulator D of pass n is drained into registers by the
-// 8 epilogue warps as soon as it is complete (d_ready -> 4 tcgen05.ld per thread -> d_free), which frees TMEM for
-// pass n+1 while the epilogue arithmetic of pass n is still running: the epilogue emits the next A operand one
-// 64-column k chunk at a time (a_ready[kc], chunks of the two column halves alternate: 0, 2, 1, 3) and the MMA
-// warp consumes the chunks in that order, so the tensor pipe works on layer l+1 underneath the epilogue of layer l.
-__device__ __constant__ int kChunkOrder[4] = {0, 2, 1, 3};
-
+// 16 epilogue warps as soon as it is complete (d_ready -> 2 tcgen05.ld per thread -> d_free), which frees TMEM for
+// pass n+1 while the epilogue arithmetic of pass n is still running: the epilogue releases the next A operand one
+// 64-column k chunk at a time (a_ready[kc]: chunks 0, 1 after the block-0 half of the epilogue, 2, 3 after the
+// block-1 half) and the MMA warp consumes them in that order, so the tensor pipe works on layer l+1 underneath the
+// epilogue of layer l.
 template <bool ATLAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(1024) char smem_raw[];
@@ -382,12 +388,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   constexpr int OUT = ATLAS ? 3 : 2;
   constexpr int KLAST = ATLAS ? 296 : 256;
   // constants in shared memory: biases of layers 0..L-2 (pre-multiplied by S_ACT) at [l*256], last-layer
-  // weights (pre-divided by S_ACT) + bias, (mapping) W0, and a small exchange area for the output layer
+  // weights (pre-divided by S_ACT) + bias, (mapping) W0, and an exchange area for the output layer
   float* s_bias = sm.cst;
   float* s_wlast = sm.cst + (L - 1) * 256;
   float* s_blast = s_wlast + OUT * KLAST;
   float* s_w0 = s_blast + 4;                              // mapping only: 768 floats
-  float* s_xch = sm.cst + SMEM_CONST_FLOATS - TM * 4;     // [128][4] partial outputs of column half 1
+  float* s_xch = sm.cst + SMEM_CONST_FLOATS - 3 * TM * 4; // [3][128][4] partial outputs of column slices 1..3
   for (int i = threadIdx.x; i < (L - 1) * 256; i += blockDim.x)
     s_bias[i] = P.params[P.b_off[i >> 8] + (i & 255)] * S_ACT;
   for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i] * (1.0f / S_ACT);
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           const char* base = P.img.w_fwd + P.img.w_fwd_layer[l];
           if (ATLAS && l == 0) { produce_items(pp, base, 2); continue; }
           if (ATLAS && l == 4) produce_items(pp, base + (int64_t)4 * 2 * STAGE_BYTES, 2);      // skip (PE) chunk first
-          for (int j = 0; j < 4; ++j) produce_items(pp, base + (int64_t)kChunkOrder[j] * 2 * STAGE_BYTES, 2);
+          produce_items(pp, base, 8);
         }
     }
   } else if (warp == 1) {
@@ -422,8 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           tc_fence_after();
           if (ATLAS && (l == 0 || l == 4)) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + ATOM_BYTES, IDESC, first);
           if (l > 0) {
-            for (int j = 0; j < 4; ++j) {
-              const int kc = kChunkOrder[j];
+            for (int kc = 0; kc < 4; ++kc) {
               mbar_wait(&sm.a_ready[kc], ts_pass & 1);
               tc_fence_after();
               mma_chunk_ts(pp, tmem, kc, IDESC, first);
@@ -436,11 +441,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (256 threads)
+    // ------------------------------------------------------------------ epilogue warps (512 threads)
     EpiThread et; et.init(tmem);
-    const int m = et.m, hh = et.hh;
-    const bool issuer = (et.q == 0 && lane == 0);       // one bulk-store issuer per column half
-    const int bar_id = 1 + hh;
+    const int m = et.m, j = et.j;
     uint32_t d_par = 0;
     const float inv_scale = 1.0f / S_W;                 // D / (S_a S_w) * S_a : activations stay scaled by S_ACT
     for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
@@ -448,16 +451,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       const int64_t row = (int64_t)gt * TM + m;
       // ---------------- prologue: layer-0 input
       if (ATLAS) {
-        // positional encoding of in = uv*0.5+0.5 (implicit_neural_networks.py:9-13) into the aux tile
-        // (K-major SW128, columns k*4 + {sin x0, sin x1, cos x0, cos x1}); half 0 does k = 0..5, half 1 the rest
+        // positional encoding of in = x*in_scale+in_shift (implicit_neural_networks.py:9-13) into the aux tile
+        // (K-major SW128, columns k*4 + {sin x0, sin x1, cos x0, cos x1}); slice j does the 8-column chunks 2j, 2j+1
         const float2 uv = *reinterpret_cast<const float2*>(P.x + row * 2);
         const float in[2] = {uv.x * P.in_scale + P.in_shift, uv.y * P.in_scale + P.in_shift};
         char* a_hi = sm.aux;
         char* a_lo = sm.aux + ATOM_BYTES;
         char* g_hi = P.img.pe + (int64_t)gt * ATOM_BYTES;
         char* g_lo = g_hi + P.img.w64_term_stride;
-        const int c_begin = hh ? 3 : 0, c_end = hh ? 8 : 3;
-        for (int c8 = c_begin; c8 < c_end; ++c8) {     // chunks of 8 columns = 2 frequencies
+        for (int c8 = 2 * j; c8 < 2 * j + 2; ++c8) {     // chunks of 8 columns = 2 frequencies
           float vals[8];
 #pragma unroll
           for (int half_k = 0; half_k < 2; ++half_k) {
@@ -487,144 +489,123 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         tc_fence_before();
         mbar_arrive(sm.x_ready);
       } else {
-        // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0), this thread's 128 columns
+        // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0), this thread's two 32-column blocks
         const float4 xv = *reinterpret_cast<const float4*>(P.x + row * 4);
         char* img = P.img.act + (int64_t)gt * TILE_IMG_BYTES;
-        uint32_t bits[4];
 #pragma unroll
-        for (int ab = 0; ab < 2; ++ab) {               // two atom blocks of this half
-          uint32_t ph[32], pl[32];
+        for (int b = 0; b < 2; ++b) {
+          const int c0 = et.col0(b);
+          uint32_t ph[16], pl[16];
+          uint32_t bw = 0;
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = ab * 2 + cc;                 // chunk inside the half
-            uint32_t bw = 0;
+          for (int i = 0; i < 32; i += 2) {
+            float z[2];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float z[2];
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int n = hh * 128 + c * 32 + i + u;
-                float a = s_bias[n];
-                a = fmaf(xv.x, s_w0[n * 3 + 0], a);
-                a = fmaf(xv.y, s_w0[n * 3 + 1], a);
-                a = fmaf(xv.z, s_w0[n * 3 + 2], a);
-                bw |= (a > 0.f ? 1u : 0u) << (i + u);
-                z[u] = fmaxf(a, 0.f);
-              }
-              split2_f16(z[0], z[1], ph[cc * 16 + i / 2], pl[cc * 16 + i / 2]);
+            for (int u = 0; u < 2; ++u) {
+              const int n = c0 + i + u;
+              float a = s_bias[n];
+              a = fmaf(xv.x, s_w0[n * 3 + 0], a);
+              a = fmaf(xv.y, s_w0[n * 3 + 1], a);
+              a = fmaf(xv.z, s_w0[n * 3 + 2], a);
+              bw |= (a > 0.f ? 1u : 0u) << (i + u);
+              z[u] = fmaxf(a, 0.f);
             }
-            bits[c] = bw;
-            uint32_t th[16], tl[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { th[i] = ph[cc * 16 + i]; tl[i] = pl[cc * 16 + i]; }
-            tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
-            tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
+            split2_f16(z[0], z[1], ph[i / 2], pl[i / 2]);
           }
+          tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
+          tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&sm.a_ready[hh * 2 + ab]);       // k chunk hh*2+ab of A_1 is in TMEM
+          mbar_arrive(&sm.a_ready[et.kchunk(b)]);      // this thread's share of k chunk kchunk(b) of A_1 is in TMEM
           if (P.store_images) {
-            char* g = img + (hh * 2 + ab) * ATOM_BYTES;
-            stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+            char* g = img + et.kchunk(b) * ATOM_BYTES;
+            stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
+            P.img.bits[((int64_t)0 * P.img.rows + row) * 8 + (c0 >> 5)] = bw;
           }
         }
-        if (P.store_images)
-          *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)0 * P.img.rows + row) * 8 + hh * 4) =
-              make_uint4(bits[0], bits[1], bits[2], bits[3]);
       }
       // ---------------- tensor-core layers
       float outacc[OUT];
 #pragma unroll
-      for (int j = 0; j < OUT; ++j) outacc[j] = 0.f;
+      for (int jj = 0; jj < OUT; ++jj) outacc[jj] = 0.f;
 #pragma unroll 1
       for (int l = FIRST_TC; l <= LAST_TC; ++l) {
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
-        // drain this thread's 128 accumulator columns, then hand D back to the MMA warp
-        uint32_t raw[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw[c]);
+        // drain this thread's 64 accumulator columns, then hand D back to the MMA warp
+        uint32_t raw[2][32];
+        tmem_ld32(et.tlane + TM_D + et.col0(0), raw[0]);
+        tmem_ld32(et.tlane + TM_D + et.col0(1), raw[1]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(sm.d_free);
         const bool last = (l == LAST_TC);
         char* img = P.img.act + (int64_t)l * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
-        const float* bias = s_bias + l * 256 + hh * 128;
-        uint32_t bits[4];
 #pragma unroll
-        for (int ab = 0; ab < 2; ++ab) {
-          uint32_t ph[32], pl[32];
+        for (int b = 0; b < 2; ++b) {
+          const int c0 = et.col0(b);
+          const float* bias = s_bias + l * 256 + c0;
+          uint32_t ph[16], pl[16];
+          uint32_t bw = 0;
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = ab * 2 + cc;
-            uint32_t bw = 0;
+          for (int i = 0; i < 32; i += 2) {
+            const float z0 = fmaf(__uint_as_float(raw[b][i]), inv_scale, bias[i]);
+            const float z1 = fmaf(__uint_as_float(raw[b][i + 1]), inv_scale, bias[i + 1]);
+            bw |= (z0 > 0.f ? 1u : 0u) << i;
+            bw |= (z1 > 0.f ? 1u : 0u) << (i + 1);
+            const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
+            if (last) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float z0 = fmaf(__uint_as_float(raw[c][i]), inv_scale, bias[c * 32 + i]);
-              const float z1 = fmaf(__uint_as_float(raw[c][i + 1]), inv_scale, bias[c * 32 + i + 1]);
-              bw |= (z0 > 0.f ? 1u : 0u) << i;
-              bw |= (z1 > 0.f ? 1u : 0u) << (i + 1);
-              const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
-              if (last) {
-#pragma unroll
-                for (int j = 0; j < OUT; ++j) {
-                  outacc[j] = fmaf(v0, s_wlast[j * KLAST + hh * 128 + c * 32 + i], outacc[j]);
-                  outacc[j] = fmaf(v1, s_wlast[j * KLAST + hh * 128 + c * 32 + i + 1], outacc[j]);
-                }
+              for (int jj = 0; jj < OUT; ++jj) {
+                outacc[jj] = fmaf(v0, s_wlast[jj * KLAST + c0 + i], outacc[jj]);
+                outacc[jj] = fmaf(v1, s_wlast[jj * KLAST + c0 + i + 1], outacc[jj]);
               }
-              split2_f16(v0, v1, ph[cc * 16 + i / 2], pl[cc * 16 + i / 2]);
             }
-            bits[c] = bw;
-            if (!last) {
-              uint32_t th[16], tl[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) { th[i] = ph[cc * 16 + i]; tl[i] = pl[cc * 16 + i]; }
-              tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
-              tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
-            }
+            split2_f16(v0, v1, ph[i / 2], pl[i / 2]);
           }
           if (!last) {
+            tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
+            tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&sm.a_ready[hh * 2 + ab]);     // next layer's MMAs on this k chunk may start
+            mbar_arrive(&sm.a_ready[et.kchunk(b)]);     // next layer's MMAs on this k chunk may start
           }
           if (P.store_images) {
-            char* g = img + (hh * 2 + ab) * ATOM_BYTES;
-            stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+            char* g = img + et.kchunk(b) * ATOM_BYTES;
+            stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
+            P.img.bits[((int64_t)l * P.img.rows + row) * 8 + (c0 >> 5)] = bw;
           }
         }
-        if (P.store_images)
-          *reinterpret_cast<uint4*>(P.img.bits + ((int64_t)l * P.img.rows + row) * 8 + hh * 4) =
-              make_uint4(bits[0], bits[1], bits[2], bits[3]);
       }
-      // ---------------- output layer (+ skip part for the atlas) and tanh; the two column halves of a row
+      // ---------------- output layer (+ skip part for the atlas) and tanh; the four column slices of a row
       // combine through shared memory
       if (ATLAS) {
         const char* a_hi = sm.aux;
         const char* a_lo = sm.aux + ATOM_BYTES;
-        for (int k = hh * 20; k < hh * 20 + 20; ++k) {
+        for (int k = j * 10; k < j * 10 + 10; ++k) {
           const int off = atom_off(m, k);
           const float pv = __half2float(*reinterpret_cast<const __half*>(a_hi + off)) +
                            __half2float(*reinterpret_cast<const __half*>(a_lo + off));     // S_ACT * pe
 #pragma unroll
-          for (int j = 0; j < OUT; ++j) outacc[j] = fmaf(pv, s_wlast[j * KLAST + 256 + k], outacc[j]);
+          for (int jj = 0; jj < OUT; ++jj) outacc[jj] = fmaf(pv, s_wlast[jj * KLAST + 256 + k], outacc[jj]);
         }
       }
-      if (hh == 1) {
+      if (j > 0) {
 #pragma unroll
-        for (int j = 0; j < OUT; ++j) s_xch[m * 4 + j] = outacc[j];
+        for (int jj = 0; jj < OUT; ++jj) s_xch[((j - 1) * TM + m) * 4 + jj] = outacc[jj];
       }
-      named_bar(3, EPI_THREADS);
-      if (hh == 0) {
+      named_bar(BAR_EPI, EPI_THREADS);
+      if (j == 0) {
 #pragma unroll
-        for (int j = 0; j < OUT; ++j) {
-          const float o = outacc[j] + s_xch[m * 4 + j] + s_blast[j];
-          P.y[row * OUT + j] = P.tanh_out ? tanhf(o) : o;
+        for (int jj = 0; jj < OUT; ++jj) {
+          const float o = ((outacc[jj] + s_xch[(0 * TM + m) * 4 + jj]) + s_xch[(1 * TM + m) * 4 + jj]) +
+                          s_xch[(2 * TM + m) * 4 + jj] + s_blast[jj];
+          P.y[row * OUT + jj] = P.tanh_out ? tanhf(o) : o;
         }
       }
-      named_bar(3, EPI_THREADS);                         // s_xch / aux tile reuse by the next tile
+      named_bar(BAR_EPI, EPI_THREADS);                   // s_xch / aux tile reuse by the next tile
     }
-    if (issuer) bulk_wait_all0();
+    if ((j & 1) == 0 && lane == 0) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -707,10 +688,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
   constexpr int KLAST = ATLAS ? 296 : 256;
   constexpr int LOW = 1;                                  // dgrad layers L-2 .. 1 (atlas: + the dPE product)
   constexpr int N_DGRAD = L - 2 - LOW + 1;
-  // shared constants: last-layer weights; bias-gradient accumulators for layers 0..L-2; (mapping) dW0
+  // shared constants: last-layer weights; bias-gradient accumulators for layers 0..L-2; (mapping) dW0; (atlas) the
+  // exchange area of the dPE partial sums
   float* s_wlast = sm.cst;                               // OUT*KLAST (<= 888)
   float* s_bacc = sm.cst + 896;                          // (L-1)*256 (<= 1792)
-  float* s_w0acc = s_bacc + (L - 1) * 256;               // mapping: 768   (896+1280+768 = 2944 <= 3072)
+  float* s_w0acc = s_bacc + (L - 1) * 256;               // mapping: 768   (896+1280+768 = 2944)
+  float* s_xch = sm.cst + SMEM_CONST_FLOATS - TM * 2;    // atlas: [128][2]
   for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i];
   for (int i = threadIdx.x; i < (L - 1) * 256 + (ATLAS ? 0 : 768); i += blockDim.x) s_bacc[i] = 0.f;
   const uint32_t tmem = setup_cta(sm, warp);
@@ -735,10 +718,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
                    &sm.misc[0]);
           h_par ^= 1;
         }
-        for (int l = L - 2; l >= (ATLAS ? 0 : LOW); --l) {
-          const char* base = P.img.w_bwd + P.img.w_bwd_layer[l];
-          for (int j = 0; j < 4; ++j) produce_items(pp, base + (int64_t)kChunkOrder[j] * 2 * STAGE_BYTES, 2);
-        }
+        for (int l = L - 2; l >= (ATLAS ? 0 : LOW); --l) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[l], 8);
       }
     }
   } else if (warp == 1) {
@@ -751,8 +731,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
           tc_fence_after();
           bool first = true;
           const uint32_t idesc = (ATLAS && l == N_DGRAD) ? IDESC64 : IDESC;
-          for (int j = 0; j < 4; ++j) {
-            const int kc = kChunkOrder[j];
+          for (int kc = 0; kc < 4; ++kc) {
             mbar_wait(&sm.a_ready[kc], pass & 1);        // every pass of this kernel is a TMEM-operand pass
             tc_fence_after();
             mma_chunk_ts(pp, tmem, kc, idesc, first);
@@ -764,9 +743,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
     }
   } else {
     EpiThread et; et.init(tmem);
-    const int m = et.m, hh = et.hh;
-    const bool issuer = (et.q == 0 && lane == 0);
-    const int bar_id = 1 + hh;
+    const int m = et.m, j = et.j;
     uint32_t d_par = 0, aux_par = 0;
     const float inv_dgrad = inv_sg * (1.0f / S_W);        // D = (S_g dZ)(S_w W)
     for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
@@ -775,17 +752,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       // ---------------- output layer: tanh', bias gradient, the 64-wide dZ_L image, dA_{L-1}
       float dzl[OUT];
 #pragma unroll
-      for (int j = 0; j < OUT; ++j) {
-        const float yv = P.y[row * OUT + j];
-        dzl[j] = P.dy[row * OUT + j] * (P.tanh_out ? (1.0f - yv * yv) : 1.0f);
+      for (int jj = 0; jj < OUT; ++jj) {
+        const float yv = P.y[row * OUT + jj];
+        dzl[jj] = P.dy[row * OUT + jj] * (P.tanh_out ? (1.0f - yv * yv) : 1.0f);
       }
-      if (hh == 0) {
+      if (j == 0) {
 #pragma unroll
-        for (int j = 0; j < OUT; ++j) {
-          float sj = dzl[j];
+        for (int jj = 0; jj < OUT; ++jj) {
+          float sj = dzl[jj];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sj += __shfl_xor_sync(0xffffffffu, sj, o);
-          if (lane == 0 && sj != 0.f) atomicAdd(P.grads + P.b_off[L - 1] + j, sj);
+          if (lane == 0 && sj != 0.f) atomicAdd(P.grads + P.b_off[L - 1] + jj, sj);
         }
         // image row: columns 0..OUT-1 = S_g * dz, rest zero
         uint32_t h0, l0, h1 = 0, l1 = 0;
@@ -804,38 +781,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       }
       // dA_{L-1}[k] = sum_j dz[j] W_last[j][k], masked by relu'(h_{L-2}) -> dZ_{L-2}
       {
-        const uint4 bb = *reinterpret_cast<const uint4*>(P.img.bits + ((int64_t)(L - 2) * P.img.rows + row) * 8 + hh * 4);
-        const uint32_t bits[4] = {bb.x, bb.y, bb.z, bb.w};
         char* img = P.img.dz + (int64_t)(L - 2) * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
 #pragma unroll
-        for (int ab = 0; ab < 2; ++ab) {
-          uint32_t ph[32], pl[32];
+        for (int b = 0; b < 2; ++b) {
+          const int c0 = et.col0(b);
+          const uint32_t bits = P.img.bits[((int64_t)(L - 2) * P.img.rows + row) * 8 + (c0 >> 5)];
+          float v[32];
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = ab * 2 + cc;
-            float v[32];
+          for (int i = 0; i < 32; ++i) {
+            float a = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float a = 0.f;
-#pragma unroll
-              for (int j = 0; j < OUT; ++j) a = fmaf(dzl[j], s_wlast[j * KLAST + hh * 128 + c * 32 + i], a);
-              v[i] = ((bits[c] >> i) & 1u) ? a : 0.f;
-            }
-            atomicAdd(&s_bacc[(L - 2) * 256 + hh * 128 + c * 32 + lane], warp_colsum32(v, lane));
-            uint32_t th[16], tl[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, th[i], tl[i]);
-              ph[cc * 16 + i] = th[i]; pl[cc * 16 + i] = tl[i];
-            }
-            tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
-            tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
+            for (int jj = 0; jj < OUT; ++jj) a = fmaf(dzl[jj], s_wlast[jj * KLAST + c0 + i], a);
+            v[i] = ((bits >> i) & 1u) ? a : 0.f;
           }
+          atomicAdd(&s_bacc[(L - 2) * 256 + c0 + lane], warp_colsum32(v, lane));
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
+          tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
+          tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&sm.a_ready[hh * 2 + ab]);
-          char* g = img + (hh * 2 + ab) * ATOM_BYTES;
-          stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+          mbar_arrive(&sm.a_ready[et.kchunk(b)]);
+          char* g = img + et.kchunk(b) * ATOM_BYTES;
+          stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
         }
       }
       // ---------------- hidden layers: dA_l = dZ_l W_l  ->  dZ_{l-1}
@@ -843,65 +812,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       for (int l = L - 2; l >= LOW; --l) {
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
-        uint32_t raw[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(et.tlane + TM_D + hh * 128 + c * 32, raw[c]);
+        uint32_t raw[2][32];
+        tmem_ld32(et.tlane + TM_D + et.col0(0), raw[0]);
+        tmem_ld32(et.tlane + TM_D + et.col0(1), raw[1]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(sm.d_free);
         const int slot = l - 1;                           // produces dZ_{l-1}
-        const uint4 bb = *reinterpret_cast<const uint4*>(P.img.bits + ((int64_t)slot * P.img.rows + row) * 8 + hh * 4);
-        const uint32_t bits[4] = {bb.x, bb.y, bb.z, bb.w};
         const bool need_img = ATLAS || slot >= 1;         // mapping dZ_0 feeds only the CUDA-core layer-0 gradient
         const bool need_tmem = ATLAS ? true : (slot >= 1);
         char* img = P.img.dz + (int64_t)slot * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!ATLAS && slot == 0) xv = *reinterpret_cast<const float4*>(P.x + row * 4);
 #pragma unroll
-        for (int ab = 0; ab < 2; ++ab) {
-          uint32_t ph[32], pl[32];
+        for (int b = 0; b < 2; ++b) {
+          const int c0 = et.col0(b);
+          const uint32_t bits = P.img.bits[((int64_t)slot * P.img.rows + row) * 8 + (c0 >> 5)];
+          float v[32];
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = ab * 2 + cc;
-            float v[32];
+          for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? __uint_as_float(raw[b][i]) * inv_dgrad : 0.f;
+          atomicAdd(&s_bacc[slot * 256 + c0 + lane], warp_colsum32(v, lane));
+          if (!ATLAS && slot == 0) {
+            // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
+            const int n = c0 + lane;
+            float w[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ((bits[c] >> i) & 1u) ? __uint_as_float(raw[c][i]) * inv_dgrad : 0.f;
-            atomicAdd(&s_bacc[slot * 256 + hh * 128 + c * 32 + lane], warp_colsum32(v, lane));
-            if (!ATLAS && slot == 0) {
-              // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
-              const int n = hh * 128 + c * 32 + lane;
-              float w[32];
+            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.x;
+            atomicAdd(&s_w0acc[n * 3 + 0], warp_colsum32(w, lane));
 #pragma unroll
-              for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.x;
-              atomicAdd(&s_w0acc[n * 3 + 0], warp_colsum32(w, lane));
+            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.y;
+            atomicAdd(&s_w0acc[n * 3 + 1], warp_colsum32(w, lane));
 #pragma unroll
-              for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.y;
-              atomicAdd(&s_w0acc[n * 3 + 1], warp_colsum32(w, lane));
-#pragma unroll
-              for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.z;
-              atomicAdd(&s_w0acc[n * 3 + 2], warp_colsum32(w, lane));
-            }
-            if (need_img || need_tmem) {
-              uint32_t th[16], tl[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, th[i], tl[i]);
-                ph[cc * 16 + i] = th[i]; pl[cc * 16 + i] = tl[i];
-              }
-              if (need_tmem) {
-                tmem_st16(et.tlane + TM_AHI + hh * 64 + c * 16, th);
-                tmem_st16(et.tlane + TM_ALO + hh * 64 + c * 16, tl);
-              }
-            }
+            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.z;
+            atomicAdd(&s_w0acc[n * 3 + 2], warp_colsum32(w, lane));
           }
-          if (need_tmem) {
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&sm.a_ready[hh * 2 + ab]);
-          }
-          if (need_img) {
-            char* g = img + (hh * 2 + ab) * ATOM_BYTES;
-            stage_and_store(et, sm.staging, ph, pl, g, g + P.img.term_stride, issuer, bar_id);
+          if (need_img || need_tmem) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
+            if (need_tmem) {
+              tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
+              tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(&sm.a_ready[et.kchunk(b)]);
+            }
+            if (need_img) {
+              char* g = img + et.kchunk(b) * ATOM_BYTES;
+              stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
+            }
           }
         }
       }
@@ -910,54 +869,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
         mbar_wait(&sm.misc[0], aux_par);                  // PE tile of this row block
-        uint32_t raw[2][32];
-        if (hh == 0) {
-          tmem_ld32(et.tlane + TM_D, raw[0]);
-          tmem_ld32(et.tlane + TM_D + 32, raw[1]);
+        uint32_t raw[32];
+        if (j < 2) {                                      // slices 0 and 1 hold the 64 accumulator columns
+          tmem_ld32(et.tlane + TM_D + j * 32, raw);
           tmem_ld_wait();
         }
         tc_fence_before();
         mbar_arrive(sm.d_free);
-        if (hh == 0) {
-          float din[2] = {0.f, 0.f};
+        float din[2] = {0.f, 0.f};
+        if (j < 2) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = c * 32 + i;
-              if (col < PE_COLS) {
-                const int k = col >> 2, e = col & 3;       // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
-                const float g = __uint_as_float(raw[c][i]) * inv_dgrad;
-                const int pcol = (e < 2) ? col + 2 : col - 2;   // d sin = cos * b,  d cos = -sin * b
-                const int off = atom_off(m, pcol);
-                const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
-                                       __half2float(*reinterpret_cast<const __half*>(sm.aux + ATOM_BYTES + off))) *
-                                      (1.0f / S_ACT);
-                const float bk = pe_freq(k);
-                din[e & 1] += (e < 2) ? g * partner * bk : -g * partner * bk;
-              }
+          for (int i = 0; i < 32; ++i) {
+            const int col = j * 32 + i;
+            if (col < PE_COLS) {
+              const int k = col >> 2, e = col & 3;         // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
+              const float g = __uint_as_float(raw[i]) * inv_dgrad;
+              const int pcol = (e < 2) ? col + 2 : col - 2;     // d sin = cos * b,  d cos = -sin * b
+              const int off = atom_off(m, pcol);
+              const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
+                                     __half2float(*reinterpret_cast<const __half*>(sm.aux + ATOM_BYTES + off))) *
+                                    (1.0f / S_ACT);
+              const float bk = pe_freq(k);
+              din[e & 1] += (e < 2) ? g * partner * bk : -g * partner * bk;
             }
           }
-          if (P.d_in) {
-            float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
-            float2 cur = P.d_in_accumulate ? *dst : make_float2(0.f, 0.f);
-            cur.x += P.in_scale * din[0];
-            cur.y += P.in_scale * din[1];
-            *dst = cur;
-            float mx = fmaxf(fabsf(cur.x), fabsf(cur.y));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0 && mx > 0.f) atomicMax(P.gmax_bits + 1, __float_as_int(mx));
-          }
+          if (j == 1) { s_xch[m * 2] = din[0]; s_xch[m * 2 + 1] = din[1]; }
         }
+        named_bar(BAR_EPI, EPI_THREADS);
+        if (j == 0 && P.d_in) {
+          float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
+          float2 cur = P.d_in_accumulate ? *dst : make_float2(0.f, 0.f);
+          cur.x += P.in_scale * (din[0] + s_xch[m * 2]);
+          cur.y += P.in_scale * (din[1] + s_xch[m * 2 + 1]);
+          *dst = cur;
+          float mx = fmaxf(fabsf(cur.x), fabsf(cur.y));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (lane == 0 && mx > 0.f) atomicMax(P.gmax_bits + 1, __float_as_int(mx));
+        }
+        named_bar(BAR_EPI, EPI_THREADS);                  // s_xch reuse
         tc_fence_before();
         mbar_arrive(&sm.misc[1]);                         // aux tile may be overwritten
         aux_par ^= 1;
       }
     }
-    if (issuer) bulk_wait_all0();
+    if ((j & 1) == 0 && lane == 0) bulk_wait_all0();
     // flush the per-CTA accumulators
-    named_bar(3, EPI_THREADS);
+    named_bar(BAR_EPI, EPI_THREADS);
     for (int i = et.tid; i < (L - 1) * 256; i += EPI_THREADS) {
       const float v = s_bacc[i];
       if (v != 0.f) atomicAdd(P.grads + P.b_off[i >> 8] + (i & 255), v);
