@@ -74,6 +74,7 @@ SIGNATURES = {
     "b200_video_pack": (C.c_int, [_P] * 7 + [_I32] * 5 + [_P, _P, _P, _P]),
     "b200_atlas_param_floats": (_I64, []),
     "b200_atlas_workspace_bytes": (_I64, [C.POINTER(AtlasConfig)]),
+    "b200_atlas_workspace_offsets": (C.c_int, [C.POINTER(AtlasConfig), _P, C.POINTER(_I64)]),
     "b200_atlas_loss_grad": (C.c_int, [C.POINTER(AtlasConfig), C.POINTER(Video), _P, _P, _P, _P, _P, _I64, _P]),
     "b200_pretrain_loss_grad": (C.c_int, [C.POINTER(AtlasConfig), _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "b200_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P, _P]),

@@ -248,6 +248,19 @@ class AtlasTrainer:
             self._ws.zero_()
         return self._ws
 
+    def workspace_views(self):
+        """Intermediate buffers of the last step as tensor views (tests / debugging): counters, x_map
+        [9][cap][4], targets [cap][12], uv [9][cap][2], y_atlas [3][cap][3]."""
+        cfg = self._config(True)
+        ws = self._workspace()
+        off = (C.c_int64 * 8)()
+        N.check(self.lib.b200_atlas_workspace_offsets(C.byref(cfg), N.ptr(ws), off), "b200_atlas_workspace_offsets")
+        cap = (cfg.batch + 127) // 128 * 128
+        f32 = lambda o, n, *shape: ws[o:o + 4 * n].view(torch.float32).view(*shape)
+        return dict(cap=cap, counters=ws[off[0]:off[0] + 32].view(torch.int32),
+                    x_map=f32(off[2], 9 * cap * 4, 9, cap, 4), targets=f32(off[3], cap * 12, cap, 12),
+                    uv=f32(off[6], 9 * cap * 2, 9, cap, 2), y_atlas=f32(off[7], 3 * cap * 3, 3, cap, 3))
+
     def uses_global(self, it: int) -> bool:
         return bool(self.cfg["include_global_rigidity_loss"]) and it <= self.cfg["stop_global_rigidity"]
 

@@ -272,6 +272,23 @@ int64_t b200_atlas_workspace_bytes(const B200AtlasConfig* cfg) {
   return pl.bytes + 256 + 2048;      // slack for the 256 / 1024-byte alignment of the real base address
 }
 
+int b200_atlas_workspace_offsets(const B200AtlasConfig* cfg, const void* ws, int64_t* offsets) {
+  B200_REQUIRE(cfg && ws && offsets, "null pointer");
+  AtlasPlan pl;
+  char* base = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(ws), 256));
+  B200_PROPAGATE(plan_atlas(cfg, base, &pl));
+  const char* w = reinterpret_cast<const char*>(ws);
+  offsets[0] = reinterpret_cast<char*>(pl.counters) - w;
+  offsets[1] = reinterpret_cast<char*>(pl.list) - w;
+  offsets[2] = reinterpret_cast<char*>(pl.x_map) - w;
+  offsets[3] = reinterpret_cast<char*>(pl.targets) - w;
+  offsets[4] = reinterpret_cast<char*>(pl.d_uv) - w;
+  offsets[5] = reinterpret_cast<char*>(pl.d_y) - w;
+  offsets[6] = reinterpret_cast<char*>(pl.map.y) - w;
+  offsets[7] = reinterpret_cast<char*>(pl.atlas.y) - w;
+  return B200_OK;
+}
+
 static int atlas_prepare(const B200AtlasConfig* cfg, void* ws, int64_t ws_bytes, AtlasPlan* pl) {
   B200_REQUIRE(ws != nullptr, "null workspace");
   char* base = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(ws), 256));

@@ -159,6 +159,13 @@ int b200_atlas_loss_grad(const B200AtlasConfig* cfg, const B200Video* video,
                          const int64_t* indices, const float* params, float* grads,
                          float* losses, void* ws, int64_t ws_bytes, void* stream);
 
+/* Test / debugging aid: byte offsets (from `ws`) of the step's intermediate buffers inside the
+ * workspace, for the configuration `cfg`: [0] counters (int32: n_local, n_fwd, n_bwd, ...),
+ * [1] local sample list, [2] coordinate rows x_map [groups][cap][4], [3] gathered targets
+ * [cap][12], [4] d_uv, [5] d_y, [6] mapping output uv [groups][cap][2], [7] atlas output
+ * [3][cap][3].  cap = batch rounded up to 128. */
+int b200_atlas_workspace_offsets(const B200AtlasConfig* cfg, const void* ws, int64_t* offsets);
+
 /* One pre_train_mapping step (src/models/stage_1/unwrap_utils.py:182-195): rows ys / columns
  * xs (int64[batch]) of frame `frame`; gradients of the mapping block only; loss -> losses[0]. */
 int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int32_t T,

@@ -148,22 +148,17 @@ def test_loss_grad_parity_and_exact_sampling(golden_dir, it):
     ref = [float(terms[k].detach()) if k in terms else 0.0
            for k in ("total", "rgb", "gradient", "rigidity", "rigidity_global", "flow")]
     np.testing.assert_allclose(losses[:6], ref, rtol=2e-4)
-    # ---- exact sampling: coordinate rows, gathered targets, counts (workspace layout of c_api.cu)
-    cap = (B + 127) // 128 * 128
-    ws = tr._workspace()
-    base = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr()
-    r256 = lambda n: (n + 255) // 256 * 256
-    off_cnt, off_list = base, base + 256
-    off_x = off_list + r256(cap * 4)
-    off_t = off_x + r256(9 * cap * 16)
-    counters = ws[off_cnt:off_cnt + 12].view(torch.int32).cpu()
+    # ---- exact sampling: coordinate rows, gathered targets, counts
+    view = tr.workspace_views()
+    cap = view["cap"]
+    counters = view["counters"].cpu()[:3]
     H, W, T = video.H, video.W, video.T
     jif = O.pixel_table(T, H, W)[:, inds]
     wf = video.mask_fwd[jif[1].squeeze(), jif[0].squeeze(), jif[2].squeeze(), 0] != 0
     wb = video.mask_bwd[jif[1].squeeze(), jif[0].squeeze(), jif[2].squeeze(), 0] != 0
     assert counters.tolist() == [B, int(wf.sum()), int(wb.sum())]
     assert losses[6] == int(wf.sum()) and losses[7] == int(wb.sum())
-    x_map = ws[off_x:off_x + 9 * cap * 16].view(torch.float32).view(9, cap, 4).cpu()
+    x_map = view["x_map"].cpu()
     larger = max(W, H)
     assert torch.equal(x_map[0, :B, :3], O.normalise_xyt(jif, larger, T))
     hx = O._half(W)
@@ -182,7 +177,7 @@ def test_loss_grad_parity_and_exact_sampling(golden_dir, it):
     _, xyt_b, rows_b = O.flow_matches(jif, video.mask_bwd, video.flow_bwd, larger, T, False, uv_dummy)
     assert torch.equal(x_map[5, rows_f, :3], xyt_f) and torch.equal(x_map[6, rows_b, :3], xyt_b)
     assert torch.all(x_map[:, B:] == 0)
-    tg = ws[off_t:off_t + cap * 48].view(torch.float32).view(cap, 12).cpu()
+    tg = view["targets"].cpu()
     assert torch.equal(tg[:B, 0:3], video.frames[jif[1], jif[0], :, jif[2]].squeeze(1))
     assert torch.equal(tg[:B, 3:6], video.frames_dx[jif[1], jif[0], :, jif[2]].squeeze(1))
     assert torch.equal(tg[:B, 6:9], video.frames_dy[jif[1], jif[0], :, jif[2]].squeeze(1))
@@ -238,11 +233,14 @@ def test_five_step_trajectory_with_graph_replay(golden_dir):
             # normalised update differs, so single entries may be off by a fraction of one step;
             # the bulk must agree to fp32 rounding
             d = (v.cpu() - r.detach()).abs()
-            # Adam's first steps move every parameter by ~lr*sign(g): a gradient component that is pure
-            # summation noise can go either way, so single entries may differ by up to 2*lr per step
-            assert d.max() <= 1.1e-3, (which, k, float(d.max()))
+            # 5 Adam steps of lr 1e-4.  Measured on B200 (tests/perf/parity_diag.py): max 1.1e-4 (a component
+            # whose gradient is summation noise flips the sign of one normalised update), mean <= 7e-7,
+            # <= 0.05 % of a tensor's entries beyond 2e-5.  Bounds = measured x 5-10 (the theoretical maximum
+            # divergence, 5 x 2 lr = 1e-3, is far above them).
+            assert d.max() <= 5e-4, (which, k, float(d.max()))
+            assert d.mean() <= 5e-6, (which, k, float(d.mean()))
             if d.numel() >= 1000:
-                assert d.median() <= 1e-5 and (d > 2e-5).float().mean() <= 0.2, \
+                assert d.median() <= 2e-6 and (d > 2e-5).float().mean() <= 5e-3, \
                     (which, k, float(d.median()), float((d > 2e-5).float().mean()))
     sd = tr.optimizer_state_dict()
     assert len(sd["state"]) == 28 and sd["param_groups"][1]["params"][0] == 12

@@ -40,17 +40,9 @@ def _params(golden_dir):
 
 
 def _tc_outputs(tr, B):
-    cap = (B + 127) // 128 * 128
-    ws = tr._workspace()
-    r256 = lambda n: (n + 255) // 256 * 256
-    off = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr() + 256
-    off += r256(cap * 4)
-    off_x = off; off += r256(9 * cap * 16)
-    off += r256(cap * 48) + r256(9 * cap * 8) + r256(3 * cap * 12) + r256(3 * cap * 160)
-    x = ws[off_x:off_x + 9 * cap * 16].view(torch.float32).view(9 * cap, 4)
-    uv = ws[off:off + 9 * cap * 8].view(torch.float32).view(9 * cap, 2); off += r256(9 * cap * 8)
-    y = ws[off:off + 3 * cap * 12].view(torch.float32).view(3 * cap, 3)
-    return cap, x, uv, y
+    view = tr.workspace_views()
+    cap = view["cap"]
+    return cap, view["x_map"].reshape(9 * cap, 4), view["uv"].reshape(9 * cap, 2), view["y_atlas"].reshape(3 * cap, 3)
 
 
 @pytest.mark.parametrize("B,shape", [(64, (24, 40, 6)), (3000, (60, 100, 9))])
@@ -131,11 +123,14 @@ def test_tc_trajectory_and_pretrain(golden_dir):
     for which, ref_p in (("mapping", mp), ("atlas", ap)):
         for (k, v), r in zip(tr.param_views(which).items(), ref_p):
             d = (v.cpu() - r.detach()).abs()
-            # Adam's first steps move every parameter by ~lr*sign(g): a gradient component that is pure
-            # summation noise can go either way, so single entries may differ by up to 2*lr per step
+            # 5 Adam steps of lr 1e-4 on an ill-conditioned toy (random-init mapping, 64 samples).  Measured on
+            # B200 (tests/perf/parity_diag.py): max 5.6e-4, mean <= 1.1e-5, <= 14 % of a tensor's entries beyond
+            # 2e-5 and <= 1.2 % beyond one learning-rate step.  Bounds = measured x ~2; the well-conditioned,
+            # full-size version with tight bounds is tests/test_tc_fullsize_gpu.py.
             assert d.max() <= 1.1e-3, (which, k, float(d.max()))
+            assert d.mean() <= 2.5e-5, (which, k, float(d.mean()))
             if d.numel() >= 1000:
-                assert d.median() <= 1e-5 and (d > 2e-5).float().mean() <= 0.2, \
+                assert d.median() <= 1.2e-5 and (d > 2e-5).float().mean() <= 0.25 and (d > 1e-4).float().mean() <= 0.03, \
                     (which, k, float(d.median()), float((d > 2e-5).float().mean()))
     # pre-training on the tensor-core path
     tr2 = A.AtlasTrainer(vid, {"samples_batch": 10000}, precision=N.PREC_TC, device=DEV)
