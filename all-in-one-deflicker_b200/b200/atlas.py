@@ -362,16 +362,22 @@ class AtlasTrainer:
         return last
 
     # ------------------------------------------------------------------ render / evaluate
-    def render_frame(self, f: int, H: int, W: int, T: int, chunk: int = 131072, want_u8: bool = False):
-        """Reconstruction of frame f (evaluate.py:644-666): (H, W, 3) fp32 [and uint8 by truncation]."""
+    def render_frame(self, f: int, H: int, W: int, T: int, chunk: Optional[int] = None, want_u8: bool = False,
+                     precision: Optional[int] = None):
+        """Reconstruction of frame f (evaluate.py:644-666): (H, W, 3) fp32 [and uint8 by truncation].  Runs in the
+        trainer's precision (tensor cores when the step does); the workspace is kept between calls."""
+        prec = self.precision if precision is None else precision
+        chunk = H * W if chunk is None else min(chunk, H * W)
         rgb = torch.empty(H * W * 3, dtype=torch.float32, device=self.device)
         u8 = torch.empty(H * W * 3, dtype=torch.uint8, device=self.device) if want_u8 else None
-        nbytes = int(self.lib.b200_render_workspace_bytes(min(chunk, H * W)))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        nbytes = int(self.lib.b200_render_workspace_bytes(chunk))
+        ws = getattr(self, "_render_ws", None)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._render_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         for p0 in range(0, H * W, chunk):
             p1 = min(H * W, p0 + chunk)
             N.check(self.lib.b200_render(N.ptr(self.params), H, W, T, f, p0, p1, N.ptr(rgb[p0 * 3:]),
-                                         N.ptr(u8[p0 * 3:]) if want_u8 else None, N.PREC_FP32, N.ptr(ws),
+                                         N.ptr(u8[p0 * 3:]) if want_u8 else None, prec, N.ptr(ws),
                                          ws.numel(), N.current_stream()), "b200_render")
         out = rgb.view(H, W, 3)
         return (out, u8.view(H, W, 3)) if want_u8 else out

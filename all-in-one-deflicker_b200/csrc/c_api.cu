@@ -430,8 +430,11 @@ int64_t b200_render_workspace_bytes(int64_t pixels) {
   resolve_mlp(&mapping_desc(), &m);
   resolve_mlp(&atlas_desc(), &a);
   const int64_t rows = round_up(pixels, kTileRows);
-  return round_up(rows * 16, 256) + plan_mlp_scratch(m, rows, false, nullptr, nullptr) +
-         plan_mlp_scratch(a, rows, false, nullptr, nullptr) + 512;
+  const int64_t fp32_path = round_up(rows * 16, 256) + plan_mlp_scratch(m, rows, false, nullptr, nullptr) +
+                            plan_mlp_scratch(a, rows, false, nullptr, nullptr) + 512;
+  const int64_t tc_path = round_up(rows * 16, 256) + round_up(rows * 8, 256) + round_up(rows * 12, 256) +
+                          tc_infer_workspace_bytes(m, a) + 1024;
+  return fp32_path > tc_path ? fp32_path : tc_path;
 }
 
 int b200_render(const float* params, int32_t H, int32_t W, int32_t T, int32_t frame, int64_t pix_begin,
@@ -445,7 +448,11 @@ int b200_render(const float* params, int32_t H, int32_t W, int32_t T, int32_t fr
     set_error("workspace too small: need %lld bytes", (long long)b200_render_workspace_bytes(count));
     return B200_ERR_WORKSPACE;
   }
-  B200_REQUIRE(precision == B200_PREC_FP32, "render runs the fp32 path in this build");
+  B200_REQUIRE(precision == B200_PREC_FP32 || precision == B200_PREC_TC, "unknown precision %d", precision);
+  if (precision == B200_PREC_TC && !b200_device_supports_tc()) {
+    set_error("B200_PREC_TC needs a compute-capability 10.x device");
+    return B200_ERR_UNSUPPORTED;
+  }
   MlpShape m, a;
   B200_PROPAGATE(resolve_mlp(&mapping_desc(), &m));
   B200_PROPAGATE(resolve_mlp(&atlas_desc(), &a));
@@ -453,12 +460,20 @@ int b200_render(const float* params, int32_t H, int32_t W, int32_t T, int32_t fr
   const int64_t rows = round_up(count, kTileRows);
   char* p = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(ws), 256));
   float* x_map = reinterpret_cast<float*>(carve(p, rows * 16));
-  MlpScratch sm, sa;
-  p += plan_mlp_scratch(m, rows, false, p, &sm);
-  p += plan_mlp_scratch(a, rows, false, p, &sa);
   const int larger = W > H ? W : H;
   const float t_norm = (float)((double)frame / ((double)T / 2.0) - 1.0);   // evaluate.py:657
   B200_PROPAGATE(launch_render_rows(W, half_of(larger), t_norm, pix_begin, count, rows, x_map, st));
+  if (precision == B200_PREC_TC) {
+    // the two fused tcgen05 forward kernels without their activation-image stores
+    float* uv = reinterpret_cast<float*>(carve(p, rows * 8));
+    float* y = reinterpret_cast<float*>(carve(p, rows * 12));
+    B200_PROPAGATE(tc_infer_forward(m, a, params, x_map, uv, y, rows, p, st));
+    B200_PROPAGATE(launch_render_out(y, count, rgb, rgb_u8, st));
+    return B200_OK;
+  }
+  MlpScratch sm, sa;
+  p += plan_mlp_scratch(m, rows, false, p, &sm);
+  p += plan_mlp_scratch(a, rows, false, p, &sa);
   RowSpan span{rows, 0, nullptr};
   B200_PROPAGATE(simt_mlp_forward(m, params, x_map, 4, span, sm, sm.y, st));
   float* skips[2] = {sa.act[4], sa.act[7]};

@@ -1335,6 +1335,98 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   return B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// inference: mapping -> atlas on `rows` coordinate rows, no activation images (full-video render,
+// evaluate.py:640-708).  Workspace: [PrepJobs table][forward weight images of both networks].
+// ---------------------------------------------------------------------------------------------
+struct InferTables { int dev; const void* base; const void* params; PrepJobs* d_prep; int n_prep; };
+static std::vector<InferTables> g_infer_tabs;
+
+static void plan_infer(const MlpShape& ms, const MlpShape& as, char* base, NetImages* im_map, NetImages* im_atl,
+                       PrepJobs** d_prep, int64_t* bytes) {
+  char* p = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(base), 1024));
+  *d_prep = reinterpret_cast<PrepJobs*>(carve_tc(p, sizeof(PrepJobs)));
+  for (int net = 0; net < 2; ++net) {
+    const MlpShape& s = net ? as : ms;
+    NetImages* n = net ? im_atl : im_map;
+    *n = NetImages{};
+    int64_t off = 0;
+    for (int l = 0; l < s.L; ++l) {
+      int chunks = 0;
+      const bool tc_layer = net ? (l <= s.L - 2) : (l >= 1 && l <= s.L - 2);
+      if (tc_layer) chunks = (l == 0 ? 0 : HID / 64) + ((l == 0 || s.skip[l]) && net ? 1 : 0);
+      n->n_chunks_fwd[l] = chunks;
+      n->w_fwd_layer[l] = off;
+      off += (int64_t)chunks * 2 * STAGE_BYTES;
+    }
+    n->w_fwd = carve_tc(p, off);
+  }
+  *bytes = p - base;
+}
+
+int64_t tc_infer_workspace_bytes(const MlpShape& ms, const MlpShape& as) {
+  NetImages a, b; PrepJobs* d; int64_t bytes = 0;
+  plan_infer(ms, as, nullptr, &a, &b, &d, &bytes);
+  return bytes + 2048;
+}
+
+int tc_infer_forward(const MlpShape& ms, const MlpShape& as, const float* params, const float* x_map, float* uv,
+                     float* y, int64_t rows, char* ws, cudaStream_t st) {
+  B200_PROPAGATE(ensure_attrs());
+  B200_REQUIRE(as.L == 8 && ms.L == 6 && as.skip[4] && as.skip[7] && as.pe == 10 && ms.pe == 0 && as.hidden == HID &&
+               ms.hidden == HID, "tensor-core path is specialised to the two stage-1 networks");
+  B200_REQUIRE(rows > 0 && rows % TM == 0 && rows / TM < (1 << 24), "rows must be a positive multiple of %d", TM);
+  NetImages im_map, im_atl; PrepJobs* d_prep; int64_t bytes;
+  plan_infer(ms, as, ws, &im_map, &im_atl, &d_prep, &bytes);
+  const int dev = current_device();
+  InferTables* tab = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_tabs_mutex);
+    for (auto& t : g_infer_tabs) if (t.dev == dev && t.base == ws && t.params == params) tab = &t;
+  }
+  if (!tab) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    B200_REQUIRE(cs != cudaStreamCaptureStatusActive, "the first tensor-core render call on a workspace must be eager");
+    std::unique_ptr<PrepJobs> pj(new PrepJobs());
+    pj->n = 0;
+    for (int net = 0; net < 2; ++net) {
+      const MlpShape& sh = net ? as : ms;
+      const NetImages& im = net ? im_atl : im_map;
+      const float* pp = net ? params + ms.total : params;
+      for (int l = 0; l < sh.L; ++l) {
+        if (im.n_chunks_fwd[l] == 0) continue;
+        char* dst = im.w_fwd + im.w_fwd_layer[l];
+        const float* Wl = pp + sh.w_off[l];
+        int item = 0;
+        if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(*pj, Wl, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+        if (net && (l == 0 || sh.skip[l]))
+          add_prep(*pj, Wl, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+      }
+    }
+    B200_CHECK_CUDA(cudaMemcpyAsync(d_prep, pj.get(), sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
+    B200_CHECK_CUDA(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> lock(g_tabs_mutex);
+    g_infer_tabs.push_back(InferTables{dev, ws, params, d_prep, pj->n});
+    tab = &g_infer_tabs.back();
+  }
+  tc_prep_kernel<<<tab->n_prep * 4, 128, 0, st>>>(tab->d_prep);
+  B200_CHECK_LAUNCH();
+  const int tiles = (int)(rows / TM);
+  FwdParams pm{};
+  fill_fwd(pm, ms, im_map, x_map, uv, params, (int)rows, 1, nullptr);
+  pm.store_images = 0;
+  tc_fwd_kernel<false><<<min(sm_count(), tiles), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
+  B200_CHECK_LAUNCH();
+  FwdParams pa{};
+  fill_fwd(pa, as, im_atl, uv, y, params + ms.total, (int)rows, 1, nullptr);
+  pa.store_images = 0;
+  tc_fwd_kernel<true><<<min(sm_count(), tiles), TC_THREADS, KCfg<true>::SMEM, st>>>(pa);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 int tc_atlas_forward(const TcStep& s, cudaStream_t st) { return run_forward(s, true, st); }
 int tc_atlas_backward(const TcStep& s, cudaStream_t st) { return run_backward(s, true, st); }
 int tc_mapping_forward(const TcStep& s, cudaStream_t st) { return run_forward(s, false, st); }

@@ -31,4 +31,9 @@ int tc_atlas_backward(const TcStep& s, cudaStream_t st);   // all parameter grad
 int tc_mapping_forward(const TcStep& s, cudaStream_t st);  // pre-training: mapping only
 int tc_mapping_backward(const TcStep& s, cudaStream_t st);
 
+// inference (render): x_map [rows][4] -> uv [rows][2] -> y [rows][3]; rows a multiple of 128; ws >= tc_infer_workspace_bytes
+int64_t tc_infer_workspace_bytes(const MlpShape& ms, const MlpShape& as);
+int tc_infer_forward(const MlpShape& ms, const MlpShape& as, const float* params, const float* x_map, float* uv,
+                     float* y, int64_t rows, char* ws, cudaStream_t st);
+
 }  // namespace b200

@@ -149,3 +149,27 @@ def test_tc_trajectory_and_pretrain(golden_dir):
     np.testing.assert_allclose(float(last[0]), float(loss.detach()), rtol=1e-4)
     for (k, v), r in zip(tr2.param_views("mapping").items(), mpp):
         assert (v.cpu() - r.detach()).abs().max() <= 1e-5, k
+
+
+def test_tc_render_parity(golden_dir):
+    """b200_render with B200_PREC_TC (the fused forward kernels without their image stores) against the oracle's
+    render (evaluate.py:640-708): |err| <= 5e-5 on the fp32 image (the atlas-output tolerance above), uint8 frames
+    within 1 LSB, PSNR within 1e-3 dB; ragged chunks and a whole-frame call give the same image."""
+    _need_tc()
+    z = np.load(os.path.join(golden_dir, "iteration.npz"))
+    data = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("video_")}
+    mp, ap = _params(golden_dir)
+    H, W, _, T = data["frames"].shape
+    vid = A.DeviceVideo.from_reference_layout(data, DEV)
+    tr = A.AtlasTrainer(vid, {"samples_batch": 64}, precision=N.PREC_TC, device=DEV)
+    tr.load_state(O.state_dict_of(mp), O.state_dict_of(ap))
+    before = N.lib().b200_launch_count()
+    img, u8 = tr.render_frame(2, H, W, T, want_u8=True)
+    assert N.lib().b200_launch_count() - before == 5          # rows, weight images, 2 fused forwards, output
+    img_chunks = tr.render_frame(2, H, W, T, chunk=500)
+    ref = O.render_frame(mp, ap, 2, H, W, T)
+    assert (img.cpu() - ref).abs().max() <= 5e-5
+    assert torch.equal(img_chunks, img)
+    diff = np.abs(u8.cpu().numpy().astype(int) - O.to_uint8(ref).astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+    assert abs(A.psnr(data["frames"][:, :, :, 2], img.cpu()) - O.psnr(data["frames"][:, :, :, 2], ref)) < 1e-3
