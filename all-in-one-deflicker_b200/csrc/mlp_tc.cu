@@ -1340,8 +1340,6 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
 // inference: mapping -> atlas on `rows` coordinate rows, no activation images (full-video render,
 // evaluate.py:640-708).  Workspace: [PrepJobs table][forward weight images of both networks].
 // ---------------------------------------------------------------------------------------------
-struct InferTables { int dev; const void* base; const void* params; PrepJobs* d_prep; int n_prep; };
-static std::vector<InferTables> g_infer_tabs;
 
 static void plan_infer(const MlpShape& ms, const MlpShape& as, char* base, NetImages* im_map, NetImages* im_atl,
                        PrepJobs** d_prep, int64_t* bytes) {
@@ -1379,39 +1377,32 @@ int tc_infer_forward(const MlpShape& ms, const MlpShape& as, const float* params
   B200_REQUIRE(rows > 0 && rows % TM == 0 && rows / TM < (1 << 24), "rows must be a positive multiple of %d", TM);
   NetImages im_map, im_atl; PrepJobs* d_prep; int64_t bytes;
   plan_infer(ms, as, ws, &im_map, &im_atl, &d_prep, &bytes);
-  const int dev = current_device();
-  InferTables* tab = nullptr;
+  // The job table lives in the caller's workspace and is rebuilt on every call (4 KB, pageable copy: the call is
+  // not graph-capturable, which a render does not need) — nothing is cached, so a recycled workspace is harmless.
   {
-    std::lock_guard<std::mutex> lock(g_tabs_mutex);
-    for (auto& t : g_infer_tabs) if (t.dev == dev && t.base == ws && t.params == params) tab = &t;
-  }
-  if (!tab) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
-    B200_REQUIRE(cs != cudaStreamCaptureStatusActive, "the first tensor-core render call on a workspace must be eager");
-    std::unique_ptr<PrepJobs> pj(new PrepJobs());
-    pj->n = 0;
-    for (int net = 0; net < 2; ++net) {
-      const MlpShape& sh = net ? as : ms;
-      const NetImages& im = net ? im_atl : im_map;
-      const float* pp = net ? params + ms.total : params;
-      for (int l = 0; l < sh.L; ++l) {
-        if (im.n_chunks_fwd[l] == 0) continue;
-        char* dst = im.w_fwd + im.w_fwd_layer[l];
-        const float* Wl = pp + sh.w_off[l];
-        int item = 0;
-        if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(*pj, Wl, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
-        if (net && (l == 0 || sh.skip[l]))
-          add_prep(*pj, Wl, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
-      }
-    }
-    B200_CHECK_CUDA(cudaMemcpyAsync(d_prep, pj.get(), sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
-    B200_CHECK_CUDA(cudaStreamSynchronize(st));
-    std::lock_guard<std::mutex> lock(g_tabs_mutex);
-    g_infer_tabs.push_back(InferTables{dev, ws, params, d_prep, pj->n});
-    tab = &g_infer_tabs.back();
+    B200_REQUIRE(cs != cudaStreamCaptureStatusActive, "the tensor-core render is not graph-capturable");
   }
-  tc_prep_kernel<<<tab->n_prep * 4, 128, 0, st>>>(tab->d_prep);
+  static thread_local PrepJobs pj_host;
+  PrepJobs* pj = &pj_host;
+  pj->n = 0;
+  for (int net = 0; net < 2; ++net) {
+    const MlpShape& sh = net ? as : ms;
+    const NetImages& im = net ? im_atl : im_map;
+    const float* pp = net ? params + ms.total : params;
+    for (int l = 0; l < sh.L; ++l) {
+      if (im.n_chunks_fwd[l] == 0) continue;
+      char* dst = im.w_fwd + im.w_fwd_layer[l];
+      const float* Wl = pp + sh.w_off[l];
+      int item = 0;
+      if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(*pj, Wl, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+      if (net && (l == 0 || sh.skip[l]))
+        add_prep(*pj, Wl, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+    }
+  }
+  B200_CHECK_CUDA(cudaMemcpyAsync(d_prep, pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
+  tc_prep_kernel<<<pj->n * 4, 128, 0, st>>>(d_prep);
   B200_CHECK_LAUNCH();
   const int tiles = (int)(rows / TM);
   FwdParams pm{};
