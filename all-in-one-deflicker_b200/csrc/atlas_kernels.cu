@@ -69,175 +69,124 @@ int launch_video_pack(const float* fr, const float* dx, const float* dy, const f
 }
 
 // ---------------------------------------------------------------------------------------------
-// sample selection: which of the B indices live on this device + global flow-row counts.
-// Order preserving, deterministic (single block scan).   counters: [0] n_local [1] n_fwd [2] n_bwd
-// Replaces jif_all[:, inds] (src/stage1_neural_atlas.py:159-162) and the torch.where of
-// loss_utils.py:328-331 (counts only).
+// sampling: selection of the resident samples, record gather, coordinate rows.  One thread per sample of the
+// GLOBAL batch.  src/stage1_neural_atlas.py:159-171 (jif_all[:, inds], rgb gather, xyt), loss_utils.py:138-151
+// (x+1 / y+1 rows, dx/dy gather), :230-233 (rigidity rows), :326-351 (flow-matched rows and the torch.where counts).
+//
+// counters (zeroed by a memset node before the launch):
+//   [0] n_local   samples whose frame is resident here (slot order: batch order on one GPU; claimed with a
+//                 warp-aggregated atomic when frame-sharded — the order only permutes fp32 summation)
+//   [1] n_fwd     [2] n_bwd    valid forward / backward flow rows of the WHOLE batch (from the replicated
+//                 bitmaps): the denominators of the two flow means on every rank
+//   [3] [4]       gradient-scale bits of the tensor-core path (written by the loss head)
+//   [5] n_lf      [6] n_lb     resident valid flow rows: the flow-match groups are COMPACTED to these counts
+//                 (row p of group G_FWD belongs to the sample whose target row stores p+1), so the networks are
+//                 never evaluated on rows the reference's torch.where drops
 // ---------------------------------------------------------------------------------------------
-constexpr int SELECT_THREADS = 1024;
-constexpr int SELECT_MAX_CHUNKS = 16;            // batch <= 16384 on the fast path
-
-// One block; sample b is handled by thread b % 1024 in pass b / 1024 (coalesced index loads, all loads of
-// a thread in flight together).  Positions come from ballots + a scan over (pass, warp) counts.
-__global__ void __launch_bounds__(SELECT_THREADS) select_kernel(const int64_t* __restrict__ indices, int B,
-                                                                 B200Video vid, int* __restrict__ counters,
-                                                                 int* __restrict__ list) {
-  __shared__ int s_cnt[SELECT_MAX_CHUNKS * 32];
-  __shared__ int s_tot[3];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int chunks = (B + SELECT_THREADS - 1) / SELECT_THREADS;
-  const int64_t HW = (int64_t)vid.H * vid.W;
-  if (tid < 3) s_tot[tid] = 0;
-  int64_t n[SELECT_MAX_CHUNKS];
-#pragma unroll
-  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
-    const int b = k * SELECT_THREADS + tid;
-    n[k] = (k < chunks && b < B) ? indices[b] : -1;
+__device__ __forceinline__ int warp_claim(bool take, int* counter, int lane) {
+  const uint32_t m = __ballot_sync(0xffffffffu, take);
+  int base = 0;
+  if (m) {
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
   }
-  uint32_t wf[SELECT_MAX_CHUNKS], wb[SELECT_MAX_CHUNKS];
-#pragma unroll
-  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
-    wf[k] = wb[k] = 0;
-    if (n[k] >= 0) { wf[k] = vid.mask_fwd_bits[n[k] >> 5]; wb[k] = vid.mask_bwd_bits[n[k] >> 5]; }
-  }
-  uint32_t loc_ballot[SELECT_MAX_CHUNKS];
-  int c_f = 0, c_b = 0;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
-    bool loc = false;
-    if (n[k] >= 0) {
-      const int t = (int)(n[k] / HW);
-      loc = (t >= vid.t_begin && t < vid.t_end);
-      c_f += (wf[k] >> (n[k] & 31)) & 1u;
-      c_b += (wb[k] >> (n[k] & 31)) & 1u;
-    }
-    loc_ballot[k] = __ballot_sync(0xffffffffu, loc);
-    if (lane == 0) s_cnt[k * 32 + wid] = __popc(loc_ballot[k]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    c_f += __shfl_xor_sync(0xffffffffu, c_f, o);
-    c_b += __shfl_xor_sync(0xffffffffu, c_b, o);
-  }
-  if (lane == 0) { atomicAdd(&s_tot[1], c_f); atomicAdd(&s_tot[2], c_b); }
-  __syncthreads();
-  if (wid == 0) {
-    // exclusive scan of the 16 x 32 counts in (pass, warp) order: lane handles 16 consecutive entries
-    int local[16], sum = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { local[i] = s_cnt[lane * 16 + i]; sum += local[i]; }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    int run = incl - sum;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { s_cnt[lane * 16 + i] = run; run += local[i]; }
-    if (lane == 31) s_tot[0] = incl;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < SELECT_MAX_CHUNKS; ++k) {
-    if ((loc_ballot[k] >> lane) & 1u)
-      list[s_cnt[k * 32 + wid] + __popc(loc_ballot[k] & ((1u << lane) - 1u))] = k * SELECT_THREADS + tid;
-  }
-  if (tid == 0) { counters[0] = s_tot[0]; counters[1] = s_tot[1]; counters[2] = s_tot[2]; counters[3] = 0; counters[4] = 0; }
+  return base + __popc(m & ((1u << lane) - 1u));
 }
 
-// ---------------------------------------------------------------------------------------------
-// gather + coordinate rows.  One thread per sample slot.
-// src/stage1_neural_atlas.py:162-171 (rgb gather, xyt), loss_utils.py:138-151 (x+1 / y+1 rows, dx/dy
-// gather), :230-233 (rigidity rows), :326-351 (flow-matched rows).
-// ---------------------------------------------------------------------------------------------
-// ALL_LOCAL: the whole video is resident (single GPU): no selection pass, slot s == sample s, and the flow-row
-// counts are accumulated here (counters zeroed by a memset node before the launch).
 template <bool ALL_LOCAL>
-__global__ void sample_kernel(const int64_t* __restrict__ indices, int* __restrict__ counters,
-                              const int* __restrict__ list, B200Video vid, SampleGeom geo, int cap, int batch,
-                              int n_groups, float4* __restrict__ x_map, float* __restrict__ targets) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ALL_LOCAL) {
-    // every thread of the block takes part in the count reduction below
-  } else if (s >= cap) return;
-  float4 rows[G_COUNT];
+__global__ void sample_kernel(const int64_t* __restrict__ indices, int* __restrict__ counters, B200Video vid,
+                              SampleGeom geo, int cap, int batch, int n_groups, float4* __restrict__ x_map,
+                              float* __restrict__ targets) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;      // index into the global batch (or a padding slot)
+  const int lane = threadIdx.x & 31;
+  bool local = false, wf = false, wb = false, gf = false, gb = false;
+  int t = 0, y = 0, x = 0;
+  float v[16];
 #pragma unroll
-  for (int g = 0; g < G_COUNT; ++g) rows[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float tg[TARGET_FLOATS];
-#pragma unroll
-  for (int q = 0; q < TARGET_FLOATS; ++q) tg[q] = 0.f;
-  int cnt_f = 0, cnt_b = 0;
-  if (s < (ALL_LOCAL ? batch : counters[0])) {
-    const int64_t n = indices[ALL_LOCAL ? s : list[s]];
+  for (int q = 0; q < 16; ++q) v[q] = 0.f;
+  if (b < batch) {
+    const int64_t n = indices[b];
     const int64_t HW = (int64_t)vid.H * vid.W;
-    const int t = (int)(n / HW);
-    const int y = (int)((n / vid.W) % vid.H);
-    const int x = (int)(n % vid.W);
-    const float4* rec = reinterpret_cast<const float4*>(
-        vid.records + (((int64_t)(t - vid.t_begin) * vid.H + y) * vid.W + x) * B200_RECORD_FLOATS);
-    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
-    const float v[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                         r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-#pragma unroll
-    for (int q = 0; q < 9; ++q) tg[q] = v[q];
-    const bool wf = v[13] != 0.f, wb = v[14] != 0.f;
-    tg[9] = wf ? 1.f : 0.f;
-    tg[10] = wb ? 1.f : 0.f;
-    cnt_f = wf; cnt_b = wb;
+    t = (int)(n / HW);
+    y = (int)((n / vid.W) % vid.H);
+    x = (int)(n % vid.W);
+    local = ALL_LOCAL || (t >= vid.t_begin && t < vid.t_end);
+    if (local) {
+      const float4* rec = reinterpret_cast<const float4*>(
+          vid.records + (((int64_t)(t - vid.t_begin) * vid.H + y) * vid.W + x) * B200_RECORD_FLOATS);
+      const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
+      v[0] = r0.x; v[1] = r0.y; v[2] = r0.z; v[3] = r0.w; v[4] = r1.x; v[5] = r1.y; v[6] = r1.z; v[7] = r1.w;
+      v[8] = r2.x; v[9] = r2.y; v[10] = r2.z; v[11] = r2.w; v[12] = r3.x; v[13] = r3.y; v[14] = r3.z; v[15] = r3.w;
+      wf = v[13] != 0.f; wb = v[14] != 0.f;
+    }
+    if (ALL_LOCAL) { gf = wf; gb = wb; }
+    else {
+      gf = (vid.mask_fwd_bits[n >> 5] >> (n & 31)) & 1u;
+      gb = (vid.mask_bwd_bits[n >> 5] >> (n & 31)) & 1u;
+    }
+  }
+  // whole-batch flow counts, slot of this sample, slots of its two flow-matched rows
+  {
+    const uint32_t mf = __ballot_sync(0xffffffffu, gf), mb = __ballot_sync(0xffffffffu, gb);
+    if (lane == 0) {
+      if (mf) atomicAdd(counters + 1, __popc(mf));
+      if (mb) atomicAdd(counters + 2, __popc(mb));
+    }
+  }
+  int s = b;
+  if (!ALL_LOCAL) s = warp_claim(local, counters + 0, lane);
+  const int pf = warp_claim(local && wf, counters + 5, lane);
+  const int pb = warp_claim(local && wb, counters + 6, lane);
+  if (ALL_LOCAL && b == 0) counters[0] = batch;
+  if (local) {
     const float fx = (float)x, fy = (float)y, ft = (float)t;
     const float hL = geo.half_larger, hX = geo.half_resx, hT = geo.half_frames;
     const float tn = norm_coord(ft, hT);
+    float4 rows[G_COUNT];
     rows[G_BASE] = make_float4(norm_coord(fx, hL), norm_coord(fy, hL), tn, 0.f);
     rows[G_XP1] = make_float4(norm_coord(fx + 1.f, hX), norm_coord(fy, hX), tn, 0.f);
     rows[G_YP1] = make_float4(norm_coord(fx, hX), norm_coord(fy + 1.f, hX), tn, 0.f);
     rows[G_YMD] = make_float4(norm_coord(fx, hL), norm_coord(fy - geo.d_local, hL), tn, 0.f);
     rows[G_XMD] = make_float4(norm_coord(fx - geo.d_local, hL), norm_coord(fy, hL), tn, 0.f);
-    if (wf) rows[G_FWD] = make_float4(norm_coord(__fadd_rn(fx, v[9]), hL), norm_coord(__fadd_rn(fy, v[10]), hL),
-                                      norm_coord(ft + 1.f, hT), 0.f);
-    if (wb) rows[G_BWD] = make_float4(norm_coord(__fadd_rn(fx, v[11]), hL), norm_coord(__fadd_rn(fy, v[12]), hL),
-                                      norm_coord(ft - 1.f, hT), 0.f);
+    rows[G_FWD] = make_float4(norm_coord(__fadd_rn(fx, v[9]), hL), norm_coord(__fadd_rn(fy, v[10]), hL),
+                              norm_coord(ft + 1.f, hT), 0.f);
+    rows[G_BWD] = make_float4(norm_coord(__fadd_rn(fx, v[11]), hL), norm_coord(__fadd_rn(fy, v[12]), hL),
+                              norm_coord(ft - 1.f, hT), 0.f);
     rows[G_YMG] = make_float4(norm_coord(fx, hL), norm_coord(fy - geo.d_global, hL), tn, 0.f);
     rows[G_XMG] = make_float4(norm_coord(fx - geo.d_global, hL), norm_coord(fy, hL), tn, 0.f);
-  }
-  if (s < cap) {
+#pragma unroll
+    for (int g = 0; g < G_COUNT; ++g) {
+      if (g >= n_groups) continue;
+      if (g == G_FWD) { if (wf) x_map[(int64_t)g * cap + pf] = rows[g]; }
+      else if (g == G_BWD) { if (wb) x_map[(int64_t)g * cap + pb] = rows[g]; }
+      else x_map[(int64_t)g * cap + s] = rows[g];
+    }
+    float4* tdst = reinterpret_cast<float4*>(targets + (int64_t)s * TARGET_FLOATS);
+    tdst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    tdst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    tdst[2] = make_float4(v[8], wf ? (float)(pf + 1) : 0.f, wb ? (float)(pb + 1) : 0.f, 0.f);
+  } else if (ALL_LOCAL && b < cap) {
+    // padding slots of the last tile: finite rows, zero targets
 #pragma unroll
     for (int g = 0; g < G_COUNT; ++g)
-      if (g < n_groups) x_map[(int64_t)g * cap + s] = rows[g];
-    float4* tdst = reinterpret_cast<float4*>(targets + (int64_t)s * TARGET_FLOATS);
-    tdst[0] = make_float4(tg[0], tg[1], tg[2], tg[3]);
-    tdst[1] = make_float4(tg[4], tg[5], tg[6], tg[7]);
-    tdst[2] = make_float4(tg[8], tg[9], tg[10], tg[11]);
-  }
-  if (ALL_LOCAL) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cnt_f += __shfl_xor_sync(0xffffffffu, cnt_f, o);
-      cnt_b += __shfl_xor_sync(0xffffffffu, cnt_b, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      if (cnt_f) atomicAdd(counters + 1, cnt_f);
-      if (cnt_b) atomicAdd(counters + 2, cnt_b);
-    }
-    if (s == 0) counters[0] = batch;
+      if (g < n_groups && g != G_FWD && g != G_BWD) x_map[(int64_t)g * cap + b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* tdst = reinterpret_cast<float4*>(targets + (int64_t)b * TARGET_FLOATS);
+    tdst[0] = tdst[1] = tdst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
 int launch_select_sample(const int64_t* indices, int B, const B200Video& vid, const SampleGeom& geo, int cap,
                          int n_groups, int* counters, int* list, float* x_map, float* targets,
                          cudaStream_t st) {
-  if (vid.t_begin == 0 && vid.t_end == vid.T) {
-    B200_CHECK_CUDA(cudaMemsetAsync(counters, 0, 32, st));
-    sample_kernel<true><<<(cap + 127) / 128, 128, 0, st>>>(indices, counters, list, vid, geo, cap, B, n_groups,
+  (void)list;
+  B200_CHECK_CUDA(cudaMemsetAsync(counters, 0, 32, st));
+  if (vid.t_begin == 0 && vid.t_end == vid.T)
+    sample_kernel<true><<<(cap + 127) / 128, 128, 0, st>>>(indices, counters, vid, geo, cap, B, n_groups,
                                                             reinterpret_cast<float4*>(x_map), targets);
-    B200_CHECK_LAUNCH();
-    return B200_OK;
-  }
-  select_kernel<<<1, SELECT_THREADS, 0, st>>>(indices, B, vid, counters, list);
-  B200_CHECK_LAUNCH();
-  sample_kernel<false><<<(cap + 127) / 128, 128, 0, st>>>(indices, counters, list, vid, geo, cap, B, n_groups,
-                                                             reinterpret_cast<float4*>(x_map), targets);
+  else
+    sample_kernel<false><<<(B + 127) / 128, 128, 0, st>>>(indices, counters, vid, geo, cap, B, n_groups,
+                                                           reinterpret_cast<float4*>(x_map), targets);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -247,7 +196,7 @@ __global__ void pretrain_sample_kernel(const int64_t* __restrict__ ys, const int
                                        int cap, float half_larger, float t_norm, float4* __restrict__ x_map,
                                        int* __restrict__ counters) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) { counters[0] = B; counters[3] = 0; counters[4] = 0; }
+  if (s == 0) { counters[0] = B; counters[3] = 0; counters[4] = 0; counters[5] = 0; counters[6] = 0; }
   if (s >= cap) return;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s < B) r = make_float4(norm_coord((float)xs[s], half_larger), norm_coord((float)ys[s], half_larger), t_norm, 0.f);
@@ -393,19 +342,23 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
                             int n_groups, LossConfig cfg, float* __restrict__ d_uv, float* __restrict__ d_y,
                             float* __restrict__ losses) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_local = counters[0], n_f = counters[1], n_b = counters[2];
+  const int n_local = counters[0], n_f = counters[1], n_b = counters[2], n_lf = counters[5], n_lb = counters[6];
   cfg.inv_nf = n_f > 0 ? 1.0f / (float)n_f : 0.f;
   cfg.inv_nb = n_b > 0 ? 1.0f / (float)n_b : 0.f;
   float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float gmx = 0.f, gmy = 0.f;
   if (s < cap) {
     SampleOut out;
+    int pf = -1, pb = -1;                 // compacted rows of this sample in the two flow-match groups
     if (s < n_local) {
       SampleIn in;
+      const float* tg = targets + (int64_t)s * TARGET_FLOATS;
+      pf = (int)tg[9] - 1; pb = (int)tg[10] - 1;
 #pragma unroll
       for (int g = 0; g < G_COUNT; ++g) {
-        if (g < n_groups) {
-          const float2 v = *reinterpret_cast<const float2*>(uv + ((int64_t)g * cap + s) * 2);
+        const int r = g == G_FWD ? pf : (g == G_BWD ? pb : s);
+        if (g < n_groups && r >= 0) {
+          const float2 v = *reinterpret_cast<const float2*>(uv + ((int64_t)g * cap + r) * 2);
           in.uv[g][0] = v.x; in.uv[g][1] = v.y;
         } else { in.uv[g][0] = in.uv[g][1] = 0.f; }
       }
@@ -413,10 +366,9 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
       for (int g = 0; g < 3; ++g)
 #pragma unroll
         for (int c = 0; c < 3; ++c) in.y[g][c] = y_atlas[((int64_t)g * cap + s) * 3 + c];
-      const float* tg = targets + (int64_t)s * TARGET_FLOATS;
 #pragma unroll
       for (int c = 0; c < 3; ++c) { in.rgb[c] = tg[c]; in.dx[c] = tg[3 + c]; in.dy[c] = tg[6 + c]; }
-      in.wf = tg[9]; in.wb = tg[10];
+      in.wf = pf >= 0 ? 1.f : 0.f; in.wb = pb >= 0 ? 1.f : 0.f;
       sample_loss(in, cfg, out);
       part[0] = out.rgb; part[1] = out.grad; part[2] = out.rig; part[3] = out.rig_global;
       part[4] = out.flow_f; part[5] = out.flow_b;
@@ -431,7 +383,14 @@ __global__ void loss_kernel(const float* __restrict__ uv, const float* __restric
 #pragma unroll
     for (int g = 0; g < G_COUNT; ++g)
       if (g < n_groups) {
-        *reinterpret_cast<float2*>(d_uv + ((int64_t)g * cap + s) * 2) = make_float2(out.duv[g][0], out.duv[g][1]);
+        if (g == G_FWD || g == G_BWD) {
+          // this sample's compacted row, and (as slot owner) zero for the padding rows of the group's last tile
+          const int r = g == G_FWD ? pf : pb, n_rows = g == G_FWD ? n_lf : n_lb;
+          if (r >= 0) *reinterpret_cast<float2*>(d_uv + ((int64_t)g * cap + r) * 2) = make_float2(out.duv[g][0], out.duv[g][1]);
+          if (s >= n_rows) *reinterpret_cast<float2*>(d_uv + ((int64_t)g * cap + s) * 2) = make_float2(0.f, 0.f);
+        } else {
+          *reinterpret_cast<float2*>(d_uv + ((int64_t)g * cap + s) * 2) = make_float2(out.duv[g][0], out.duv[g][1]);
+        }
         gmx = fmaxf(gmx, fmaxf(fabsf(out.duv[g][0]), fabsf(out.duv[g][1])));
       }
 #pragma unroll
@@ -496,9 +455,11 @@ int launch_loss(const float* uv, const float* y_atlas, const float* targets, int
 //   m.lerp_(g, 1-b1);  v.mul_(b2).addcmul_(g, g, value=1-b2);
 //   denom = sqrt(v) / sqrt(1-b2^t) + eps;  p.addcdiv_(m, denom, value=-lr/(1-b1^t))
 // ---------------------------------------------------------------------------------------------
+__device__ unsigned int g_adam_ticket = 0u;
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, double lr, double b1d, double b2d, double epsd,
-                            float grad_scale, const int64_t* __restrict__ step_in) {
+                            float grad_scale, int64_t* __restrict__ step_in) {
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const double t = (double)(*step_in + 1);
@@ -512,8 +473,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   // python floats (doubles) rounded to fp32 where torch passes them to fp32 kernels
   const float w1 = (float)(1.0 - b1d), w2 = (float)(1.0 - b2d), b2 = (float)b2d, eps = (float)epsd;
   const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  if (i4 + 3 < n) {
+  if (i4 >= n) {
+  } else if (i4 + 3 < n) {
     const float4 gg = *reinterpret_cast<const float4*>(g + i4);
     float4 pp = *reinterpret_cast<float4*>(p + i4);
     float4 mm = *reinterpret_cast<float4*>(m + i4);
@@ -540,9 +501,16 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
       m[i] = mq; v[i] = vq;
     }
   }
+  // the step counter is advanced by the LAST block to finish: every block has read it before taking its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&g_adam_ticket, 1u) == gridDim.x - 1) {
+      *step_in += 1;
+      g_adam_ticket = 0u;
+    }
+  }
 }
-
-__global__ void bump_step_kernel(int64_t* step) { *step += 1; }
 
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2,
                 double eps, float grad_scale, int64_t* step, cudaStream_t st) {
@@ -550,8 +518,6 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, double 
   timer_begin(TAG_ADAM, st);
   adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, grad_scale, step);
   timer_end(TAG_ADAM, st);
-  B200_CHECK_LAUNCH();
-  bump_step_kernel<<<1, 1, 0, st>>>(step);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -319,6 +319,15 @@ int b200_atlas_loss_grad(const B200AtlasConfig* cfg, const B200Video* video, con
   const int cap = pl.cap;
   const int ng = cfg->with_global ? G_COUNT : G_YMG;        // 9 or 7 row groups
   const int64_t n_params = pl.ms.total + pl.as.total;
+  TcStep ts{};
+  if (cfg->precision == B200_PREC_TC) {
+    ts.ms = &pl.ms; ts.as = &pl.as; ts.plan = &pl.tc;
+    ts.params = params; ts.grads = grads;
+    ts.x_map = pl.x_map; ts.uv = pl.map.y; ts.y_atlas = pl.atlas.y;
+    ts.d_uv = pl.d_uv; ts.d_y = pl.d_y;
+    ts.cap = cap; ts.n_groups = ng; ts.counters = pl.counters; ts.flow_groups = 1;
+    B200_PROPAGATE(tc_begin_step(ts, st));          // weight images on a side stream, under the sampling kernels
+  }
   B200_CHECK_CUDA(cudaMemsetAsync(grads, 0, (size_t)n_params * 4, st));
   B200_CHECK_CUDA(cudaMemsetAsync(losses, 0, B200_LOSS_FLOATS * 4, st));
 
@@ -365,12 +374,6 @@ int b200_atlas_loss_grad(const B200AtlasConfig* cfg, const B200Video* video, con
                                       2, 1, span_atl, st));
     B200_PROPAGATE(simt_mlp_backward(pl.ms, p_map, pl.x_map, 4, span_map, pl.map, pl.d_uv, g_map, nullptr, 0, st));
   } else {
-    TcStep ts{};
-    ts.ms = &pl.ms; ts.as = &pl.as; ts.plan = &pl.tc;
-    ts.params = params; ts.grads = grads;
-    ts.x_map = pl.x_map; ts.uv = pl.map.y; ts.y_atlas = pl.atlas.y;
-    ts.d_uv = pl.d_uv; ts.d_y = pl.d_y;
-    ts.cap = cap; ts.n_groups = ng; ts.counters = pl.counters;
     B200_PROPAGATE(tc_atlas_forward(ts, st));
     B200_PROPAGATE(launch_loss(pl.map.y, pl.atlas.y, pl.targets, pl.counters, cap, ng, lc, pl.d_uv, pl.d_y, losses,
                                st));

@@ -174,13 +174,27 @@ struct Pipe {                        // weight-image ring shared by producer and
 };
 
 struct TileIter {                    // static round-robin over the live tiles of a group-major batch
-  int ntg, total, cap_tiles;
-  __device__ __forceinline__ void init(int cap, int n_groups, const int* n_valid) {
+  int t0, tf, tb, total, cap_tiles, n_groups, flow;
+  // counters: [0] rows of an ordinary group, [5] / [6] rows of the compacted flow-match groups (G_FWD = 5, G_BWD = 6
+  // of the mapping batch when `flow_groups` is set); nullptr: every row of every group is live
+  __device__ __forceinline__ void init(int cap, int groups, const int* counters, int flow_groups) {
     cap_tiles = cap / TM;
-    ntg = n_valid ? min(cap_tiles, (*n_valid + TM - 1) / TM) : cap_tiles;
-    total = ntg * n_groups;
+    n_groups = groups;
+    flow = (flow_groups && groups > 6) ? 1 : 0;
+    t0 = counters ? min(cap_tiles, (counters[0] + TM - 1) / TM) : cap_tiles;
+    tf = flow ? min(cap_tiles, (counters[5] + TM - 1) / TM) : t0;
+    tb = flow ? min(cap_tiles, (counters[6] + TM - 1) / TM) : t0;
+    total = t0 * (groups - (flow ? 2 : 0)) + (flow ? tf + tb : 0);
   }
-  __device__ __forceinline__ int global_tile(int t) const { return (t / ntg) * cap_tiles + (t % ntg); }
+  __device__ __forceinline__ int group_tiles(int g) const { return (flow && g == 5) ? tf : ((flow && g == 6) ? tb : t0); }
+  __device__ __forceinline__ int global_tile(int t) const {
+    for (int g = 0; g < n_groups; ++g) {
+      const int n = group_tiles(g);
+      if (t < n) return g * cap_tiles + t;
+      t -= n;
+    }
+    return 0;
+  }
 };
 
 // MMAs of one 64-wide k chunk whose A operand is in TMEM (hi at TM_AHI, lo at TM_ALO):
@@ -362,6 +376,7 @@ struct FwdParams {
   int64_t w_off[B200_MAX_LAYERS], b_off[B200_MAX_LAYERS];
   NetImages img;
   int cap, n_groups; const int* n_valid;
+  int flow_groups;           // mapping batch of the loop: groups 5 / 6 are compacted to counters[5] / counters[6] rows
   float in_scale, in_shift;  // atlas: network input = x * in_scale + in_shift (0.5, 0.5 inside the loop: uv -> [0,1])
   int store_images;          // 0: inference (render / IMLP.forward without grad): no activation images, no flags
   int tanh_out;
@@ -400,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   if (threadIdx.x < OUT) s_blast[threadIdx.x] = P.params[P.b_off[L - 1] + threadIdx.x];
   if (!ATLAS) for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[i] = P.params[P.w_off[0] + i] * S_ACT;
   const uint32_t tmem = setup_cta(sm, warp);
-  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid);
+  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid, P.flow_groups);
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
 
   if (warp == 0) {
@@ -626,6 +641,7 @@ struct BwdParams {
   NetImages img;
   int cap, n_groups; const int* n_valid;
   int* gmax_bits;            // [0] max |dL/dy| from the loss head, [1] max |dL/duv| after the atlas backward
+  int flow_groups;
   float in_scale;            // atlas: d(network input)/d(x) (0.5 inside the loop)
   int d_in_accumulate;       // atlas: 1 = d_in already holds the direct loss-head gradient (the loop), 0 = overwrite
   int tanh_out;
@@ -697,7 +713,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
   for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i];
   for (int i = threadIdx.x; i < (L - 1) * 256 + (ATLAS ? 0 : 768); i += blockDim.x) s_bacc[i] = 0.f;
   const uint32_t tmem = setup_cta(sm, warp);
-  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid);
+  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid, P.flow_groups);
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
   constexpr uint32_t IDESC64 = make_idesc(128, 64, 0, 0);
   float s_g, inv_sg;
@@ -945,6 +961,7 @@ struct WgradItem {
   int cap, n_groups;      // row geometry of the network this item belongs to
   int split, n_split;     // this CTA's share of the live tiles
   int mapping;            // 1: gradients of the mapping network (second gradient scale)
+  int flow_groups;        // row geometry: compacted flow-match groups (mapping batch of the loop)
 };
 constexpr int MAX_WGRAD_ITEMS = 320;
 struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; };
@@ -976,7 +993,7 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const WgradItem W = items->it[blockIdx.x];
-  TileIter ti; ti.init(W.cap, W.n_groups, n_valid);
+  TileIter ti; ti.init(W.cap, W.n_groups, n_valid, W.flow_groups);
   const int t_begin = (int)((int64_t)ti.total * W.split / W.n_split);
   const int t_end = (int)((int64_t)ti.total * (W.split + 1) / W.n_split);
   const int a_atoms = W.a_cols / 64, b_atoms = W.b_cols / 64;
@@ -1106,7 +1123,7 @@ static int ensure_attrs() {
 struct HostTables {
   int key_dev = -1;
   const void* key_base = nullptr; int key_cap = 0, key_groups = 0; const void* key_params = nullptr;
-  const void* key_grads = nullptr; bool key_atlas = false;
+  const void* key_grads = nullptr; bool key_atlas = false; int key_flow = 0;
   PrepJobs* d_prep = nullptr; WgradItems* d_wg = nullptr;
   int n_wg = 0, n_prep = 0;
 };
@@ -1125,7 +1142,7 @@ static HostTables* find_tables(const TcStep& s) {
   for (size_t i = 0; i < g_tabs.size(); ++i) {
     HostTables& t = *g_tabs[i];
     if (t.key_dev == dev && t.key_base == s.plan->base && t.key_cap == s.cap && t.key_groups == s.n_groups && t.key_params == s.params &&
-        t.key_grads == s.grads && t.key_atlas == atlas)
+        t.key_grads == s.grads && t.key_atlas == atlas && t.key_flow == s.flow_groups)
       return &t;
   }
   return nullptr;
@@ -1251,6 +1268,7 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
       it.b_img = pr.b; it.b_term = pr.b_term; it.b_cols = pr.b_cols;
       it.out = pr.out; it.ld_out = pr.ld; it.n_rows = pr.n_rows; it.n_cols = pr.n_cols;
       it.cap = s.cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split[i]; it.mapping = pr.mapping;
+      it.flow_groups = (pr.mapping && s.flow_groups) ? 1 : 0;
     }
   }
   if (pj.n > MAX_PREP_JOBS) { set_error("table overflow"); return B200_ERR_INVALID; }
@@ -1259,7 +1277,7 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
   B200_CHECK_CUDA(cudaStreamSynchronize(st));
   tab.n_wg = wi.n; tab.n_prep = pj.n;
   tab.key_base = s.plan->base; tab.key_cap = s.cap; tab.key_groups = s.n_groups; tab.key_params = s.params;
-  tab.key_grads = s.grads; tab.key_atlas = atlas; tab.key_dev = current_device();
+  tab.key_grads = s.grads; tab.key_atlas = atlas; tab.key_dev = current_device(); tab.key_flow = s.flow_groups;
   {
     std::lock_guard<std::mutex> lock(g_tabs_mutex);
     g_tabs.push_back(tab_owner.release());
@@ -1271,21 +1289,47 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
 static void fill_fwd(FwdParams& P, const MlpShape& sh, const NetImages& im, const float* x, float* y,
                      const float* params, int cap, int groups, const int* n_valid) {
   P.x = x; P.y = y; P.params = params; P.img = im; P.cap = cap; P.n_groups = groups; P.n_valid = n_valid;
-  P.in_scale = 0.5f; P.in_shift = 0.5f; P.store_images = 1; P.tanh_out = 1;
+  P.in_scale = 0.5f; P.in_shift = 0.5f; P.store_images = 1; P.tanh_out = 1; P.flow_groups = 0;
   for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
 }
 
-static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
+// The weight images depend only on the parameters, so their preparation runs on a side stream, forked from the
+// caller's stream before the sampling kernels and joined before the first fused kernel (also under capture: the
+// fork / join become parallel branches of the graph).
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool pending = false; };
+static SideStream g_side[64];
+
+int tc_begin_step(const TcStep& s, cudaStream_t st) {
   B200_PROPAGATE(ensure_attrs());
   const TcLayout lay = layout_of(s);
   HostTables* tab = nullptr;
   B200_PROPAGATE(build_tables(s, lay, st, &tab));
+  SideStream& sd = g_side[current_device()];
+  if (!sd.stream) {
+    B200_CHECK_CUDA(cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking));
+    B200_CHECK_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
+    B200_CHECK_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
+  }
+  B200_CHECK_CUDA(cudaEventRecord(sd.fork, st));
+  B200_CHECK_CUDA(cudaStreamWaitEvent(sd.stream, sd.fork, 0));
   // weight images of both networks — every step, since Adam changed the parameters
-  tc_prep_kernel<<<tab->n_prep * 4, 128, 0, st>>>(tab->d_prep);
+  tc_prep_kernel<<<tab->n_prep * 4, 128, 0, sd.stream>>>(tab->d_prep);
   B200_CHECK_LAUNCH();
+  B200_CHECK_CUDA(cudaEventRecord(sd.join, sd.stream));
+  sd.pending = true;
+  return B200_OK;
+}
+
+static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
+  const TcLayout lay = layout_of(s);
+  SideStream& sd = g_side[current_device()];
+  if (!sd.pending) B200_PROPAGATE(tc_begin_step(s, st));     // callers that did not fork earlier
+  B200_CHECK_CUDA(cudaStreamWaitEvent(st, sd.join, 0));
+  sd.pending = false;
   const int tiles_map = s.n_groups * (s.cap / TM);
   FwdParams pm{};
   fill_fwd(pm, *s.ms, lay.map, s.x_map, s.uv, s.params, s.cap, s.n_groups, s.counters);
+  pm.flow_groups = s.flow_groups;
   timer_begin(TAG_MAP_FWD, st);
   tc_fwd_kernel<false><<<min(sm_count(), tiles_map), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
   timer_end(TAG_MAP_FWD, st);
@@ -1310,7 +1354,7 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
                   const float* x, float* d_in, const float* params, float* grads, int groups) {
     P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = im;
     P.cap = s.cap; P.n_groups = groups; P.n_valid = s.counters; P.gmax_bits = gmax;
-    P.in_scale = 0.5f; P.d_in_accumulate = 1; P.tanh_out = 1;
+    P.in_scale = 0.5f; P.d_in_accumulate = 1; P.tanh_out = 1; P.flow_groups = 0;
     for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
   };
   if (with_atlas) {
@@ -1324,6 +1368,7 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   }
   BwdParams pm{};
   fill(pm, *s.ms, lay.map, s.d_uv, s.uv, s.x_map, nullptr, s.params, s.grads, s.n_groups);
+  pm.flow_groups = s.flow_groups;
   timer_begin(TAG_MAP_BWD, st);
   tc_bwd_kernel<false><<<min(sm_count(), s.n_groups * (s.cap / TM)), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
   timer_end(TAG_MAP_BWD, st);

@@ -22,10 +22,12 @@ struct TcStep {
   const float* d_y;          // [3*cap][3]
   int cap, n_groups;
   const int* counters;
+  int flow_groups;           // 1: groups 5 / 6 of the mapping batch hold counters[5] / counters[6] compacted rows
 };
 
 int64_t tc_plan(const MlpShape& ms, const MlpShape& as, int64_t rows_map, int64_t rows_atlas, char* base,
                 TcPlan* out);
+int tc_begin_step(const TcStep& s, cudaStream_t st);       // optional: start the weight-image preparation early (side stream)
 int tc_atlas_forward(const TcStep& s, cudaStream_t st);    // mapping on all groups, atlas on groups 0..2
 int tc_atlas_backward(const TcStep& s, cudaStream_t st);   // all parameter gradients
 int tc_mapping_forward(const TcStep& s, cudaStream_t st);  // pre-training: mapping only

@@ -175,9 +175,14 @@ def test_loss_grad_parity_and_exact_sampling(golden_dir, it):
     uv_dummy = torch.zeros(B, 2)
     _, xyt_f, rows_f = O.flow_matches(jif, video.mask_fwd, video.flow_fwd, larger, T, True, uv_dummy)
     _, xyt_b, rows_b = O.flow_matches(jif, video.mask_bwd, video.flow_bwd, larger, T, False, uv_dummy)
-    assert torch.equal(x_map[5, rows_f, :3], xyt_f) and torch.equal(x_map[6, rows_b, :3], xyt_b)
-    assert torch.all(x_map[:, B:] == 0)
+    # the flow-match groups are compacted: target column 9 / 10 of a sample holds (row in group 5 / 6) + 1, 0 = no flow
     tg = view["targets"].cpu()
+    pf, pb = tg[:B, 9].long() - 1, tg[:B, 10].long() - 1
+    assert torch.equal(torch.nonzero(pf >= 0).squeeze(1), rows_f) and torch.equal(torch.nonzero(pb >= 0).squeeze(1), rows_b)
+    assert sorted(pf[rows_f].tolist()) == list(range(len(rows_f))) and sorted(pb[rows_b].tolist()) == list(range(len(rows_b)))
+    assert torch.equal(x_map[5, pf[rows_f], :3], xyt_f) and torch.equal(x_map[6, pb[rows_b], :3], xyt_b)
+    keep = [g for g in range(9) if g not in (5, 6)]
+    assert torch.all(x_map[keep][:, B:] == 0) and torch.all(x_map[5, len(rows_f):] == 0) and torch.all(x_map[6, len(rows_b):] == 0)
     assert torch.equal(tg[:B, 0:3], video.frames[jif[1], jif[0], :, jif[2]].squeeze(1))
     assert torch.equal(tg[:B, 3:6], video.frames_dx[jif[1], jif[0], :, jif[2]].squeeze(1))
     assert torch.equal(tg[:B, 6:9], video.frames_dy[jif[1], jif[0], :, jif[2]].squeeze(1))
