@@ -47,6 +47,14 @@ class ConvDesc(C.Structure):
                 ("res_c_total", C.c_int32), ("res_c_off", C.c_int32), ("upsample_mode", C.c_int32)]
 
 
+MAX_RANKS = 16
+
+
+class DpComm(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("partials", C.c_void_p * MAX_RANKS),
+                ("params", C.c_void_p * MAX_RANKS), ("flags", C.c_void_p * MAX_RANKS)]
+
+
 class AtlasConfig(C.Structure):
     _fields_ = [("batch", C.c_int32), ("with_global", C.c_int32), ("precision", C.c_int32),
                 ("resx", C.c_int32), ("uv_mapping_scale", C.c_float), ("derivative_amount", C.c_float),
@@ -81,6 +89,9 @@ SIGNATURES = {
     "b200_gradient_loss_head": (C.c_int, [_P] * 5 + [_I64] + [_P] * 5),
     "b200_rigidity_loss_head": (C.c_int, [_P, _P, _I64, _F, _F, _F, _P, _P, _P, _P, _P]),
     "b200_flow_loss_head": (C.c_int, [_P, _P, _I64, _F, _F, _P, _P, _P, _P]),
+    "b200_dp_adam_step": (C.c_int, [C.POINTER(DpComm), _P, _P, _I64, _I64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    _P, _P, _P]),
+    "b200_dp_slice": (C.c_int, [_I32, _I32, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
     "b200_render_workspace_bytes": (_I64, [_I64]),
     "b200_render": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, C.c_int, _P, _I64, _P]),
     "b200_corr_pyramid_floats": (_I64, [_I32, _I32]),

@@ -119,7 +119,8 @@ class AtlasTrainer:
     """Flat parameters/optimiser state of (mapping, atlas) + the fused step."""
 
     def __init__(self, video: Optional[DeviceVideo], config: Optional[dict] = None, precision: int = N.PREC_FP32,
-                 device="cuda", lr: float = 1e-4, process_group=None, resx: Optional[int] = None):
+                 device="cuda", lr: float = 1e-4, process_group=None, resx: Optional[int] = None,
+                 fused_dp: Optional[bool] = None):
         self.lib = N.lib()
         self.video = video
         self.cfg = dict(DEFAULTS)
@@ -141,9 +142,13 @@ class AtlasTrainer:
         self.n_params = int(self.lib.b200_atlas_param_floats())
         assert self.n_params == self.map_total + self.atl_total
         dev = self.device
-        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
-        # gradients + the loss vector share one buffer so that data parallelism needs ONE all-reduce
-        self.grad_loss = torch.zeros(self.n_params + N.LOSS_FLOATS, dtype=torch.float32, device=dev)
+        # gradients + the loss vector share one buffer so that data parallelism needs ONE exchange
+        self._dp = None
+        if self.world > 1 and dev.type == "cuda" and fused_dp is not False:
+            self._dp = self._setup_fused_dp(required=bool(fused_dp))
+        if self._dp is None:
+            self.params = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+            self.grad_loss = torch.zeros(self.n_params + N.LOSS_FLOATS, dtype=torch.float32, device=dev)
         self.grads = self.grad_loss[:self.n_params]
         self.losses = self.grad_loss[self.n_params:]
         self.exp_avg = torch.zeros_like(self.params)
@@ -194,6 +199,7 @@ class AtlasTrainer:
     def optimizer_state_dict(self):
         """Schema of torch.optim.Adam.state_dict() for [{'params': mapping}, {'params': atlas}]
         (what evaluate.py:621 stores)."""
+        self.gather_moments()
         state, groups, idx = {}, [], 0
         step = self.step_count.detach().float().cpu().reshape(())
         for which in ("mapping", "atlas"):
@@ -272,6 +278,60 @@ class AtlasTrainer:
                                               N.ptr(self.params), N.ptr(self.grads), N.ptr(self.losses),
                                               N.ptr(ws), ws.numel(), N.current_stream()), "b200_atlas_loss_grad")
 
+    # ------------------------------------------------------------------ data parallelism over NVLink peer memory
+    def _setup_fused_dp(self, required: bool):
+        """Symmetric (peer-mapped) allocations for b200_dp_adam_step: parameters, the [gradients || losses] buffer and
+        the flag words.  torch's symmetric-memory allocator does the rendezvous (plumbing); the exchange itself is
+        this library's kernel.  Returns the communicator struct, or None (-> NCCL all-reduce + local Adam) when the
+        allocator is unavailable."""
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            dev, n = self.device, self.n_params + N.LOSS_FLOATS
+            self.params = symm.empty(self.n_params, dtype=torch.float32, device=dev)
+            self.grad_loss = symm.empty(n, dtype=torch.float32, device=dev)
+            self._dp_flags = symm.empty(2 * N.MAX_RANKS, dtype=torch.int64, device=dev)
+            self.params.zero_(); self.grad_loss.zero_(); self._dp_flags.zero_()
+            handles = [symm.rendezvous(t, self.pg) for t in (self.grad_loss, self.params, self._dp_flags)]
+            comm = N.DpComm()
+            comm.world, comm.rank = self.world, dist.get_rank(self.pg)
+            for j in range(self.world):
+                comm.partials[j] = int(handles[0].buffer_ptrs[j])
+                comm.params[j] = int(handles[1].buffer_ptrs[j])
+                comm.flags[j] = int(handles[2].buffer_ptrs[j])
+            self._dp_handles = handles
+            self._dp_epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+            torch.cuda.synchronize(dev)
+            dist.barrier(self.pg)
+            return comm
+        except Exception as e:                      # noqa: BLE001 - any allocator / rendezvous failure
+            if required:
+                raise
+            import sys
+            print(f"b200: fused data-parallel optimiser unavailable ({type(e).__name__}: {e}); "
+                  f"using NCCL all-reduce + local Adam", file=sys.stderr)
+            return None
+
+    def dp_adam(self):
+        """reduce-scatter + Adam + all-gather in one kernel (b200_dp_adam_step)."""
+        N.check(self.lib.b200_dp_adam_step(C.byref(self._dp), N.ptr(self.exp_avg), N.ptr(self.exp_avg_sq), self.n_params,
+                                           self.n_params + N.LOSS_FLOATS, self.lr, 0.9, 0.999, 1e-8,
+                                           N.ptr(self.step_count), N.ptr(self._dp_epoch), N.current_stream()),
+                "b200_dp_adam_step")
+
+    def gather_moments(self):
+        """With the fused optimiser a rank maintains only the Adam moments of its slice: assemble the full state
+        (checkpoint time) with one all-reduce of the owned slices."""
+        if self._dp is None:
+            return
+        import torch.distributed as dist
+        b, c = C.c_int64(), C.c_int64()
+        N.check(self.lib.b200_dp_slice(self.world, self._dp.rank, self.n_params + N.LOSS_FLOATS, C.byref(b), C.byref(c)))
+        lo, hi = min(b.value, self.n_params), min(b.value + c.value, self.n_params)
+        for t in (self.exp_avg, self.exp_avg_sq):
+            t[:lo].zero_(); t[hi:].zero_()
+            dist.all_reduce(t, group=self.pg)
+
     def all_reduce(self):
         if self.pg is not None and self.world > 1:
             import torch.distributed as dist
@@ -288,8 +348,11 @@ class AtlasTrainer:
 
     def _iteration(self, with_global: bool):
         self.loss_grad(with_global)
-        self.all_reduce()
-        self.adam()
+        if self._dp is not None:
+            self.dp_adam()
+        else:
+            self.all_reduce()
+            self.adam()
 
     def step(self, it: int, use_graph: bool = True):
         """One loop trip on the indices in self.indices (device).  Returns the device loss vector

@@ -31,6 +31,8 @@ int launch_loss(const float* uv, const float* y_atlas, const float* targets, int
                 cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2,
                 double eps, float grad_scale, int64_t* step, cudaStream_t st);
+int launch_dp_adam(const B200DpComm& comm, float* m, float* v, int64_t n_params, int64_t n_total, double lr,
+                   double b1, double b2, double eps, int64_t* step, unsigned long long* epoch, cudaStream_t st);
 int launch_render_rows(int W, float half_larger, float t_norm, int64_t pix_begin, int64_t count,
                        int64_t rows_padded, float* x_map, cudaStream_t st);
 int launch_render_out(const float* y, int64_t count, float* rgb, uint8_t* u8, cudaStream_t st);

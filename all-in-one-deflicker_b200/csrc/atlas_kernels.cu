@@ -560,4 +560,120 @@ int launch_render_out(const float* y, int64_t count, float* rgb, uint8_t* u8, cu
   return B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Data-parallel optimiser step over NVLink peer memory: reduce-scatter + Adam + all-gather in ONE kernel
+// (SURVEY.md §8e).  Replaces  all_reduce(grads || losses)  +  Adam  of the frame-sharded loop.
+//
+// Every rank owns one contiguous slice of the flat [gradients || 8 losses] buffer.  For its slice it sums the
+// W partial buffers (peer loads, fixed rank order: every element is summed exactly once, by one rank, so all ranks
+// end with bit-identical parameters), applies Adam (same arithmetic as adam_kernel; the moments of a slice live
+// on its owner) and stores the new parameters / the reduced losses into every rank's buffer (peer stores).
+// Cross-GPU ordering uses two flag rounds in symmetric memory, numbered by a monotonically increasing epoch:
+//   round A  "my partial buffer is complete"  — set at kernel start, awaited by every block before it loads
+//   round B  "I have finished reading and writing" — set by the last block of a rank, awaited by that block
+//            before the kernel ends, so the next kernel on any rank sees complete parameters and may overwrite
+//            its own partial buffer.
+// ---------------------------------------------------------------------------------------------
+__device__ unsigned int g_dp_ticket = 0u;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) dp_adam_kernel(B200DpComm comm, float* __restrict__ m, float* __restrict__ v,
+                                                      int64_t n_params, int64_t n_total, double lr, double b1d,
+                                                      double b2d, double epsd, int64_t* __restrict__ step_io,
+                                                      unsigned long long* __restrict__ epoch_io) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  __shared__ unsigned long long s_epoch;
+  const int W = comm.world, R = comm.rank;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_io + 1);
+    s_step_size = (float)(lr / (1.0 - pow(b1d, t)));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow(b2d, t));
+    s_epoch = *epoch_io + 1;
+  }
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
+  // ---- round A: publish "my partials are complete" (once per rank), then wait for every peer
+  if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(comm.flags[threadIdx.x] + R, epoch);
+  if (threadIdx.x < W) {
+    const unsigned long long* f = comm.flags[R] + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < epoch) {
+      if (clock64() - t0 > 20000000000ll) { printf("b200: dp_adam round A timed out (rank %d waits for %d)\n", R, (int)threadIdx.x); __trap(); }
+    }
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = (float)(1.0 - b1d), w2 = (float)(1.0 - b2d), b2 = (float)b2d, eps = (float)epsd;
+  const int64_t total4 = (n_total + 3) / 4, per = (total4 + W - 1) / W;
+  const int64_t begin4 = per * R, end4 = min(total4, per * (R + 1));
+  for (int64_t i4 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < end4; i4 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i4 * 4;
+    float4 g = *reinterpret_cast<const float4*>(comm.partials[0] + i);
+    for (int j = 1; j < W; ++j) {
+      const float4 q = *reinterpret_cast<const float4*>(comm.partials[j] + i);
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    float out[4];
+    const float ga[4] = {g.x, g.y, g.z, g.w};
+    if (i < n_params) {              // parameter block (n_params is a multiple of 4)
+      const float4 pp = *reinterpret_cast<const float4*>(comm.params[R] + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+      float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ma[q] = ma[q] + w1 * (ga[q] - ma[q]);
+        va[q] = va[q] * b2 + (w2 * ga[q]) * ga[q];
+        const float denom = sqrtf(va[q]) / bc2_sqrt + eps;
+        out[q] = pa[q] + (-step_size * ma[q]) / denom;
+      }
+      *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+      *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
+      const float4 o = make_float4(out[0], out[1], out[2], out[3]);
+      for (int j = 0; j < W; ++j) *reinterpret_cast<float4*>(comm.params[j] + i) = o;
+    } else {                          // the loss vector: every rank gets the sums in place
+      for (int j = 0; j < W; ++j) *reinterpret_cast<float4*>(const_cast<float*>(comm.partials[j]) + i) = g;
+    }
+  }
+  // ---- round B: the last block of this rank tells every peer "done" and waits for all of them
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(&g_dp_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < W) st_release_sys(comm.flags[threadIdx.x] + W + R, epoch);
+    if (threadIdx.x < W) {
+      const unsigned long long* f = comm.flags[R] + W + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < epoch) {
+        if (clock64() - t0 > 20000000000ll) { printf("b200: dp_adam round B timed out (rank %d waits for %d)\n", R, (int)threadIdx.x); __trap(); }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *step_io += 1; *epoch_io = epoch; g_dp_ticket = 0u; }
+  }
+}
+
+int launch_dp_adam(const B200DpComm& comm, float* m, float* v, int64_t n_params, int64_t n_total, double lr,
+                   double b1, double b2, double eps, int64_t* step, unsigned long long* epoch, cudaStream_t st) {
+  const int64_t total4 = (n_total + 3) / 4, per = (total4 + comm.world - 1) / comm.world;
+  int blocks = (int)((per + 255) / 256);
+  if (blocks > 148) blocks = 148;                 // all blocks must be co-resident (they wait on remote flags)
+  if (blocks < 1) blocks = 1;
+  timer_begin(TAG_ADAM, st);
+  dp_adam_kernel<<<blocks, 256, 0, st>>>(comm, m, v, n_params, n_total, lr, b1, b2, eps, step, epoch);
+  timer_end(TAG_ADAM, st);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 }  // namespace b200

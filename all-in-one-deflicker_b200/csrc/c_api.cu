@@ -427,6 +427,31 @@ int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                      reinterpret_cast<cudaStream_t>(stream));
 }
 
+int b200_dp_slice(int32_t world, int32_t rank, int64_t n_total, int64_t* begin, int64_t* count) {
+  B200_REQUIRE(world >= 1 && world <= B200_MAX_RANKS && rank >= 0 && rank < world && n_total > 0 && begin && count,
+               "bad slice request");
+  const int64_t total4 = (n_total + 3) / 4, per = (total4 + world - 1) / world;
+  const int64_t b4 = per * rank, e4 = per * (rank + 1) < total4 ? per * (rank + 1) : total4;
+  *begin = b4 * 4 < n_total ? b4 * 4 : n_total;
+  *count = e4 > b4 ? ((e4 * 4 < n_total ? e4 * 4 : n_total) - *begin) : 0;
+  return B200_OK;
+}
+
+int b200_dp_adam_step(const B200DpComm* comm, float* exp_avg, float* exp_avg_sq, int64_t n_params, int64_t n_total,
+                      double lr, double beta1, double beta2, double eps, int64_t* step, unsigned long long* epoch,
+                      void* stream) {
+  B200_REQUIRE(comm && exp_avg && exp_avg_sq && step && epoch, "null pointer");
+  B200_REQUIRE(comm->world >= 1 && comm->world <= B200_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
+               "bad communicator (world %d rank %d)", comm->world, comm->rank);
+  B200_REQUIRE(n_params > 0 && n_params % 4 == 0 && n_total >= n_params, "n_params must be a positive multiple of 4");
+  for (int j = 0; j < comm->world; ++j)
+    B200_REQUIRE(comm->partials[j] && comm->params[j] && comm->flags[j] &&
+                 (reinterpret_cast<uintptr_t>(comm->partials[j]) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(comm->params[j]) & 15) == 0, "peer buffer %d missing or misaligned", j);
+  return launch_dp_adam(*comm, exp_avg, exp_avg_sq, n_params, n_total, lr, beta1, beta2, eps, step, epoch,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
 int64_t b200_render_workspace_bytes(int64_t pixels) {
   if (pixels <= 0) return -1;
   MlpShape m, a;

@@ -174,6 +174,35 @@ int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int3
                             int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Data-parallel optimiser step (frame-sharded loop): reduce-scatter of the partial
+ * [gradients || 8 losses] buffers + Adam + all-gather of the new parameters in ONE kernel over
+ * NVLink peer memory.  Replaces  torch.distributed.all_reduce + optimizer.step()  of a data-parallel
+ * port of src/stage1_neural_atlas.py:229-231.  Every rank calls it once per iteration with the same
+ * arguments; the buffers are symmetric allocations (same size on every rank, peer-mapped):
+ *   partials[j]  rank j's flat buffer of n_total floats (gradients then the loss vector): read by all
+ *                ranks; on return its last (n_total - n_params) floats hold the global loss sums
+ *                (the one place the call writes through this pointer)
+ *   params[j]    rank j's flat parameters: on return identical on all ranks
+ *   flags[j]     rank j's 2*world uint64 flags (zero-initialised once, then owned by this call)
+ * exp_avg / exp_avg_sq are local; a rank maintains only the moments of its slice
+ * [rank * ceil(total4 / world), ...) in float4 units (b200_dp_slice).  `step` as in b200_adam_step;
+ * `epoch` is a device counter private to this call (zero-initialised).  Graph-capturable; the ranks
+ * must run the call concurrently (it waits on peer flags).
+ * ------------------------------------------------------------------------------------------ */
+#define B200_MAX_RANKS 16
+typedef struct B200DpComm {
+  int32_t world, rank;
+  const float* partials[B200_MAX_RANKS];
+  float* params[B200_MAX_RANKS];
+  unsigned long long* flags[B200_MAX_RANKS];
+} B200DpComm;
+int b200_dp_adam_step(const B200DpComm* comm, float* exp_avg, float* exp_avg_sq, int64_t n_params,
+                      int64_t n_total, double lr, double beta1, double beta2, double eps,
+                      int64_t* step, unsigned long long* epoch, void* stream);
+/* first float and number of floats of rank's slice of a buffer of n_total floats */
+int b200_dp_slice(int32_t world, int32_t rank, int64_t n_total, int64_t* begin, int64_t* count);
+
+/* ------------------------------------------------------------------------------------------
  * Stand-alone loss heads — the arithmetic of the reference's three loss FUNCTIONS
  *   get_gradient_loss_single  src/models/stage_1/loss_utils.py:134-170
  *   get_rigidity_loss         src/models/stage_1/loss_utils.py:227-278

@@ -363,3 +363,36 @@ def test_empty_flow_sets_give_nan_loss_values(golden_dir):
     assert np.isnan(losses[0]) and np.isnan(losses[5]) and losses[6] == 0 and losses[7] == 0
     ref = [float(terms[k]) for k in ("rgb", "gradient", "rigidity", "rigidity_global")]
     np.testing.assert_allclose(losses[1:5], ref, rtol=5e-4)
+
+
+def test_dp_adam_single_rank_equals_adam():
+    """b200_dp_adam_step with world = 1 (reduce over one buffer, Adam, store) is bit-identical to b200_adam_step and
+    leaves the loss tail in place; b200_dp_slice partitions a buffer without gaps."""
+    n, extra = 4096, 8
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=g)
+    partial = torch.cat((torch.randn(n, generator=g) * 1e-2, torch.arange(extra, dtype=torch.float32))).to(DEV)
+    pa, pb = p0.to(DEV), p0.to(DEV)
+    ma, va, mb, vb = (torch.zeros(n, device=DEV) for _ in range(4))
+    sa, sb = torch.zeros(1, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
+    flags = torch.zeros(2 * N.MAX_RANKS, dtype=torch.int64, device=DEV)
+    epoch = torch.zeros(1, dtype=torch.int64, device=DEV)
+    comm = N.DpComm()
+    comm.world, comm.rank = 1, 0
+    comm.partials[0], comm.params[0], comm.flags[0] = partial.data_ptr(), pb.data_ptr(), flags.data_ptr()
+    for _ in range(3):
+        N.check(N.lib().b200_adam_step(N.ptr(pa), N.ptr(partial), N.ptr(ma), N.ptr(va), n, 1e-4, 0.9, 0.999, 1e-8, 1.0,
+                                       N.ptr(sa), N.current_stream()))
+        N.check(N.lib().b200_dp_adam_step(C.byref(comm), N.ptr(mb), N.ptr(vb), n, n + extra, 1e-4, 0.9, 0.999, 1e-8,
+                                          N.ptr(sb), N.ptr(epoch), N.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+    assert int(sa) == int(sb) == 3 and int(epoch) == 3
+    assert torch.equal(partial[n:].cpu(), torch.arange(extra, dtype=torch.float32))
+    covered = 0
+    for r in range(5):
+        b, c = C.c_int64(), C.c_int64()
+        N.check(N.lib().b200_dp_slice(5, r, n + extra, C.byref(b), C.byref(c)))
+        assert b.value == covered
+        covered += c.value
+    assert covered == n + extra
