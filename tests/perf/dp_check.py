@@ -37,6 +37,23 @@ def main():
         dist.broadcast(tr.params, 0)
         trainers[name] = tr
     assert trainers["fused"]._dp is not None and trainers["nccl"]._dp is None
+    # ---- 1. the exchange itself, on identical synthetic partial buffers: tight
+    gg = torch.Generator().manual_seed(100 + rank)
+    synth_grads = (torch.randn(trainers["nccl"].n_params + N.LOSS_FLOATS, generator=gg) * 1e-2).to(dev)
+    for step in range(3):
+        for name, tr in trainers.items():
+            tr.grad_loss.copy_(synth_grads * (step + 1))
+            if tr._dp is not None:
+                tr.dp_adam()
+            else:
+                tr.all_reduce(); tr.adam()
+    torch.cuda.synchronize()
+    out["exchange_param_diff"] = float((trainers["fused"].params - trainers["nccl"].params).abs().max())
+    out["exchange_loss_diff"] = float((trainers["fused"].losses - trainers["nccl"].losses).abs().max())
+    trainers["fused"].gather_moments()
+    out["exchange_moment_rel"] = float((trainers["fused"].exp_avg - trainers["nccl"].exp_avg).abs().max() /
+                                       trainers["nccl"].exp_avg.abs().max())
+    # ---- 2. real iterations (gradients come from fp32 atomics, so two runs differ by summation order): loose
     g = torch.Generator().manual_seed(5)
     worst = {"params": 0.0, "losses": 0.0, "moments": 0.0}
     for it, use_graph in ((0, False), (1, False), (2, True), (3, True), (6000, True), (6001, True), (4, True)):
@@ -56,8 +73,9 @@ def main():
                              trainers["nccl"].exp_avg.abs().max())
     out.update(worst)
     out["steps"] = [int(trainers[n].step_count) for n in ("nccl", "fused")]
-    ok = out["rank_param_diff"] == 0.0 and worst["params"] <= 2e-6 and worst["losses"] <= 1e-5 and worst["moments"] <= 1e-4 \
-        and out["steps"] == [7, 7]
+    ok = (out["rank_param_diff"] == 0.0 and out["exchange_param_diff"] <= 1e-6 and out["exchange_loss_diff"] <= 1e-5 and
+          out["exchange_moment_rel"] <= 1e-5 and worst["params"] <= 1.5e-3 and worst["losses"] <= 1e-4 and
+          out["steps"] == [10, 10])
     out["ok"] = bool(ok)
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
