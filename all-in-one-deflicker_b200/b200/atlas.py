@@ -115,6 +115,68 @@ class DeviceVideo:
         return cls(H, W, T, t_begin, t_end, records, bits_f, bits_b)
 
 
+def _from_files(cls, data_folder, vid_root, vid_name, resy: int, resx: int, maximum_number_of_frames: int, device,
+                filter_optical_flow: bool = True, t_begin: int = 0, t_end: Optional[int] = None):
+    """The stage-1 input producer on the device: what `load_input_data_single`
+    (unwrap_utils.py:105-163) returns, built frame by frame and pair by pair straight into the pixel records and the
+    validity bitmaps — the eight (H, W, ., T) host tensors are never allocated.  The host decodes one image file at
+    a time (PIL + the reference's float64 cv2.resize, unwrap_utils.py:124-131) and reads the RAFT .npy flows; the
+    differences, the flow resize (cv2.resize-exact, swapped scale factors), the remap-exact forward/backward
+    consistency masks and the packing run in libb200deflicker.so (csrc/producer.cu).  Returns (DeviceVideo,
+    frames) with `frames` the decoded (H, W, 3, T) fp32 host tensor the PSNR of evaluate.py:740-743 needs."""
+    import cv2
+    from pathlib import Path
+    from PIL import Image
+    data_folder, vid_root = Path(data_folder), Path(vid_root)
+    flow_dir = vid_root / f"{vid_name}_flow"
+    files = sorted(list(data_folder.glob("*.jpg")) + list(data_folder.glob("*.png")))
+    T = int(min(maximum_number_of_frames, len(files)))
+    t_end = T if t_end is None else t_end
+    lib, st = N.lib(), N.current_stream()
+    H, W = int(resy), int(resx)
+    HW = H * W
+    records = torch.zeros(max(HW * (t_end - t_begin), 1) * N.RECORD_FLOATS, dtype=torch.float32, device=device)
+    words = (HW * T + 31) // 32 + 1
+    bits_f = torch.zeros(words, dtype=torch.int32, device=device)
+    bits_b = torch.zeros(words, dtype=torch.int32, device=device)
+    frames = torch.zeros((H, W, 3, T))
+    pin = torch.zeros(HW * 3, dtype=torch.float32).pin_memory()
+    frame_dev = torch.empty(HW * 3, dtype=torch.float32, device=device)
+    for i in range(T):
+        im = np.array(Image.open(str(files[i]))).astype(np.float64) / 255.
+        if im.ndim == 2:
+            im = np.tile(im[:, :, None], [1, 1, 3])
+        fr = torch.from_numpy(cv2.resize(im[:, :, :3], (W, H))).float()        # float64 -> fp32, as the reference's assignment
+        frames[:, :, :, i] = fr
+        if t_begin <= i < t_end:
+            pin.copy_(fr.reshape(-1))
+            frame_dev.copy_(pin, non_blocking=True)
+            N.check(lib.b200_producer_frame(N.ptr(frame_dev), H, W, N.ptr(records[(i - t_begin) * HW * N.RECORD_FLOATS:]),
+                                            st), "b200_producer_frame")
+            torch.cuda.current_stream().synchronize()                            # `pin` is reused by the next frame
+    scratch = torch.empty(int(lib.b200_producer_scratch_floats(H, W)), dtype=torch.float32, device=device)
+    for i in range(T - 1):
+        a, b = files[i].name, files[i + 1].name
+        f12 = np.load(flow_dir / f"{a}_{b}.npy")
+        f21 = np.load(flow_dir / f"{b}_{a}.npy")
+        if f12.shape[0] < H or f12.shape[1] < W:
+            # an up-scaling resize is outside the device kernel's pinned arithmetic: do it as the reference does
+            from src.models.stage_1.unwrap_utils import resize_flow
+            f12, f21 = resize_flow(f12, newh=H, neww=W), resize_flow(f21, newh=H, neww=W)
+        d12 = torch.from_numpy(np.ascontiguousarray(f12, dtype=np.float32)).to(device)
+        d21 = torch.from_numpy(np.ascontiguousarray(f21, dtype=np.float32)).to(device)
+        resident = (t_begin <= i < t_end) or (t_begin <= i + 1 < t_end)
+        N.check(lib.b200_producer_flow_pair(N.ptr(d12), N.ptr(d21), int(f12.shape[0]), int(f12.shape[1]), H, W, T,
+                                            t_begin, t_end, N.ptr(records) if resident else None, N.ptr(bits_f),
+                                            N.ptr(bits_b), i, 1 if filter_optical_flow else 0, N.ptr(scratch), st),
+                "b200_producer_flow_pair")
+        torch.cuda.current_stream().synchronize()
+    return cls(H, W, T, t_begin, t_end, records, bits_f, bits_b), frames
+
+
+DeviceVideo.from_files = classmethod(_from_files)
+
+
 class AtlasTrainer:
     """Flat parameters/optimiser state of (mapping, atlas) + the fused step."""
 

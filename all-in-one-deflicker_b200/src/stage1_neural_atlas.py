@@ -24,7 +24,7 @@ from tqdm import tqdm  # noqa: E402
 from b200 import _native as N  # noqa: E402
 from b200 import atlas as A    # noqa: E402
 from src.models.stage_1.evaluate import evaluate_model_single  # noqa: E402
-from src.models.stage_1.unwrap_utils import load_input_data_single, pre_train_mapping  # noqa: E402
+from src.models.stage_1.unwrap_utils import pre_train_mapping  # noqa: E402
 
 
 def main(config, args):
@@ -40,13 +40,12 @@ def main(config, args):
     with open('%s/config.json' % results_folder, 'w') as f:
         json.dump(config, f, indent=4)
 
-    flows_mask, frames, flows_rev_mask, _, dx, dy, flows_rev, flows = load_input_data_single(
-        resy, resx, config["maximum_number_of_frames"], data_folder, True, True, vid_root, vid_name)
-    T = frames.shape[3]
     device = torch.device("cuda")
-    data = dict(frames=frames, frames_dx=dx, frames_dy=dy, flow_fwd=flows, flow_bwd=flows_rev,
-                mask_fwd=flows_mask, mask_bwd=flows_rev_mask)
-    video = A.DeviceVideo.from_reference_layout(data, device)
+    # input producer on the device (the reference's load_input_data_single, unwrap_utils.py:105-163): frames, image
+    # differences, resized flows and consistency masks go straight into HBM; `frames` is the decoded video for PSNR
+    video, frames = A.DeviceVideo.from_files(data_folder, vid_root, vid_name, resy, resx,
+                                             config["maximum_number_of_frames"], device, filter_optical_flow=True)
+    T = frames.shape[3]
     precision = N.PREC_TC if N.lib().b200_device_supports_tc() else N.PREC_FP32
     trainer = A.AtlasTrainer(video, config, precision=precision, device=device, resx=resx)
     trainer.init_like_reference()          # mapping then atlas, nn.Linear stream order (:112-128)

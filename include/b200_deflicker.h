@@ -174,6 +174,29 @@ int b200_pretrain_loss_grad(const B200AtlasConfig* cfg, int32_t larger_dim, int3
                             int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input producer on the device — replaces the per-frame / per-pair arithmetic of
+ *   load_input_data_single   src/models/stage_1/unwrap_utils.py:105-163
+ *   resize_flow              :33-38   (cv2.resize INTER_LINEAR + the swapped scale factors)
+ *   compute_consistency      :10-23   (cv2.remap bilinear, zero border; mask = error < 1.0)
+ * writing B200Video.records / bitmaps directly (no (H,W,.,T) host tensors).  Bit-exact with the
+ * reference's tensors for flows that are not smaller than the working resolution (down-scaling or
+ * equal size; an up-scaling flow is refused with B200_ERR_INVALID: resize it on the host first).
+ * `records` and the bitmaps must be zero-initialised once (slots of missing partners stay 0).
+ * ------------------------------------------------------------------------------------------ */
+/* frame: decoded + resized frame (H, W, 3) fp32 in [0,1]; frame_records: records of that frame */
+int b200_producer_frame(const float* frame, int32_t H, int32_t W, float* frame_records,
+                        void* stream);
+int64_t b200_producer_scratch_floats(int32_t H, int32_t W);
+/* flow12 / flow21: the two RAFT flows of the frame pair (first_frame, first_frame + 1), (h, w, 2)
+ * fp32 as stored in <vid>_flow/{a}_{b}.npy.  (H, W, T, t_begin, t_end) as in B200Video; records =
+ * the resident records (NULL on a rank that holds neither frame: only the whole-video bitmaps,
+ * replicated on every rank, are updated).  filter = filter_optical_flow. */
+int b200_producer_flow_pair(const float* flow12, const float* flow21, int32_t h, int32_t w,
+                            int32_t H, int32_t W, int32_t T, int32_t t_begin, int32_t t_end,
+                            float* records, uint32_t* mask_fwd_bits, uint32_t* mask_bwd_bits,
+                            int32_t first_frame, int32_t filter, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Data-parallel optimiser step (frame-sharded loop): reduce-scatter of the partial
  * [gradients || 8 losses] buffers + Adam + all-gather of the new parameters in ONE kernel over
  * NVLink peer memory.  Replaces  torch.distributed.all_reduce + optimizer.step()  of a data-parallel

@@ -46,3 +46,51 @@ def consistency_error(flow12, flow21):
     gy = flow12[:, :, 1] + np.arange(H, dtype=np.float32)[:, None]
     d = flow12 + remap_bilinear_zero(flow21, gx, gy)
     return (d[:, :, 0] ** 2 + d[:, :, 1] ** 2) ** np.float32(.5)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# cv2.resize(INTER_LINEAR) for fp32 images when the output is not larger than the input in either dimension — the
+# case `resize_flow` (unwrap_utils.py:33-38) meets: RAFT flows are computed at the frame files' resolution and the
+# atlas runs at that resolution divided by `--down`.  Pinned bit-exactly against cv2.resize by
+# tests/test_loader_oracle.py (random sizes, integer and fractional factors).
+#   * sampling position of destination index d: fx = fp32((d + 0.5) * (src / dst) - 0.5) (the product in float64),
+#     s = floor(fx), weight = fx - s; positions left of the first / right of the last source sample clamp to it with
+#     weight 0
+#   * two passes, each result rounded to fp32: rows first  S[s]*(1-a) + S[s+1]*a, then columns  R[s]*(1-b) + R[s+1]*b,
+#     products and sums as separate fp32 operations (no fused multiply-add)
+#   * exactly half size in BOTH dimensions is OpenCV's "area fast" path: ((a + b) + c) + d) * 0.25 over the 2x2 block
+# ----------------------------------------------------------------------------------------------------------------
+def _resize_taps(dst: int, src: int):
+    scale = np.float64(src) / np.float64(dst)
+    f = ((np.arange(dst) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    f[s < 0] = 0; s[s < 0] = 0
+    f[s >= src - 1] = 0; s[s >= src - 1] = src - 1
+    return s, np.minimum(s + 1, src - 1), f
+
+
+def resize_bilinear_down(img, neww: int, newh: int):
+    """cv2.resize(img, (neww, newh), interpolation=cv2.INTER_LINEAR) for fp32 (H, W, C), newh <= H and neww <= W."""
+    img = np.asarray(img, dtype=np.float32)
+    h, w = img.shape[:2]
+    assert newh <= h and neww <= w, "the restatement covers down-scaling (and identity) only"
+    f32 = lambda a: a.astype(np.float32)
+    if h == 2 * newh and w == 2 * neww:
+        a, b, c, d = img[0::2, 0::2], img[0::2, 1::2], img[1::2, 0::2], img[1::2, 1::2]
+        return f32(f32(f32(f32(a + b) + c) + d) * np.float32(0.25))
+    sx, sx1, fx = _resize_taps(neww, w)
+    sy, sy1, fy = _resize_taps(newh, h)
+    a0, a1 = f32(np.float32(1) - fx)[None, :, None], fx[None, :, None]
+    b0, b1 = f32(np.float32(1) - fy)[:, None, None], fy[:, None, None]
+    rows = f32(f32(img[:, sx] * a0) + f32(img[:, sx1] * a1))
+    return f32(f32(rows[sy] * b0) + f32(rows[sy1] * b1))
+
+
+def resize_flow(flow, newh: int, neww: int):
+    """`resize_flow` of unwrap_utils.py:33-38, including its swapped scale factors (x by newh/oldh, y by neww/oldw)."""
+    oldh, oldw = flow.shape[:2]
+    out = resize_bilinear_down(flow, neww, newh).copy()
+    out[:, :, 0] *= np.float32(newh / oldh)
+    out[:, :, 1] *= np.float32(neww / oldw)
+    return out

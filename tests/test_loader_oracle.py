@@ -37,3 +37,38 @@ def test_consistency_matches_the_input_producer():
     got = L.consistency_error(f12, f21)
     assert got.dtype == want.dtype == np.float32 and np.array_equal(got, want)
     assert 0.05 < float((got < 1.0).mean()) < 0.95
+
+
+def test_resize_restatement_matches_opencv_bit_for_bit():
+    """cv2.resize(INTER_LINEAR) on fp32 flows for every down-scaling / identity geometry class: fractional factors,
+    integer factors (4 = the scripts' --down default), exactly 2x in both dimensions (OpenCV's area-fast path), 2x
+    in one dimension only, same size."""
+    rng = np.random.default_rng(2)
+    checked = 0
+    for trial in range(120):
+        h, w = int(rng.integers(8, 160)), int(rng.integers(8, 220))
+        kind = trial % 4
+        if kind == 0:
+            nh, nw = int(rng.integers(4, h + 1)), int(rng.integers(4, w + 1))
+        elif kind == 1:
+            k = int(rng.integers(1, 5)); nh, nw = max(2, h // k), max(2, w // k); h, w = nh * k, nw * k
+        elif kind == 2:
+            nh, nw = h // 2, int(rng.integers(4, w + 1)); h = nh * 2
+        else:
+            nh, nw = h, w
+        src = (rng.standard_normal((h, w, 2)) * 5).astype(np.float32)
+        want = cv2.resize(src, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(L.resize_bilinear_down(src, nw, nh), want), (h, w, nh, nw)
+        checked += 1
+    assert checked == 120
+
+
+def test_resize_flow_matches_the_input_producer():
+    path = os.path.join(ROOT, "all-in-one-deflicker_b200", "src", "models", "stage_1", "unwrap_utils.py")
+    spec = importlib.util.spec_from_file_location("our_unwrap_utils2", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                             # pinned against the reference (test_loader_golden.py)
+    rng = np.random.default_rng(9)
+    for (h, w, nh, nw) in ((36, 52, 30, 44), (360, 640, 90, 160), (90, 160, 45, 80), (40, 40, 40, 40)):
+        f = (rng.standard_normal((h, w, 2)) * 4).astype(np.float32)
+        assert np.array_equal(L.resize_flow(f, nh, nw), mod.resize_flow(f.copy(), nh, nw)), (h, w, nh, nw)
