@@ -7,14 +7,24 @@ import torch.nn as nn
 from b200 import nn as K
 
 
+_fold_cache = {}     # id(conv) -> (versions of every source tensor, folded weight, folded bias)
+
+
 def _folded(conv, norm):
-    """conv followed by eval-mode BatchNorm2d == conv with scaled weights / shifted bias."""
-    w, b = conv.weight, conv.bias.detach()      # the parameter itself: b200.nn caches its packed images
-    if isinstance(norm, nn.BatchNorm2d):
+    """conv followed by eval-mode BatchNorm2d == conv with scaled weights / shifted bias.  The folded tensors are
+    cached per convolution and per in-place version of their sources, so `b200.nn` keeps hitting its packed
+    weight-image cache (which is keyed on the weight TENSOR) instead of re-packing every forward."""
+    if not isinstance(norm, nn.BatchNorm2d):
+        return conv.weight, conv.bias.detach()   # the parameter itself: b200.nn caches its packed images
+    src = (conv.weight, conv.bias, norm.weight, norm.bias, norm.running_mean, norm.running_var)
+    key = tuple((t.data_ptr(), t._version) for t in src)
+    ent = _fold_cache.get(id(conv))
+    if ent is None or ent[0] != key:
         s = norm.weight.detach() / torch.sqrt(norm.running_var + norm.eps)
-        w = (w * s.view(-1, 1, 1, 1)).contiguous()
-        b = (b - norm.running_mean) * s + norm.bias.detach()
-    return w, b
+        w = (conv.weight.detach() * s.view(-1, 1, 1, 1)).contiguous()
+        b = ((conv.bias.detach() - norm.running_mean) * s + norm.bias.detach()).contiguous()
+        ent = _fold_cache[id(conv)] = (key, w, b)
+    return ent[1], ent[2]
 
 
 def _conv_norm(conv, norm, x, relu=True):
