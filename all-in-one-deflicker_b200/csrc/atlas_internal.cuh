@@ -33,6 +33,9 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, double 
                 double eps, float grad_scale, int64_t* step, cudaStream_t st);
 int launch_dp_adam(const B200DpComm& comm, float* m, float* v, int64_t n_params, int64_t n_total, double lr,
                    double b1, double b2, double eps, int64_t* step, unsigned long long* epoch, cudaStream_t st);
+int launch_pack_rows(const float* src, int ld_src, int cols, float* dst, int ld_dst, int64_t rows, int64_t rows_pad,
+                     cudaStream_t st);
+int launch_absmax(const float* src, int64_t n, int* out_bits, cudaStream_t st);
 int launch_render_rows(int W, float half_larger, float t_norm, int64_t pix_begin, int64_t count,
                        int64_t rows_padded, float* x_map, cudaStream_t st);
 int launch_render_out(const float* y, int64_t count, float* rgb, uint8_t* u8, cudaStream_t st);

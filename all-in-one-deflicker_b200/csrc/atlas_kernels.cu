@@ -562,6 +562,42 @@ int launch_render_out(const float* y, int64_t count, float* rgb, uint8_t* u8, cu
 
 
 // ---------------------------------------------------------------------------------------------
+// helpers of the stand-alone tensor-core IMLP entry points (c_api.cu): zero-padded row packing, max |x|
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_rows_kernel(const float* __restrict__ src, int ld_src, int cols, float* __restrict__ dst, int ld_dst,
+                                 int64_t rows, int64_t rows_pad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows_pad * ld_dst) return;
+  const int64_t r = e / ld_dst;
+  const int c = (int)(e % ld_dst);
+  dst[e] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.f;
+}
+
+__global__ void absmax_kernel(const float* __restrict__ src, int64_t n, int* __restrict__ out_bits) {
+  float mx = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(src[i]));
+  publish_gmax(mx, out_bits);
+}
+
+int launch_pack_rows(const float* src, int ld_src, int cols, float* dst, int ld_dst, int64_t rows, int64_t rows_pad,
+                     cudaStream_t st) {
+  const int64_t n = rows_pad * ld_dst;
+  pack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, ld_src, cols, dst, ld_dst, rows, rows_pad);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int launch_absmax(const float* src, int64_t n, int* out_bits, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 592) blocks = 592;
+  absmax_kernel<<<blocks, 256, 0, st>>>(src, n, out_bits);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // Data-parallel optimiser step over NVLink peer memory: reduce-scatter + Adam + all-gather in ONE kernel
 // (SURVEY.md §8e).  Replaces  all_reduce(grads || losses)  +  Adam  of the frame-sharded loop.
 //

@@ -172,10 +172,65 @@ int64_t b200_mlp_layout(const B200MlpDesc* d, int64_t* w_off, int64_t* b_off) {
   return s.total;
 }
 
+// which of the two stage-1 architectures a descriptor is (tensor-core kernels are specialised to them): 1 mapping,
+// 2 atlas, 0 neither
+static int tc_architecture(const MlpShape& s) {
+  if (s.hidden != 256) return 0;
+  if (s.L == 6 && s.pe == 0 && s.in_dim == 3 && s.out_dim == 2) {
+    for (int l = 1; l < s.L; ++l) if (s.skip[l]) return 0;
+    return 1;
+  }
+  if (s.L == 8 && s.pe == 10 && s.in_dim == 2 && s.out_dim == 3) {
+    for (int l = 1; l < s.L; ++l) if (s.skip[l] != (l == 4 || l == 7)) return 0;
+    return 2;
+  }
+  return 0;
+}
+
+// buffers of a stand-alone tensor-core call, carved from the caller's workspace
+struct TcCallPlan { int* gmax2; float* x; float* y; float* dy; float* d_in; char* tc; int64_t bytes; };
+static void plan_tc_call(const MlpShape& s, int arch, int64_t rows_pad, char* base, TcCallPlan* pl) {
+  char* p = base;
+  pl->gmax2 = reinterpret_cast<int*>(carve(p, 64));
+  pl->x = reinterpret_cast<float*>(carve(p, rows_pad * 16));
+  pl->y = reinterpret_cast<float*>(carve(p, rows_pad * s.out_dim * 4));
+  pl->dy = reinterpret_cast<float*>(carve(p, rows_pad * s.out_dim * 4));
+  pl->d_in = reinterpret_cast<float*>(carve(p, rows_pad * 8));
+  pl->tc = p;
+  pl->bytes = (p - base) + tc_single_workspace_bytes(s, arch == 2, rows_pad);
+}
+
 int64_t b200_mlp_workspace_bytes(const B200MlpDesc* d, int64_t rows, int training) {
   MlpShape s;
   if (resolve_mlp(d, &s) != B200_OK || rows < 0) return -1;
-  return plan_mlp_scratch(s, round_up(rows, kTileRows), training != 0, nullptr, nullptr) + 256;
+  const int64_t rows_pad = round_up(rows, kTileRows);
+  int64_t need = plan_mlp_scratch(s, rows_pad, training != 0, nullptr, nullptr) + 256;
+  const int arch = tc_architecture(s);
+  if (arch) {          // enough for either precision
+    TcCallPlan pl;
+    plan_tc_call(s, arch, rows_pad, nullptr, &pl);
+    if (pl.bytes + 2048 > need) need = pl.bytes + 2048;
+  }
+  return need;
+}
+
+static int tc_call_prepare(const B200MlpDesc* d, int64_t rows, void* ws, int64_t ws_bytes, MlpShape* s, int* arch,
+                           int64_t* rows_pad, TcCallPlan* pl) {
+  B200_PROPAGATE(resolve_mlp(d, s));
+  *arch = tc_architecture(*s);
+  B200_REQUIRE(*arch != 0, "B200_PREC_TC serves the two stage-1 architectures (mapping: 3-256x4-2 without encoding; "
+               "atlas: 2-PE10-256x6-3 with skips 4, 7); use B200_PREC_FP32 for other shapes");
+  if (!b200_device_supports_tc()) { set_error("B200_PREC_TC needs a compute-capability 10.x device"); return B200_ERR_UNSUPPORTED; }
+  B200_REQUIRE(rows > 0 && rows < (1ll << 26), "rows out of range: %lld", (long long)rows);
+  B200_REQUIRE(ws != nullptr, "null workspace");
+  *rows_pad = round_up(rows, kTileRows);
+  char* base = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(ws), 1024));
+  plan_tc_call(*s, *arch, *rows_pad, base, pl);
+  if (base + pl->bytes > reinterpret_cast<char*>(ws) + ws_bytes) {
+    set_error("workspace too small: need %lld bytes", (long long)(pl->bytes + 2048));
+    return B200_ERR_WORKSPACE;
+  }
+  return B200_OK;
 }
 
 static int mlp_prepare(const B200MlpDesc* d, int64_t rows, void* ws, int64_t ws_bytes, MlpShape* s,
@@ -195,13 +250,19 @@ static int mlp_prepare(const B200MlpDesc* d, int64_t rows, void* ws, int64_t ws_
 
 int b200_mlp_forward(const B200MlpDesc* d, const float* params, const float* x, float* y, int64_t rows,
                      int training, int precision, void* ws, int64_t ws_bytes, void* stream) {
-  (void)training;
   MlpShape s; MlpScratch sc; RowSpan span;
   B200_REQUIRE(params && x && y, "null pointer");
-  B200_PROPAGATE(mlp_prepare(d, rows, ws, ws_bytes, &s, &sc, &span));
-  B200_REQUIRE(precision == B200_PREC_FP32, "generic IMLP entry points run the fp32 path; the tensor-core path "
-               "is reached through b200_atlas_loss_grad / b200_render");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == B200_PREC_TC) {
+    int arch; int64_t rows_pad; TcCallPlan pl;
+    B200_PROPAGATE(tc_call_prepare(d, rows, ws, ws_bytes, &s, &arch, &rows_pad, &pl));
+    B200_PROPAGATE(launch_pack_rows(x, s.in_dim, s.in_dim, pl.x, arch == 1 ? 4 : 2, rows, rows_pad, st));
+    B200_PROPAGATE(tc_single_forward(s, arch == 2, params, pl.x, pl.y, rows_pad, training != 0, pl.tc, st));
+    B200_CHECK_CUDA(cudaMemcpyAsync(y, pl.y, (size_t)rows * s.out_dim * 4, cudaMemcpyDeviceToDevice, st));
+    return B200_OK;
+  }
+  B200_REQUIRE(precision == B200_PREC_FP32, "unknown precision %d", precision);
+  B200_PROPAGATE(mlp_prepare(d, rows, ws, ws_bytes, &s, &sc, &span));
   if (s.pe > 0) {
     float* skips[B200_MAX_LAYERS]; int lds[B200_MAX_LAYERS]; int ns = 0;
     for (int l = 1; l < s.L; ++l) if (s.skip[l]) { skips[ns] = sc.act[l]; lds[ns] = s.K[l]; ++ns; }
@@ -224,9 +285,23 @@ int b200_mlp_backward(const B200MlpDesc* d, const float* params, const float* x,
                       void* stream) {
   MlpShape s; MlpScratch sc; RowSpan span;
   B200_REQUIRE(params && dy && dparams && x, "null pointer");
-  B200_PROPAGATE(mlp_prepare(d, rows, ws, ws_bytes, &s, &sc, &span));
-  B200_REQUIRE(precision == B200_PREC_FP32, "generic IMLP entry points run the fp32 path");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == B200_PREC_TC) {
+    // the workspace still holds the padded input, the outputs and the activation images of the forward call
+    int arch; int64_t rows_pad; TcCallPlan pl;
+    B200_PROPAGATE(tc_call_prepare(d, rows, ws, ws_bytes, &s, &arch, &rows_pad, &pl));
+    B200_REQUIRE(arch == 2 || dx == nullptr, "the tensor-core mapping network has no input gradient (its inputs are "
+                 "pixel coordinates); use B200_PREC_FP32 when x requires grad");
+    B200_PROPAGATE(launch_pack_rows(dy, s.out_dim, s.out_dim, pl.dy, s.out_dim, rows, rows_pad, st));
+    B200_CHECK_CUDA(cudaMemsetAsync(pl.gmax2, 0, 8, st));
+    B200_PROPAGATE(launch_absmax(pl.dy, rows_pad * s.out_dim, pl.gmax2 + (arch == 1 ? 1 : 0), st));
+    B200_PROPAGATE(tc_single_backward(s, arch == 2, params, dparams, pl.x, pl.y, pl.dy, (arch == 2 && dx) ? pl.d_in : nullptr,
+                                      pl.gmax2, rows_pad, pl.tc, st));
+    if (arch == 2 && dx) B200_CHECK_CUDA(cudaMemcpyAsync(dx, pl.d_in, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st));
+    return B200_OK;
+  }
+  B200_REQUIRE(precision == B200_PREC_FP32, "unknown precision %d", precision);
+  B200_PROPAGATE(mlp_prepare(d, rows, ws, ws_bytes, &s, &sc, &span));
   if (s.pe > 0) {
     // the encoded-input gradient is staged in a slice carved after the scratch
     float* d_enc = nullptr;

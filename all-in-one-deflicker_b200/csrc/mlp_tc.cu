@@ -1154,92 +1154,61 @@ static void add_prep(PrepJobs& pj, const float* W, int ldw, int n_rows, int k0, 
   j.hi = dst; j.lo = dst + STAGE_BYTES;
 }
 
-static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, HostTables** out) {
-  if (HostTables* t = find_tables(s)) { *out = t; return B200_OK; }
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(st, &cs);
-  if (cs == cudaStreamCaptureStatusActive) {
-    set_error("tensor-core tables must be built by one eager call before graph capture");
-    return B200_ERR_INVALID;
+
+// ---- table builders shared by the cached (training loop) and the ephemeral (stand-alone IMLP) paths
+static void prep_jobs_for_net(PrepJobs& pj, const MlpShape& sh, const NetImages& im, const float* pp, bool is_atlas,
+                              bool with_bwd) {
+  for (int l = 0; l < sh.L; ++l) {
+    char* dst = im.w_fwd + im.w_fwd_layer[l];
+    if (im.n_chunks_fwd[l] == 0) continue;
+    const float* W = pp + sh.w_off[l];
+    int item = 0;
+    if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+    if (is_atlas && (l == 0 || sh.skip[l]))
+      add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
   }
-  B200_REQUIRE(s.as->L == 8 && s.ms->L == 6 && s.as->skip[4] && s.as->skip[7] && s.as->pe == 10 && s.ms->pe == 0 &&
-               s.as->hidden == HID && s.ms->hidden == HID, "tensor-core path is specialised to the two stage-1 networks");
-  {
-    std::lock_guard<std::mutex> lock(g_tabs_mutex);
-    B200_REQUIRE((int)g_tabs.size() < MAX_TABLES, "too many distinct tensor-core workspaces in one process (%d)",
-                 MAX_TABLES);
+  if (!with_bwd) return;
+  for (int l = 0; l < sh.L - 1; ++l) {
+    if (!is_atlas && l < 1) continue;
+    char* dst = im.w_bwd + im.w_bwd_layer[l];
+    const float* W = pp + sh.w_off[l];
+    // image rows = input index k of layer l (256, or 40 for atlas layer 0), chunk over the output index n
+    const int rows = (is_atlas && l == 0) ? PE_COLS : 256;
+    for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], rows, kc * 64, 64, 1, dst + (int64_t)kc * 2 * STAGE_BYTES);
   }
-  std::unique_ptr<HostTables> tab_owner(new HostTables());
-  HostTables& tab = *tab_owner;
-  B200_CHECK_CUDA(cudaMalloc(&tab.d_prep, sizeof(PrepJobs)));
-  B200_CHECK_CUDA(cudaMalloc(&tab.d_wg, sizeof(WgradItems)));
-  std::unique_ptr<PrepJobs> pj_owner(new PrepJobs()); std::unique_ptr<WgradItems> wi_owner(new WgradItems());
-  PrepJobs& pj = *pj_owner; WgradItems& wi = *wi_owner;
-  pj.n = 0; wi.n = 0;
-  const float* pm = s.params;
-  const float* pa = s.params + s.ms->total;
-  const bool atlas = s.y_atlas != nullptr;
-  // ---- forward / dgrad weight images
-  for (int net = 0; net < 2; ++net) {
-    const MlpShape& sh = net ? *s.as : *s.ms;
-    const NetImages& im = net ? lay.atl : lay.map;
-    const float* pp = net ? pa : pm;
-    for (int l = 0; l < sh.L; ++l) {
-      char* dst = im.w_fwd + im.w_fwd_layer[l];
-      if (im.n_chunks_fwd[l] == 0) continue;
-      const float* W = pp + sh.w_off[l];
-      int item = 0;
-      if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
-      if (net && (l == 0 || sh.skip[l]))
-        add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
-    }
-    for (int l = 0; l < sh.L - 1; ++l) {
-      if (!net && l < 1) continue;
-      char* dst = im.w_bwd + im.w_bwd_layer[l];
-      const float* W = pp + sh.w_off[l];
-      // image rows = input index k of layer l (256, or 40 for atlas layer 0), chunk over the output index n
-      const int rows = (net && l == 0) ? PE_COLS : 256;
-      for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], rows, kc * 64, 64, 1, dst + (int64_t)kc * 2 * STAGE_BYTES);
-    }
-  }
-  // ---- wgrad items.  The kernel is HBM-bound: balance CTAs by bytes read per tile
-  //      (A + B, both terms): 256x256 -> 256 KB, 256x64 -> 160 KB, 64x256 -> 160 KB, 64x64 -> 64 KB
-  struct Proto { const char* a; int64_t a_term; int a_cols; const char* b; int64_t b_term; int b_cols;
+}
+
+// wgrad work list.  The kernel is HBM-bound: CTAs are balanced by bytes read per tile
+// (A + B, both terms): 256x256 -> 256 KB, 256x64 -> 160 KB, 64x256 -> 160 KB, 64x64 -> 64 KB
+struct WgProto { const char* a; int64_t a_term; int a_cols; const char* b; int64_t b_term; int b_cols;
                  float* out; int ld; int n_rows, n_cols, groups; double bytes; int mapping; };
-  Proto protos[32]; int np = 0;
-  float* gm = s.grads;
-  float* ga = s.grads + s.ms->total;
-  auto add_proto = [&](const char* a, int64_t a_term, int a_cols, const char* b, int64_t b_term,
-                       int b_cols, float* out, int ld, int n_rows, int n_cols, int groups) {
-    protos[np++] = Proto{a, a_term, a_cols, b, b_term, b_cols, out, ld, n_rows, n_cols, groups,
-                         (double)groups * (a_cols + b_cols) * 512.0, out < ga ? 1 : 0};
+
+static void protos_for_net(WgProto* protos, int& np, const MlpShape& sh, const NetImages& im, float* g, bool is_atlas,
+                           int groups) {
+  auto add = [&](const char* a, int64_t a_term, int a_cols, const char* b, int64_t b_term, int b_cols, float* out, int ld,
+                 int n_rows, int n_cols) {
+    protos[np++] = WgProto{a, a_term, a_cols, b, b_term, b_cols, out, ld, n_rows, n_cols, groups,
+                           (double)groups * (a_cols + b_cols) * 512.0, is_atlas ? 0 : 1};
   };
-  {
-    const NetImages& im = lay.map; const MlpShape& sh = *s.ms;
-    for (int l = 1; l <= sh.L - 2; ++l)
-      add_proto(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.act + (int64_t)(l - 1) * im.slot_stride,
-                im.term_stride, 256, gm + sh.w_off[l], sh.K[l], 256, 256, s.n_groups);
-    add_proto(im.dzl, im.w64_term_stride, 64, im.act + (int64_t)(sh.L - 2) * im.slot_stride, im.term_stride, 256,
-              gm + sh.w_off[sh.L - 1], sh.K[sh.L - 1], sh.out_dim, 256, s.n_groups);
+  for (int l = 1; l <= sh.L - 2; ++l)
+    add(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.act + (int64_t)(l - 1) * im.slot_stride,
+        im.term_stride, 256, g + sh.w_off[l], sh.K[l], 256, 256);
+  add(im.dzl, im.w64_term_stride, 64, im.act + (int64_t)(sh.L - 2) * im.slot_stride, im.term_stride, 256,
+      g + sh.w_off[sh.L - 1], sh.K[sh.L - 1], sh.out_dim, 256);
+  if (is_atlas) {
+    // positional-encoding parts: layer 0 and the skip layers; output layer's skip part
+    add(im.dz, im.term_stride, 256, im.pe, im.w64_term_stride, 64, g + sh.w_off[0], sh.K[0], 256, PE_COLS);
+    add(im.dz + (int64_t)4 * im.slot_stride, im.term_stride, 256, im.pe, im.w64_term_stride, 64, g + sh.w_off[4] + 256,
+        sh.K[4], 256, PE_COLS);
+    add(im.dzl, im.w64_term_stride, 64, im.pe, im.w64_term_stride, 64, g + sh.w_off[sh.L - 1] + 256, sh.K[sh.L - 1],
+        sh.out_dim, PE_COLS);
   }
-  if (atlas) {
-    const NetImages& im = lay.atl; const MlpShape& sh = *s.as;
-    for (int l = 1; l <= sh.L - 2; ++l)
-      add_proto(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.act + (int64_t)(l - 1) * im.slot_stride,
-                im.term_stride, 256, ga + sh.w_off[l], sh.K[l], 256, 256, 3);
-    // positional-encoding parts: layer 0 and the skip layers
-    add_proto(im.dz, im.term_stride, 256, im.pe, im.w64_term_stride, 64, ga + sh.w_off[0], sh.K[0], 256, PE_COLS, 3);
-    add_proto(im.dz + (int64_t)4 * im.slot_stride, im.term_stride, 256, im.pe, im.w64_term_stride, 64,
-              ga + sh.w_off[4] + 256, sh.K[4], 256, PE_COLS, 3);
-    // output layer: hidden part and skip part
-    add_proto(im.dzl, im.w64_term_stride, 64, im.act + (int64_t)(sh.L - 2) * im.slot_stride, im.term_stride, 256,
-              ga + sh.w_off[sh.L - 1], sh.K[sh.L - 1], sh.out_dim, 256, 3);
-    add_proto(im.dzl, im.w64_term_stride, 64, im.pe, im.w64_term_stride, 64, ga + sh.w_off[sh.L - 1] + 256,
-              sh.K[sh.L - 1], sh.out_dim, PE_COLS, 3);
-  }
+}
+
+// exactly one CTA per SM (each CTA owns all 512 TMEM columns): largest-remainder apportionment of the SMs
+static void apportion_items(WgradItems& wi, const WgProto* protos, int np, int cap, int flow_groups) {
   double total_bytes = 0;
   for (int i = 0; i < np; ++i) total_bytes += protos[i].bytes;
-  // exactly one CTA per SM (each CTA owns all 512 TMEM columns): largest-remainder apportionment
   const int sms = sm_count();
   int n_split[32], used = 0;
   double frac[32];
@@ -1263,14 +1232,47 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
   for (int i = 0; i < np; ++i) {
     for (int sp = 0; sp < n_split[i] && wi.n < MAX_WGRAD_ITEMS; ++sp) {
       WgradItem& it = wi.it[wi.n++];
-      const Proto& pr = protos[i];
+      const WgProto& pr = protos[i];
       it.a_img = pr.a; it.a_term = pr.a_term; it.a_cols = pr.a_cols;
       it.b_img = pr.b; it.b_term = pr.b_term; it.b_cols = pr.b_cols;
       it.out = pr.out; it.ld_out = pr.ld; it.n_rows = pr.n_rows; it.n_cols = pr.n_cols;
-      it.cap = s.cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split[i]; it.mapping = pr.mapping;
-      it.flow_groups = (pr.mapping && s.flow_groups) ? 1 : 0;
+      it.cap = cap; it.n_groups = pr.groups; it.split = sp; it.n_split = n_split[i]; it.mapping = pr.mapping;
+      it.flow_groups = (pr.mapping && flow_groups) ? 1 : 0;
     }
   }
+}
+
+static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, HostTables** out) {
+  if (HostTables* t = find_tables(s)) { *out = t; return B200_OK; }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs == cudaStreamCaptureStatusActive) {
+    set_error("tensor-core tables must be built by one eager call before graph capture");
+    return B200_ERR_INVALID;
+  }
+  B200_REQUIRE(s.as->L == 8 && s.ms->L == 6 && s.as->skip[4] && s.as->skip[7] && s.as->pe == 10 && s.ms->pe == 0 &&
+               s.as->hidden == HID && s.ms->hidden == HID, "tensor-core path is specialised to the two stage-1 networks");
+  {
+    std::lock_guard<std::mutex> lock(g_tabs_mutex);
+    B200_REQUIRE((int)g_tabs.size() < MAX_TABLES, "too many distinct tensor-core workspaces in one process (%d)",
+                 MAX_TABLES);
+  }
+  std::unique_ptr<HostTables> tab_owner(new HostTables());
+  HostTables& tab = *tab_owner;
+  B200_CHECK_CUDA(cudaMalloc(&tab.d_prep, sizeof(PrepJobs)));
+  B200_CHECK_CUDA(cudaMalloc(&tab.d_wg, sizeof(WgradItems)));
+  std::unique_ptr<PrepJobs> pj_owner(new PrepJobs()); std::unique_ptr<WgradItems> wi_owner(new WgradItems());
+  PrepJobs& pj = *pj_owner; WgradItems& wi = *wi_owner;
+  pj.n = 0; wi.n = 0;
+  const bool atlas = s.y_atlas != nullptr;
+  // ---- forward / dgrad weight images (the atlas network only where it is evaluated: not in pre-training)
+  prep_jobs_for_net(pj, *s.ms, lay.map, s.params, false, true);
+  if (atlas) prep_jobs_for_net(pj, *s.as, lay.atl, s.params + s.ms->total, true, true);
+  // ---- wgrad items
+  WgProto protos[32]; int np = 0;
+  protos_for_net(protos, np, *s.ms, lay.map, s.grads, false, s.n_groups);
+  if (atlas) protos_for_net(protos, np, *s.as, lay.atl, s.grads + s.ms->total, true, 3);
+  apportion_items(wi, protos, np, s.cap, s.flow_groups);
   if (pj.n > MAX_PREP_JOBS) { set_error("table overflow"); return B200_ERR_INVALID; }
   B200_CHECK_CUDA(cudaMemcpyAsync(tab.d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
   B200_CHECK_CUDA(cudaMemcpyAsync(tab.d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice, st));
@@ -1432,20 +1434,8 @@ int tc_infer_forward(const MlpShape& ms, const MlpShape& as, const float* params
   static thread_local PrepJobs pj_host;
   PrepJobs* pj = &pj_host;
   pj->n = 0;
-  for (int net = 0; net < 2; ++net) {
-    const MlpShape& sh = net ? as : ms;
-    const NetImages& im = net ? im_atl : im_map;
-    const float* pp = net ? params + ms.total : params;
-    for (int l = 0; l < sh.L; ++l) {
-      if (im.n_chunks_fwd[l] == 0) continue;
-      char* dst = im.w_fwd + im.w_fwd_layer[l];
-      const float* Wl = pp + sh.w_off[l];
-      int item = 0;
-      if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(*pj, Wl, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
-      if (net && (l == 0 || sh.skip[l]))
-        add_prep(*pj, Wl, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
-    }
-  }
+  prep_jobs_for_net(*pj, ms, im_map, params, false, false);
+  prep_jobs_for_net(*pj, as, im_atl, params + ms.total, true, false);
   B200_CHECK_CUDA(cudaMemcpyAsync(d_prep, pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
   tc_prep_kernel<<<pj->n * 4, 128, 0, st>>>(d_prep);
   B200_CHECK_LAUNCH();
@@ -1459,6 +1449,91 @@ int tc_infer_forward(const MlpShape& ms, const MlpShape& as, const float* params
   fill_fwd(pa, as, im_atl, uv, y, params + ms.total, (int)rows, 1, nullptr);
   pa.store_images = 0;
   tc_fwd_kernel<true><<<min(sm_count(), tiles), TC_THREADS, KCfg<true>::SMEM, st>>>(pa);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone evaluation of ONE of the two networks with autograd support: what the `IMLP` class needs
+// (implicit_neural_networks.py:62-81 forward + the autograd of its Linear/ReLU/tanh/skip stack).  Tables are
+// rebuilt into the caller's workspace on every call (pageable copies; not graph-capturable): no process-wide cache.
+// Workspace: [PrepJobs][WgradItems][images of the network].
+// ---------------------------------------------------------------------------------------------
+struct SinglePlan { PrepJobs* d_prep; WgradItems* d_wg; NetImages im; int64_t bytes; };
+
+static void plan_single(const MlpShape& sh, bool is_atlas, int64_t rows, char* base, SinglePlan* out) {
+  char* p = reinterpret_cast<char*>(round_up(reinterpret_cast<int64_t>(base), 1024));
+  out->d_prep = reinterpret_cast<PrepJobs*>(carve_tc(p, sizeof(PrepJobs)));
+  out->d_wg = reinterpret_cast<WgradItems*>(carve_tc(p, sizeof(WgradItems)));
+  plan_net(sh, rows, is_atlas, p, &out->im);
+  out->bytes = p - base;
+}
+
+int64_t tc_single_workspace_bytes(const MlpShape& sh, bool is_atlas, int64_t rows) {
+  SinglePlan pl;
+  plan_single(sh, is_atlas, rows, nullptr, &pl);
+  return pl.bytes + 2048;
+}
+
+static int check_single(const MlpShape& sh, bool is_atlas, int64_t rows, cudaStream_t st) {
+  B200_PROPAGATE(ensure_attrs());
+  if (is_atlas) B200_REQUIRE(sh.L == 8 && sh.skip[4] && sh.skip[7] && sh.pe == 10 && sh.hidden == HID && sh.in_dim == 2 &&
+                             sh.out_dim == 3, "tensor-core IMLP: not the atlas architecture");
+  else B200_REQUIRE(sh.L == 6 && sh.pe == 0 && sh.hidden == HID && sh.in_dim == 3 && sh.out_dim == 2 && !sh.skip[1] &&
+                    !sh.skip[2] && !sh.skip[3] && !sh.skip[4] && !sh.skip[5], "tensor-core IMLP: not the mapping architecture");
+  B200_REQUIRE(rows > 0 && rows % TM == 0 && rows / TM < (1 << 20), "rows must be a positive multiple of %d", TM);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  B200_REQUIRE(cs != cudaStreamCaptureStatusActive, "the stand-alone tensor-core IMLP calls are not graph-capturable");
+  return B200_OK;
+}
+
+// x: mapping [rows][4], atlas [rows][2] (network input itself).  y: [rows][out_dim].
+int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, const float* x, float* y, int64_t rows,
+                      bool training, char* ws, cudaStream_t st) {
+  B200_PROPAGATE(check_single(sh, is_atlas, rows, st));
+  SinglePlan pl;
+  plan_single(sh, is_atlas, rows, ws, &pl);
+  static thread_local PrepJobs pj;
+  pj.n = 0;
+  prep_jobs_for_net(pj, sh, pl.im, params, is_atlas, training);
+  B200_CHECK_CUDA(cudaMemcpyAsync(pl.d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
+  tc_prep_kernel<<<pj.n * 4, 128, 0, st>>>(pl.d_prep);
+  B200_CHECK_LAUNCH();
+  FwdParams P{};
+  fill_fwd(P, sh, pl.im, x, y, params, (int)rows, 1, nullptr);
+  P.in_scale = 1.0f; P.in_shift = 0.0f; P.store_images = training ? 1 : 0; P.tanh_out = sh.tanh_out ? 1 : 0;
+  const int grid = min(sm_count(), (int)(rows / TM));
+  if (is_atlas) tc_fwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  else tc_fwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+// after tc_single_forward(training) on the same workspace.  y: the saved outputs, dy [rows][out_dim] (zero in padding
+// rows), gmax: device int holding the bits of max|dy| (>= 0), d_in: atlas only, [rows][2] or null.
+int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, float* grads, const float* x,
+                       const float* y, const float* dy, float* d_in, int* gmax2, int64_t rows, char* ws,
+                       cudaStream_t st) {
+  B200_PROPAGATE(check_single(sh, is_atlas, rows, st));
+  SinglePlan pl;
+  plan_single(sh, is_atlas, rows, ws, &pl);
+  static thread_local WgradItems wi;
+  wi.n = 0;
+  WgProto protos[16]; int np = 0;
+  protos_for_net(protos, np, sh, pl.im, grads, is_atlas, 1);
+  apportion_items(wi, protos, np, (int)rows, 0);
+  B200_CHECK_CUDA(cudaMemcpyAsync(pl.d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice, st));
+  BwdParams P{};
+  P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = pl.im;
+  P.cap = (int)rows; P.n_groups = 1; P.n_valid = nullptr; P.gmax_bits = gmax2;      // [0] atlas scale, [1] mapping scale
+  P.in_scale = 1.0f; P.d_in_accumulate = 0; P.tanh_out = sh.tanh_out ? 1 : 0; P.flow_groups = 0;
+  for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
+  const int grid = min(sm_count(), (int)(rows / TM));
+  if (is_atlas) tc_bwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  else tc_bwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
+  B200_CHECK_LAUNCH();
+  tc_wgrad_kernel<<<wi.n, WG_THREADS, WG_SMEM, st>>>(pl.d_wg, nullptr, gmax2);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -38,4 +38,11 @@ int64_t tc_infer_workspace_bytes(const MlpShape& ms, const MlpShape& as);
 int tc_infer_forward(const MlpShape& ms, const MlpShape& as, const float* params, const float* x_map, float* uv,
                      float* y, int64_t rows, char* ws, cudaStream_t st);
 
+// stand-alone IMLP (one network, autograd): see mlp_tc.cu
+int64_t tc_single_workspace_bytes(const MlpShape& sh, bool is_atlas, int64_t rows);
+int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, const float* x, float* y, int64_t rows,
+                      bool training, char* ws, cudaStream_t st);
+int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, float* grads, const float* x,
+                       const float* y, const float* dy, float* d_in, int* gmax2, int64_t rows, char* ws, cudaStream_t st);
+
 }  // namespace b200

@@ -34,10 +34,11 @@ class _ImlpFunction(torch.autograd.Function):
         nbytes = int(lib.b200_mlp_workspace_bytes(C.byref(desc), rows, 1)) + rows * enc * 4 + 512
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         y = torch.empty(rows, desc.output_dim, dtype=torch.float32, device=x.device)
-        N.check(lib.b200_mlp_forward(C.byref(desc), N.ptr(flat), N.ptr(x), N.ptr(y), rows, 1, N.PREC_FP32, N.ptr(ws),
+        prec = module._precision(ctx.needs_input_grad[0])
+        N.check(lib.b200_mlp_forward(C.byref(desc), N.ptr(flat), N.ptr(x), N.ptr(y), rows, 1, prec, N.ptr(ws),
                                      ws.numel(), N.current_stream()), "b200_mlp_forward")
         ctx.save_for_backward(x, flat)
-        ctx.ws, ctx.module = ws, module
+        ctx.ws, ctx.module, ctx.prec = ws, module, prec
         return y
 
     @staticmethod
@@ -48,7 +49,7 @@ class _ImlpFunction(torch.autograd.Function):
         dflat = torch.zeros_like(flat)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         N.check(lib.b200_mlp_backward(C.byref(desc), N.ptr(flat), N.ptr(x), N.ptr(dy.contiguous().float()),
-                                      N.ptr(dflat), N.ptr(dx), x.shape[0], N.PREC_FP32, N.ptr(ctx.ws),
+                                      N.ptr(dflat), N.ptr(dx), x.shape[0], ctx.prec, N.ptr(ctx.ws),
                                       ctx.ws.numel(), N.current_stream()), "b200_mlp_backward")
         return dx, dflat, None
 
@@ -60,6 +61,15 @@ class IMLP(nn.Module):
         if apply_softmax:
             raise NotImplementedError("apply_softmax is unused by the stage-1 scripts and not provided")
         self.verbose, self.use_tanh = verbose, use_tanh
+        # The two architectures of the stage-1 scripts (src/stage1_neural_atlas.py:112-128) have tcgen05 kernels:
+        # 1 = mapping (3 -> 256 x 4 -> 2, no encoding), 2 = atlas (2 -> PE 10 -> 256 x 6 -> 3, skips 4 and 7)
+        self._tc_arch = 0
+        if hidden_dim == 256 and not use_positional and input_dim == 3 and output_dim == 2 and num_layers == 6 \
+                and not [k for k in skip_layers if 0 < k < num_layers]:
+            self._tc_arch = 1
+        if hidden_dim == 256 and use_positional and positional_dim == 10 and input_dim == 2 and output_dim == 3 \
+                and num_layers == 8 and sorted(k for k in skip_layers if 0 < k < num_layers) == [4, 7]:
+            self._tc_arch = 2
         self.skip_layers, self.num_layers = list(skip_layers), num_layers
         self.positional_dim, self.use_positional = positional_dim, use_positional
         self._desc = A.make_desc(input_dim, output_dim, hidden_dim, num_layers,
@@ -93,6 +103,17 @@ class IMLP(nn.Module):
                     v.copy_(sd[k])
                 elif strict:
                     raise KeyError(k)
+
+    def _precision(self, input_needs_grad: bool) -> int:
+        """Tensor cores (B200_PREC_TC: 2-term fp16 operands, fp32 accumulation — DESIGN.md §3) whenever the
+        architecture has the fused kernels and the device is sm_100; `B200_IMLP_PRECISION=fp32|tc` overrides.  The
+        mapping kernels produce no input gradient (their inputs are pixel coordinates)."""
+        import os
+        want = os.environ.get("B200_IMLP_PRECISION", "auto")
+        ok = self._tc_arch != 0 and bool(N.lib().b200_device_supports_tc()) and not (self._tc_arch == 1 and input_needs_grad)
+        if want == "tc" and not ok:
+            raise N.B200Error("B200_IMLP_PRECISION=tc: this IMLP has no tensor-core kernels on this device / call")
+        return N.PREC_TC if (ok and want != "fp32") else N.PREC_FP32
 
     def forward(self, x):
         return _ImlpFunction.apply(x, self.flat, self)

@@ -19,6 +19,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _fp32_imlp(monkeypatch):
+    """These tests pin the loss-head arithmetic with tight bounds: run the IMLP objects on the fp32 CUDA-core kernels
+    (the tensor-core IMLP has its own test, tests/test_tc_gpu.py::test_imlp_class_on_tensor_cores)."""
+    monkeypatch.setenv("B200_IMLP_PRECISION", "fp32")
+
+
 def _nets(golden_dir):
     from src.models.stage_1.implicit_neural_networks import IMLP
     z = np.load(os.path.join(golden_dir, "params_seed1234.npz"))

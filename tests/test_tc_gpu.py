@@ -174,3 +174,47 @@ def test_tc_render_parity(golden_dir):
     diff = np.abs(u8.cpu().numpy().astype(int) - O.to_uint8(ref).astype(int))
     assert diff.max() <= 1 and (diff != 0).mean() < 0.01
     assert abs(A.psnr(data["frames"][:, :, :, 2], img.cpu()) - O.psnr(data["frames"][:, :, :, 2], ref)) < 1e-3
+
+
+@pytest.mark.parametrize("which", ["mapping", "atlas"])
+def test_imlp_class_on_tensor_cores(golden_dir, which, monkeypatch):
+    """The drop-in `IMLP` class (b200_mlp_forward / b200_mlp_backward with B200_PREC_TC) against the oracle network
+    with the same parameters: forward |err| <= 5e-6 (mapping) / 5e-5 (atlas, positional-encoding amplification),
+    parameter gradients of a random linear functional against FLOAT64: ||err||_F <= 3e-3 ||g||_F per tensor, input
+    gradient of the atlas 3e-3 likewise.  rows = 1000: a ragged last tile."""
+    _need_tc()
+    monkeypatch.setenv("B200_IMLP_PRECISION", "tc")
+    from src.models.stage_1.implicit_neural_networks import IMLP
+    mp, ap = _params(golden_dir)
+    if which == "mapping":
+        net = IMLP(input_dim=3, output_dim=2, hidden_dim=256, use_positional=False, positional_dim=4, num_layers=6,
+                   skip_layers=[], verbose=False)
+        spec, params, scale, tol = O.MAPPING_SPEC, mp, 2.0, 5e-6
+    else:
+        net = IMLP(input_dim=2, output_dim=3, hidden_dim=256, use_positional=True, positional_dim=10, num_layers=8,
+                   skip_layers=[4, 7], verbose=False)
+        spec, params, scale, tol = O.ATLAS_SPEC, ap, 1.0, 5e-5
+    assert net._tc_arch == (1 if which == "mapping" else 2)
+    net.load_state_dict(O.state_dict_of(params))
+    net = net.to(DEV)
+    g = torch.Generator().manual_seed(4)
+    rows = 1000
+    x = torch.rand(rows, spec.input_dim, generator=g) * scale - (scale - 1.0)
+    w = torch.randn(rows, spec.output_dim, generator=g)
+    xd = x.to(DEV).requires_grad_(which == "atlas")
+    y = net(xd)
+    with torch.no_grad():
+        y_ref = O.mlp_forward(spec, params, x)
+    assert (y.detach().cpu() - y_ref).abs().max() <= tol
+    (y * w.to(DEV)).sum().backward()
+    p64 = [p.double().requires_grad_(True) for p in params]
+    x64 = x.double().requires_grad_(True)
+    (O.mlp_forward(spec, p64, x64) * w.double()).sum().backward()
+    views = net._views(net.flat.grad)
+    for i in range(len(params) // 2):
+        for kind, t in (("weight", p64[2 * i]), ("bias", p64[2 * i + 1])):
+            e = (views[f"hidden.{i}.{kind}"].cpu().double() - t.grad).norm() / t.grad.norm()
+            assert float(e) <= 3e-3, (which, i, kind, float(e))
+    if which == "atlas":
+        e = (xd.grad.cpu().double() - x64.grad).norm() / x64.grad.norm()
+        assert float(e) <= 3e-3, float(e)
