@@ -963,7 +963,7 @@ struct WgradItem {
   int mapping;            // 1: gradients of the mapping network (second gradient scale)
   int flow_groups;        // row geometry: compacted flow-match groups (mapping batch of the loop)
 };
-constexpr int MAX_WGRAD_ITEMS = 320;
+constexpr int MAX_WGRAD_ITEMS = 768;
 struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; };
 
 constexpr int WG_STAGE = 65536;          // 32 rows: A hi 16K | A lo 16K | B hi 16K | B lo 16K, each [atom][4 groups][1 KB]
@@ -971,6 +971,12 @@ constexpr int WG_NSTAGE = 3;
 constexpr int WG_SMEM = WG_NSTAGE * WG_STAGE + 256;
 constexpr int WG_THREADS = 192;
 
+// Work units ("items" = one dW GEMM restricted to a share of the rows) are several times more numerous than CTAs and are
+// dealt round-robin: CTA b processes items b, b + grid, b + 2 grid, ...  The list is ordered by GEMM, every GEMM is cut
+// into units of equal bytes, so all CTAs receive the same mix of wide and narrow units and finish together whatever the
+// relative cost of a narrow unit is (a single static share per CTA left the average SM idle 43 % of the kernel:
+// profiles/r2_tc_v3_ncu_summary.md).  The operand ring runs across units; the accumulator is flushed (vector atomics)
+// after every unit.
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_valid, const int* __restrict__ gmax_bits) {
   extern __shared__ __align__(1024) char smem_raw[];
@@ -979,12 +985,14 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
   uint64_t* full = reinterpret_cast<uint64_t*>(p + WG_NSTAGE * WG_STAGE);
   uint64_t* empty = full + WG_NSTAGE;
   uint64_t* d_ready = empty + WG_NSTAGE;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + 1);
+  uint64_t* d_free = d_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     if (smem_u32(stage) & 1023u) { printf("b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < WG_NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(d_ready, 1);
+    mbar_init(d_free, WG_THREADS - 64);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -992,94 +1000,121 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const WgradItem W = items->it[blockIdx.x];
-  TileIter ti; ti.init(W.cap, W.n_groups, n_valid, W.flow_groups);
-  const int t_begin = (int)((int64_t)ti.total * W.split / W.n_split);
-  const int t_end = (int)((int64_t)ti.total * (W.split + 1) / W.n_split);
-  const int a_atoms = W.a_cols / 64, b_atoms = W.b_cols / 64;
-  const int n_steps = (t_end - t_begin) * 4;     // 32-row steps
+  const int n_items = items->n;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < n_steps; ++s) {
-        const int slot = s % WG_NSTAGE;
-        mbar_wait(&empty[slot], ((s / WG_NSTAGE) & 1) ^ 1);
-        const int gt = ti.global_tile(t_begin + (s >> 2));
-        const int ch = s & 3;                      // 32-row chunk = groups 4ch .. 4ch+3 of every atom block
-        char* dst = stage + slot * WG_STAGE;
-        mbar_expect_tx(&full[slot], 2 * 4096 * (a_atoms + b_atoms));
-        const char* a = W.a_img + (int64_t)gt * a_atoms * ATOM_BYTES + ch * 4096;
-        for (int j = 0; j < a_atoms; ++j) {
-          bulk_g2s(dst + j * 4096, a + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
-          bulk_g2s(dst + 16384 + j * 4096, a + W.a_term + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
-        }
-        const char* b = W.b_img + (int64_t)gt * b_atoms * ATOM_BYTES + ch * 4096;
-        for (int j = 0; j < b_atoms; ++j) {
-          bulk_g2s(dst + 32768 + j * 4096, b + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
-          bulk_g2s(dst + 49152 + j * 4096, b + W.b_term + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+      uint32_t gs = 0;                                  // running stage counter across units
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WgradItem W = items->it[it];
+        TileIter ti; ti.init(W.cap, W.n_groups, n_valid, W.flow_groups);
+        const int t_begin = (int)((int64_t)ti.total * W.split / W.n_split);
+        const int t_end = (int)((int64_t)ti.total * (W.split + 1) / W.n_split);
+        const int a_atoms = W.a_cols / 64, b_atoms = W.b_cols / 64;
+        const int n_steps = (t_end - t_begin) * 4;     // 32-row steps
+        for (int s = 0; s < n_steps; ++s, ++gs) {
+          const int slot = gs % WG_NSTAGE;
+          mbar_wait(&empty[slot], ((gs / WG_NSTAGE) & 1) ^ 1);
+          const int gt = ti.global_tile(t_begin + (s >> 2));
+          const int ch = s & 3;                        // 32-row chunk = groups 4ch .. 4ch+3 of every atom block
+          char* dst = stage + slot * WG_STAGE;
+          mbar_expect_tx(&full[slot], 2 * 4096 * (a_atoms + b_atoms));
+          const char* a = W.a_img + (int64_t)gt * a_atoms * ATOM_BYTES + ch * 4096;
+          for (int j = 0; j < a_atoms; ++j) {
+            bulk_g2s(dst + j * 4096, a + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+            bulk_g2s(dst + 16384 + j * 4096, a + W.a_term + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+          }
+          const char* b = W.b_img + (int64_t)gt * b_atoms * ATOM_BYTES + ch * 4096;
+          for (int j = 0; j < b_atoms; ++j) {
+            bulk_g2s(dst + 32768 + j * 4096, b + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+            bulk_g2s(dst + 49152 + j * 4096, b + W.b_term + (int64_t)j * ATOM_BYTES, 4096, &full[slot]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // smem operand: [atom][4 groups][1 KB] -> MN-major SW128: LBO (atom stride) 4096, SBO (8-row group) 1024
-      const int m_inst = W.a_cols == 256 ? 128 : 64;
-      const uint32_t idesc = make_idesc(m_inst, W.b_cols, 1, 1);
-      const int m_halves = W.a_cols == 256 ? 2 : 1;
-      for (int s = 0; s < n_steps; ++s) {
-        const int slot = s % WG_NSTAGE;
-        mbar_wait(&full[slot], (s / WG_NSTAGE) & 1);
-        tc_fence_after();
-        const uint32_t sb = smem_u32(stage + slot * WG_STAGE);
+      uint32_t gs = 0, unit = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WgradItem W = items->it[it];
+        TileIter ti; ti.init(W.cap, W.n_groups, n_valid, W.flow_groups);
+        const int t_begin = (int)((int64_t)ti.total * W.split / W.n_split);
+        const int t_end = (int)((int64_t)ti.total * (W.split + 1) / W.n_split);
+        const int n_steps = (t_end - t_begin) * 4;
+        if (n_steps == 0) continue;
+        // smem operand: [atom][4 groups][1 KB] -> MN-major SW128: LBO (atom stride) 4096, SBO (8-row group) 1024
+        const int m_inst = W.a_cols == 256 ? 128 : 64;
+        const uint32_t idesc = make_idesc(m_inst, W.b_cols, 1, 1);
+        const int m_halves = W.a_cols == 256 ? 2 : 1;
+        if (unit > 0) { mbar_wait(d_free, (unit - 1) & 1); tc_fence_after(); }   // previous accumulator flushed
+        for (int s = 0; s < n_steps; ++s, ++gs) {
+          const int slot = gs % WG_NSTAGE;
+          mbar_wait(&full[slot], (gs / WG_NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(stage + slot * WG_STAGE);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {             // 16 rows = 2 groups per MMA
-          for (int mh = 0; mh < m_halves; ++mh) {
-            const uint32_t acc = (s | ks) ? 1u : 0u;
-            const uint32_t d = tmem + mh * W.b_cols;
-            const uint64_t a_hi = make_desc(sb + ks * 2048 + mh * 8192, 4096, 1024);
-            const uint64_t a_lo = make_desc(sb + 16384 + ks * 2048 + mh * 8192, 4096, 1024);
-            const uint64_t b_hi = make_desc(sb + 32768 + ks * 2048, 4096, 1024);
-            const uint64_t b_lo = make_desc(sb + 49152 + ks * 2048, 4096, 1024);
-            mma_ss(d, a_hi, b_hi, idesc, acc);
-            mma_ss(d, a_hi, b_lo, idesc, 1u);
-            mma_ss(d, a_lo, b_hi, idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {             // 16 rows = 2 groups per MMA
+            for (int mh = 0; mh < m_halves; ++mh) {
+              const uint32_t acc = (s | ks) ? 1u : 0u;
+              const uint32_t d = tmem + mh * W.b_cols;
+              const uint64_t a_hi = make_desc(sb + ks * 2048 + mh * 8192, 4096, 1024);
+              const uint64_t a_lo = make_desc(sb + 16384 + ks * 2048 + mh * 8192, 4096, 1024);
+              const uint64_t b_hi = make_desc(sb + 32768 + ks * 2048, 4096, 1024);
+              const uint64_t b_lo = make_desc(sb + 49152 + ks * 2048, 4096, 1024);
+              mma_ss(d, a_hi, b_hi, idesc, acc);
+              mma_ss(d, a_hi, b_lo, idesc, 1u);
+              mma_ss(d, a_lo, b_hi, idesc, 1u);
+            }
           }
+          mma_commit(&empty[slot]);
         }
-        mma_commit(&empty[slot]);
+        mma_commit(d_ready);
+        ++unit;
       }
-      mma_commit(d_ready);
     }
-  } else if (n_steps > 0) {
-    float s_g, inv_sg;
-    grad_scales(gmax_bits, W.mapping != 0, s_g, inv_sg);
-    const float inv = inv_sg * (1.0f / S_ACT);
+  } else {
+    float s_gm, inv_gm, s_ga, inv_ga;
+    grad_scales(gmax_bits, true, s_gm, inv_gm);
+    grad_scales(gmax_bits, false, s_ga, inv_ga);
     const int q = warp & 3;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    mbar_wait(d_ready, 0);
-    tc_fence_after();
-    const int m_halves = W.a_cols == 256 ? 2 : 1;
-    for (int mh = 0; mh < m_halves; ++mh) {
-      // M=128: accumulator row i of half mh lives in TMEM lane i.  M=64: rows 0..15 in lanes 0..15 of quadrant 0.
-      const int n = mh * 128 + q * 32 + lane;              // layer output index of this thread's accumulator row
-      const bool live = W.a_cols == 256 ? true : (q == 0 && lane < W.n_rows);
-      float* orow = W.out + (int64_t)n * W.ld_out;
-      for (int c = 0; c < W.b_cols / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tlane + mh * W.b_cols + c * 32, raw);
-        tmem_ld_wait();
-        if (!live) continue;
-        if (((W.ld_out & 3) == 0) && c * 32 + 32 <= W.n_cols) {
+    uint32_t unit = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WgradItem W = items->it[it];
+      TileIter ti; ti.init(W.cap, W.n_groups, n_valid, W.flow_groups);
+      const int t_begin = (int)((int64_t)ti.total * W.split / W.n_split);
+      const int t_end = (int)((int64_t)ti.total * (W.split + 1) / W.n_split);
+      if (t_end == t_begin) continue;
+      const float inv = (W.mapping ? inv_gm : inv_ga) * (1.0f / S_ACT);
+      mbar_wait(d_ready, unit & 1);
+      tc_fence_after();
+      const int m_halves = W.a_cols == 256 ? 2 : 1;
+      for (int mh = 0; mh < m_halves; ++mh) {
+        // M=128: accumulator row i of half mh lives in TMEM lane i.  M=64: rows 0..15 in lanes 0..15 of quadrant 0.
+        const int n = mh * 128 + q * 32 + lane;              // layer output index of this thread's accumulator row
+        const bool live = W.a_cols == 256 ? true : (q == 0 && lane < W.n_rows);
+        float* orow = W.out + (int64_t)n * W.ld_out;
+        for (int c = 0; c < W.b_cols / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tlane + mh * W.b_cols + c * 32, raw);
+          tmem_ld_wait();
+          if (!live) continue;
+          if (((W.ld_out & 3) == 0) && c * 32 + 32 <= W.n_cols) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + i),
-                      make_float4(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv,
-                                  __uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv));
-        } else {
+            for (int i = 0; i < 32; i += 4)
+              atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + i),
+                        make_float4(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv,
+                                    __uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv));
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < W.n_cols) atomicAdd(orow + c * 32 + i, __uint_as_float(raw[i]) * inv);
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < W.n_cols) atomicAdd(orow + c * 32 + i, __uint_as_float(raw[i]) * inv);
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(d_free);                                   // the MMA warp may overwrite the accumulator
+      ++unit;
     }
   }
   tc_fence_before();
@@ -1205,11 +1240,13 @@ static void protos_for_net(WgProto* protos, int& np, const MlpShape& sh, const N
   }
 }
 
-// exactly one CTA per SM (each CTA owns all 512 TMEM columns): largest-remainder apportionment of the SMs
+// One CTA per SM (each CTA owns all 512 TMEM columns); the GEMMs are cut into WG_UNITS_PER_CTA x SMs units of equal
+// bytes (largest-remainder apportionment) that the CTAs take round-robin (see tc_wgrad_kernel).
+constexpr int WG_UNITS_PER_CTA = 4;
 static void apportion_items(WgradItems& wi, const WgProto* protos, int np, int cap, int flow_groups) {
   double total_bytes = 0;
   for (int i = 0; i < np; ++i) total_bytes += protos[i].bytes;
-  const int sms = sm_count();
+  const int sms = sm_count() * WG_UNITS_PER_CTA;
   int n_split[32], used = 0;
   double frac[32];
   for (int i = 0; i < np; ++i) {
@@ -1376,7 +1413,7 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   timer_end(TAG_MAP_BWD, st);
   B200_CHECK_LAUNCH();
   timer_begin(TAG_WGRAD, st);
-  tc_wgrad_kernel<<<tab->n_wg, WG_THREADS, WG_SMEM, st>>>(tab->d_wg, s.counters, gmax);
+  tc_wgrad_kernel<<<min(tab->n_wg, sm_count()), WG_THREADS, WG_SMEM, st>>>(tab->d_wg, s.counters, gmax);
   timer_end(TAG_WGRAD, st);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -1533,7 +1570,7 @@ int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, f
   if (is_atlas) tc_bwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
   else tc_bwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   B200_CHECK_LAUNCH();
-  tc_wgrad_kernel<<<wi.n, WG_THREADS, WG_SMEM, st>>>(pl.d_wg, nullptr, gmax2);
+  tc_wgrad_kernel<<<min(wi.n, sm_count()), WG_THREADS, WG_SMEM, st>>>(pl.d_wg, nullptr, gmax2);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
