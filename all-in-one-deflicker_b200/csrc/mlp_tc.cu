@@ -971,12 +971,9 @@ constexpr int WG_NSTAGE = 3;
 constexpr int WG_SMEM = WG_NSTAGE * WG_STAGE + 256;
 constexpr int WG_THREADS = 192;
 
-// Work units ("items" = one dW GEMM restricted to a share of the rows) are several times more numerous than CTAs and are
-// dealt round-robin: CTA b processes items b, b + grid, b + 2 grid, ...  The list is ordered by GEMM, every GEMM is cut
-// into units of equal bytes, so all CTAs receive the same mix of wide and narrow units and finish together whatever the
-// relative cost of a narrow unit is (a single static share per CTA left the average SM idle 43 % of the kernel:
-// profiles/r2_tc_v3_ncu_summary.md).  The operand ring runs across units; the accumulator is flushed (vector atomics)
-// after every unit.
+// Work units ("items" = one dW GEMM restricted to a share of the rows) are dealt round-robin: CTA b processes items b,
+// b + grid, b + 2 grid, ... (WG_UNITS_PER_CTA of them; the host builds the list).  The operand ring runs across units; the
+// accumulator is flushed (vector atomics) after every unit.
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_valid, const int* __restrict__ gmax_bits) {
   extern __shared__ __align__(1024) char smem_raw[];
@@ -1214,7 +1211,10 @@ static void prep_jobs_for_net(PrepJobs& pj, const MlpShape& sh, const NetImages&
 }
 
 // wgrad work list.  The kernel is HBM-bound: CTAs are balanced by bytes read per tile
-// (A + B, both terms): 256x256 -> 256 KB, 256x64 -> 160 KB, 64x256 -> 160 KB, 64x64 -> 64 KB
+// (A + B, both terms): 256x256 -> 256 KB, 256x64 -> 160 KB, 64x256 -> 160 KB, and 64x64 is ALSO costed at 160 KB:
+// a 32-row step never takes less than the ~1 k cycles of its mbarrier round trips, whatever it loads (with the
+// plain 64 KB figure the two CTAs of the output-layer skip GEMM ran 1.6x longer than everyone else and the
+// average SM idled 43 % of the kernel: profiles/README.md)
 struct WgProto { const char* a; int64_t a_term; int a_cols; const char* b; int64_t b_term; int b_cols;
                  float* out; int ld; int n_rows, n_cols, groups; double bytes; int mapping; };
 
@@ -1223,7 +1223,7 @@ static void protos_for_net(WgProto* protos, int& np, const MlpShape& sh, const N
   auto add = [&](const char* a, int64_t a_term, int a_cols, const char* b, int64_t b_term, int b_cols, float* out, int ld,
                  int n_rows, int n_cols) {
     protos[np++] = WgProto{a, a_term, a_cols, b, b_term, b_cols, out, ld, n_rows, n_cols, groups,
-                           (double)groups * (a_cols + b_cols) * 512.0, is_atlas ? 0 : 1};
+                           (double)groups * (a_cols + b_cols < 320 ? 320 : a_cols + b_cols) * 512.0, is_atlas ? 0 : 1};
   };
   for (int l = 1; l <= sh.L - 2; ++l)
     add(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.act + (int64_t)(l - 1) * im.slot_stride,
@@ -1241,8 +1241,10 @@ static void protos_for_net(WgProto* protos, int& np, const MlpShape& sh, const N
 }
 
 // One CTA per SM (each CTA owns all 512 TMEM columns); the GEMMs are cut into WG_UNITS_PER_CTA x SMs units of equal
-// bytes (largest-remainder apportionment) that the CTAs take round-robin (see tc_wgrad_kernel).
-constexpr int WG_UNITS_PER_CTA = 4;
+// cost (largest-remainder apportionment) that the CTAs take round-robin (see tc_wgrad_kernel).  More than one unit
+// per CTA balances any cost-model error but multiplies the accumulator flushes (64 K fp32 vector atomics each): 4 units
+// per CTA cost as much in L2 atomics as they gained in balance (measured), so the default is 1.
+constexpr int WG_UNITS_PER_CTA = 1;
 static void apportion_items(WgradItems& wi, const WgProto* protos, int np, int cap, int flow_groups) {
   double total_bytes = 0;
   for (int i = 0; i < np; ++i) total_bytes += protos[i].bytes;
