@@ -74,6 +74,7 @@ SIGNATURES = {
     "b200_version": (C.c_int, []),
     "b200_device_supports_tc": (C.c_int, []),
     "b200_launch_count": (C.c_longlong, []),
+    "b200_debug_wgrad": (C.c_int, [_P, _P, _I32]),
     "b200_set_kernel_timer": (C.c_int, [_P, _P, C.c_int]),
     "b200_mlp_layout": (_I64, [C.POINTER(MlpDesc), C.POINTER(_I64), C.POINTER(_I64)]),
     "b200_mlp_workspace_bytes": (_I64, [C.POINTER(MlpDesc), _I64, C.c_int]),

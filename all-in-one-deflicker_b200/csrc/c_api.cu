@@ -502,6 +502,10 @@ int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                      reinterpret_cast<cudaStream_t>(stream));
 }
 
+int b200_debug_wgrad(long long* cycles_host, int32_t* shapes_host, int32_t max_ctas) {
+  return tc_debug_wgrad(cycles_host, shapes_host, max_ctas);
+}
+
 int b200_dp_slice(int32_t world, int32_t rank, int64_t n_total, int64_t* begin, int64_t* count) {
   B200_REQUIRE(world >= 1 && world <= B200_MAX_RANKS && rank >= 0 && rank < world && n_total > 0 && begin && count,
                "bad slice request");

@@ -964,7 +964,7 @@ struct WgradItem {
   int flow_groups;        // row geometry: compacted flow-match groups (mapping batch of the loop)
 };
 constexpr int MAX_WGRAD_ITEMS = 768;
-struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; };
+struct WgradItems { WgradItem it[MAX_WGRAD_ITEMS]; int n; long long cycles[256]; };   // cycles: per-CTA duration (diagnostics)
 
 constexpr int WG_STAGE = 65536;          // 32 rows: A hi 16K | A lo 16K | B hi 16K | B lo 16K, each [atom][4 groups][1 KB]
 constexpr int WG_NSTAGE = 3;
@@ -998,6 +998,7 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_items = items->n;
+  const long long t_start = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1116,6 +1117,7 @@ tc_wgrad_kernel(const WgradItems* __restrict__ items, const int* __restrict__ n_
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 256) const_cast<WgradItems*>(items)->cycles[blockIdx.x] = clock64() - t_start;
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -1386,6 +1388,22 @@ static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   return B200_OK;
 }
 
+static const WgradItems* g_last_wg = nullptr;
+static int g_last_wg_n = 0;
+
+// diagnostics: per-CTA cycle counts and (a_cols, b_cols, n_split) of the item each CTA ran in the last weight-gradient launch
+int tc_debug_wgrad(long long* cycles, int* shapes, int max_ctas) {
+  if (!g_last_wg) { set_error("no weight-gradient launch yet"); return -1; }
+  static WgradItems host;
+  if (cudaMemcpy(&host, g_last_wg, sizeof(WgradItems), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  const int n = g_last_wg_n < max_ctas ? g_last_wg_n : max_ctas;
+  for (int i = 0; i < n; ++i) {
+    cycles[i] = host.cycles[i];
+    shapes[3 * i] = host.it[i].a_cols; shapes[3 * i + 1] = host.it[i].b_cols; shapes[3 * i + 2] = host.it[i].n_split;
+  }
+  return n;
+}
+
 static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   const TcLayout lay = layout_of(s);
   HostTables* tab = find_tables(s);
@@ -1415,6 +1433,7 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   timer_end(TAG_MAP_BWD, st);
   B200_CHECK_LAUNCH();
   timer_begin(TAG_WGRAD, st);
+  g_last_wg = tab->d_wg; g_last_wg_n = min(tab->n_wg, sm_count());
   tc_wgrad_kernel<<<min(tab->n_wg, sm_count()), WG_THREADS, WG_SMEM, st>>>(tab->d_wg, s.counters, gmax);
   timer_end(TAG_WGRAD, st);
   B200_CHECK_LAUNCH();

@@ -45,4 +45,6 @@ int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, co
 int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, float* grads, const float* x,
                        const float* y, const float* dy, float* d_in, int* gmax2, int64_t rows, char* ws, cudaStream_t st);
 
+int tc_debug_wgrad(long long* cycles, int* shapes, int max_ctas);
+
 }  // namespace b200

@@ -60,6 +60,10 @@ int b200_device_supports_tc(void);
 #define B200_TAG_WGRAD 5
 #define B200_TAG_ADAM 6
 long long b200_launch_count(void);
+/* Diagnostics: cycles each CTA of the LAST weight-gradient launch of the training step was busy, and the shape
+ * (dZ columns, input columns, number of CTAs sharing the GEMM) of its work item; HOST arrays of max_ctas and
+ * 3 * max_ctas entries; returns the number of CTAs or -1.  Synchronises the device. */
+int b200_debug_wgrad(long long* cycles_host, int32_t* shapes_host, int32_t max_ctas);
 int b200_set_kernel_timer(void* ev_start, void* ev_stop, int tag);
 
 /* ------------------------------------------------------------------------------------------
