@@ -1213,10 +1213,13 @@ static void prep_jobs_for_net(PrepJobs& pj, const MlpShape& sh, const NetImages&
 }
 
 // wgrad work list.  The kernel is HBM-bound: CTAs are balanced by bytes read per tile
-// (A + B, both terms): 256x256 -> 256 KB, 256x64 -> 160 KB, 64x256 -> 160 KB, and 64x64 is ALSO costed at 160 KB:
-// a 32-row step never takes less than the ~1 k cycles of its mbarrier round trips, whatever it loads (with the
-// plain 64 KB figure the two CTAs of the output-layer skip GEMM ran 1.6x longer than everyone else and the
-// average SM idled 43 % of the kernel: profiles/README.md)
+// (A + B, both terms) corrected by the measured cost of narrow steps (step_cost): with plain byte counts the CTAs of
+// the narrow GEMMs ran 1.3 - 1.6x longer than everyone else and the average SM idled 43 % of the kernel
+// measured per-CTA busy time of the kernel at the benchmark shape (tests/perf/wgrad_balance.py), per 32-row step, in units
+// of "image columns loaded": a 256x256 step (512 columns, 64 KB) is HBM-bound; a 320-column step costs 0.81 of it
+// rather than 0.625, a 128-column step 0.66 rather than 0.25 (barrier round trips and M=64 / N=64 MMAs do not shrink)
+static double step_cost(int cols) { return cols >= 512 ? 512.0 : (cols >= 320 ? 416.0 : 340.0); }
+
 struct WgProto { const char* a; int64_t a_term; int a_cols; const char* b; int64_t b_term; int b_cols;
                  float* out; int ld; int n_rows, n_cols, groups; double bytes; int mapping; };
 
@@ -1225,7 +1228,7 @@ static void protos_for_net(WgProto* protos, int& np, const MlpShape& sh, const N
   auto add = [&](const char* a, int64_t a_term, int a_cols, const char* b, int64_t b_term, int b_cols, float* out, int ld,
                  int n_rows, int n_cols) {
     protos[np++] = WgProto{a, a_term, a_cols, b, b_term, b_cols, out, ld, n_rows, n_cols, groups,
-                           (double)groups * (a_cols + b_cols < 320 ? 320 : a_cols + b_cols) * 512.0, is_atlas ? 0 : 1};
+                           (double)groups * step_cost(a_cols + b_cols), is_atlas ? 0 : 1};
   };
   for (int l = 1; l <= sh.L - 2; ++l)
     add(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.act + (int64_t)(l - 1) * im.slot_stride,
