@@ -174,24 +174,21 @@ struct Pipe {                        // weight-image ring shared by producer and
 };
 
 struct TileIter {                    // static round-robin over the live tiles of a group-major batch
-  int t0, tf, tb, total, cap_tiles, n_groups, flow, g0;
+  int t0, tf, tb, total, cap_tiles, n_groups, flow;
   // counters: [0] rows of an ordinary group, [5] / [6] rows of the compacted flow-match groups (G_FWD = 5, G_BWD = 6
   // of the mapping batch when `flow_groups` is set); nullptr: every row of every group is live
-  // the iterator covers the groups [g_begin, g_begin + groups) of the batch
-  __device__ __forceinline__ void init(int cap, int groups, const int* counters, int flow_groups, int g_begin = 0) {
+  __device__ __forceinline__ void init(int cap, int groups, const int* counters, int flow_groups) {
     cap_tiles = cap / TM;
     n_groups = groups;
-    g0 = g_begin;
-    flow = flow_groups ? 1 : 0;
+    flow = (flow_groups && groups > 6) ? 1 : 0;
     t0 = counters ? min(cap_tiles, (counters[0] + TM - 1) / TM) : cap_tiles;
     tf = flow ? min(cap_tiles, (counters[5] + TM - 1) / TM) : t0;
     tb = flow ? min(cap_tiles, (counters[6] + TM - 1) / TM) : t0;
-    total = 0;
-    for (int g = 0; g < groups; ++g) total += group_tiles(g0 + g);
+    total = t0 * (groups - (flow ? 2 : 0)) + (flow ? tf + tb : 0);
   }
   __device__ __forceinline__ int group_tiles(int g) const { return (flow && g == 5) ? tf : ((flow && g == 6) ? tb : t0); }
   __device__ __forceinline__ int global_tile(int t) const {
-    for (int g = g0; g < g0 + n_groups; ++g) {
+    for (int g = 0; g < n_groups; ++g) {
       const int n = group_tiles(g);
       if (t < n) return g * cap_tiles + t;
       t -= n;
@@ -380,7 +377,6 @@ struct FwdParams {
   NetImages img;
   int cap, n_groups; const int* n_valid;
   int flow_groups;           // mapping batch of the loop: groups 5 / 6 are compacted to counters[5] / counters[6] rows
-  int group_begin;           // first row group this launch covers (n_groups of them)
   float in_scale, in_shift;  // atlas: network input = x * in_scale + in_shift (0.5, 0.5 inside the loop: uv -> [0,1])
   int store_images;          // 0: inference (render / IMLP.forward without grad): no activation images, no flags
   int tanh_out;
@@ -419,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   if (threadIdx.x < OUT) s_blast[threadIdx.x] = P.params[P.b_off[L - 1] + threadIdx.x];
   if (!ATLAS) for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[i] = P.params[P.w_off[0] + i] * S_ACT;
   const uint32_t tmem = setup_cta(sm, warp);
-  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid, P.flow_groups, P.group_begin);
+  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid, P.flow_groups);
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
 
   if (warp == 0) {
@@ -646,7 +642,6 @@ struct BwdParams {
   int cap, n_groups; const int* n_valid;
   int* gmax_bits;            // [0] max |dL/dy| from the loss head, [1] max |dL/duv| after the atlas backward
   int flow_groups;
-  int group_begin;
   float in_scale;            // atlas: d(network input)/d(x) (0.5 inside the loop)
   int d_in_accumulate;       // atlas: 1 = d_in already holds the direct loss-head gradient (the loop), 0 = overwrite
   int tanh_out;
@@ -718,7 +713,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
   for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i];
   for (int i = threadIdx.x; i < (L - 1) * 256 + (ATLAS ? 0 : 768); i += blockDim.x) s_bacc[i] = 0.f;
   const uint32_t tmem = setup_cta(sm, warp);
-  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid, P.flow_groups, P.group_begin);
+  TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid, P.flow_groups);
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
   constexpr uint32_t IDESC64 = make_idesc(128, 64, 0, 0);
   float s_g, inv_sg;
@@ -1340,14 +1335,14 @@ static int build_tables(const TcStep& s, const TcLayout& lay, cudaStream_t st, H
 static void fill_fwd(FwdParams& P, const MlpShape& sh, const NetImages& im, const float* x, float* y,
                      const float* params, int cap, int groups, const int* n_valid) {
   P.x = x; P.y = y; P.params = params; P.img = im; P.cap = cap; P.n_groups = groups; P.n_valid = n_valid;
-  P.in_scale = 0.5f; P.in_shift = 0.5f; P.store_images = 1; P.tanh_out = 1; P.flow_groups = 0; P.group_begin = 0;
+  P.in_scale = 0.5f; P.in_shift = 0.5f; P.store_images = 1; P.tanh_out = 1; P.flow_groups = 0;
   for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
 }
 
 // The weight images depend only on the parameters, so their preparation runs on a side stream, forked from the
 // caller's stream before the sampling kernels and joined before the first fused kernel (also under capture: the
 // fork / join become parallel branches of the graph).
-struct SideStream { cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr; bool pending = false; };
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool pending = false; };
 static SideStream g_side[64];
 
 int tc_begin_step(const TcStep& s, cudaStream_t st) {
@@ -1360,9 +1355,6 @@ int tc_begin_step(const TcStep& s, cudaStream_t st) {
     B200_CHECK_CUDA(cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking));
     B200_CHECK_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
     B200_CHECK_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
-    B200_CHECK_CUDA(cudaStreamCreateWithFlags(&sd.stream2, cudaStreamNonBlocking));
-    B200_CHECK_CUDA(cudaEventCreateWithFlags(&sd.fork2, cudaEventDisableTiming));
-    B200_CHECK_CUDA(cudaEventCreateWithFlags(&sd.join2, cudaEventDisableTiming));
   }
   B200_CHECK_CUDA(cudaEventRecord(sd.fork, st));
   B200_CHECK_CUDA(cudaStreamWaitEvent(sd.stream, sd.fork, 0));
@@ -1380,30 +1372,14 @@ static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
   if (!sd.pending) B200_PROPAGATE(tc_begin_step(s, st));     // callers that did not fork earlier
   B200_CHECK_CUDA(cudaStreamWaitEvent(st, sd.join, 0));
   sd.pending = false;
+  const int tiles_map = s.n_groups * (s.cap / TM);
   FwdParams pm{};
   fill_fwd(pm, *s.ms, lay.map, s.x_map, s.uv, s.params, s.cap, s.n_groups, s.counters);
   pm.flow_groups = s.flow_groups;
-  if (with_atlas && s.n_groups > 3) {
-    // The atlas needs the mapping output of groups 0-2 only.  Groups 3.. run on a second branch, concurrently with
-    // the atlas forward: its 235 tiles leave 61 SMs idle for half of its run time, which this branch fills.
-    B200_CHECK_CUDA(cudaEventRecord(sd.fork2, st));
-    B200_CHECK_CUDA(cudaStreamWaitEvent(sd.stream2, sd.fork2, 0));
-    FwdParams pr = pm;
-    pr.group_begin = 3; pr.n_groups = s.n_groups - 3;
-    timer_begin(TAG_MAP_FWD, sd.stream2);
-    tc_fwd_kernel<false><<<min(sm_count(), pr.n_groups * (s.cap / TM)), TC_THREADS, KCfg<false>::SMEM, sd.stream2>>>(pr);
-    timer_end(TAG_MAP_FWD, sd.stream2);
-    B200_CHECK_LAUNCH();
-    B200_CHECK_CUDA(cudaEventRecord(sd.join2, sd.stream2));
-    pm.n_groups = 3;
-    tc_fwd_kernel<false><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
-    B200_CHECK_LAUNCH();
-  } else {
-    timer_begin(TAG_MAP_FWD, st);
-    tc_fwd_kernel<false><<<min(sm_count(), s.n_groups * (s.cap / TM)), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
-    timer_end(TAG_MAP_FWD, st);
-    B200_CHECK_LAUNCH();
-  }
+  timer_begin(TAG_MAP_FWD, st);
+  tc_fwd_kernel<false><<<min(sm_count(), tiles_map), TC_THREADS, KCfg<false>::SMEM, st>>>(pm);
+  timer_end(TAG_MAP_FWD, st);
+  B200_CHECK_LAUNCH();
   if (with_atlas) {
     FwdParams pa{};
     fill_fwd(pa, *s.as, lay.atl, s.uv, s.y_atlas, s.params + s.ms->total, s.cap, 3, s.counters);
@@ -1411,7 +1387,6 @@ static int run_forward(const TcStep& s, bool with_atlas, cudaStream_t st) {
     tc_fwd_kernel<true><<<min(sm_count(), 3 * (s.cap / TM)), TC_THREADS, KCfg<true>::SMEM, st>>>(pa);
     timer_end(TAG_ATLAS_FWD, st);
     B200_CHECK_LAUNCH();
-    if (s.n_groups > 3) B200_CHECK_CUDA(cudaStreamWaitEvent(st, sd.join2, 0));
   }
   return B200_OK;
 }
@@ -1441,7 +1416,7 @@ static int run_backward(const TcStep& s, bool with_atlas, cudaStream_t st) {
                   const float* x, float* d_in, const float* params, float* grads, int groups) {
     P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = im;
     P.cap = s.cap; P.n_groups = groups; P.n_valid = s.counters; P.gmax_bits = gmax;
-    P.in_scale = 0.5f; P.d_in_accumulate = 1; P.tanh_out = 1; P.flow_groups = 0; P.group_begin = 0;
+    P.in_scale = 0.5f; P.d_in_accumulate = 1; P.tanh_out = 1; P.flow_groups = 0;
     for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
   };
   if (with_atlas) {
@@ -1613,7 +1588,7 @@ int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, f
   BwdParams P{};
   P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = pl.im;
   P.cap = (int)rows; P.n_groups = 1; P.n_valid = nullptr; P.gmax_bits = gmax2;      // [0] atlas scale, [1] mapping scale
-  P.in_scale = 1.0f; P.d_in_accumulate = 0; P.tanh_out = sh.tanh_out ? 1 : 0; P.flow_groups = 0; P.group_begin = 0;
+  P.in_scale = 1.0f; P.d_in_accumulate = 0; P.tanh_out = sh.tanh_out ? 1 : 0; P.flow_groups = 0;
   for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
   const int grid = min(sm_count(), (int)(rows / TM));
   if (is_atlas) tc_bwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);

@@ -55,9 +55,7 @@ def site_flop(site: str, rm: float) -> float:
     """Algorithmic FLOPs of one tagged site: 2 FLOP/MAC x rows x MACs/row; forward, dgrad and wgrad each count
     the full per-row MAC figure of SURVEY.md §8(d)."""
     ra = 3.0 * BATCH
-    # map_fwd: the tagged launch covers the row groups 3.. of the mapping batch (it runs concurrently with the atlas
-    # forward; the groups 0-2 launch that precedes the atlas is not tagged)
-    return {"map_fwd": 2 * (rm - 3.0 * BATCH) * MAC_MAP, "map_bwd": 2 * rm * MAC_MAP, "atlas_fwd": 2 * ra * MAC_ATLAS,
+    return {"map_fwd": 2 * rm * MAC_MAP, "map_bwd": 2 * rm * MAC_MAP, "atlas_fwd": 2 * ra * MAC_ATLAS,
             "atlas_bwd": 2 * ra * MAC_ATLAS, "wgrad": 2 * (rm * MAC_MAP + ra * MAC_ATLAS), "adam": 0.0}[site]
 
 
