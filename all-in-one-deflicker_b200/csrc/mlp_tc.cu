@@ -305,7 +305,7 @@ __device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp)
   if (threadIdx.x == 0) {
     if (smem_u32(sm.stage) & 1023u) { printf("b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < NST; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], EPI_THREADS / 2);   // 2 column slices x 4 quadrants x 32 lanes
+    for (int i = 0; i < 4; ++i) mbar_init(&sm.a_ready[i], EPI_THREADS);       // every epilogue thread owns a piece of every chunk
     mbar_init(sm.x_ready, EPI_THREADS);
     mbar_init(sm.d_ready, 1);
     mbar_init(sm.d_free, EPI_THREADS);
@@ -321,12 +321,12 @@ __device__ __forceinline__ uint32_t setup_cta(SmemMap<NST, ATLAS>& sm, int warp)
 }
 
 // Epilogue thread geometry: 16 warps.  A warp may only touch the TMEM lanes of quadrant (warp_id & 3); the four
-// warps of a quadrant split the 256 accumulator columns into slices j = 0..3, and every warp owns TWO 32-column
-// blocks: columns [32j, 32j+32) ("block 0", inside k chunk j>>1) and [128+32j, 128+32j+32) ("block 1", inside k
-// chunk 2 + (j>>1)).  All block-0 work of a layer finishes half-way through the epilogue, so the k chunks 0, 1 of
-// the next layer's A operand are released to the MMA warp while blocks 1 are still being computed.
+// warps of a quadrant are the column slices j = 0..3, and every warp owns a 16-column piece of EACH of the four
+// 64-column k chunks: columns [64c + 16j, 64c + 16j + 16), c = 0..3.  All 16 warps therefore finish k chunk 0 a quarter
+// of the way through the epilogue, chunk 1 at half, ...: the next layer's A operand is released chunk by chunk in
+// exactly the order the MMA warp consumes it.
 struct EpiThread {
-  int e, q, j, lane, m, tid, pb;    // epilogue warp, TMEM quadrant, column slice, lane, tile row, 0..511, pair buffer
+  int e, q, j, lane, m, tid;        // epilogue warp, TMEM quadrant, column slice, lane, tile row, 0..511
   uint32_t tlane;
   __device__ __forceinline__ void init(uint32_t tmem) {
     const int warp = threadIdx.x >> 5;
@@ -334,33 +334,31 @@ struct EpiThread {
     e = warp - 2; q = warp & 3; j = e >> 2;
     m = q * 32 + lane;
     tid = threadIdx.x - 64;
-    pb = q * 2 + (j >> 1);
     tlane = tmem + ((uint32_t)(q * 32) << 16);
   }
-  __device__ __forceinline__ int col0(int b) const { return b * 128 + j * 32; }     // first column of block b
-  __device__ __forceinline__ int kchunk(int b) const { return b * 2 + (j >> 1); }   // 64-column k chunk of block b
+  __device__ __forceinline__ int col0(int c) const { return c * 64 + j * 16; }      // first column of the piece in chunk c
 };
 
-// Pushes one finished 32-column block (packed hi/lo words of this thread's row) to the HBM image.  The two warps
-// (q, 2p) and (q, 2p+1) fill one 32-row x 64-column piece of an atom block = 4 KB contiguous bytes of the image per
-// term, staged in their pair buffer and written with one bulk store per term.  Called by both warps of the pair.
-__device__ __forceinline__ void stage_pair(const EpiThread& t, char* staging, const uint32_t (&ph)[16],
-                                           const uint32_t (&pl)[16], char* g_hi_atom, char* g_lo_atom) {
-  char* sh = staging + t.pb * 8192;
+// Pushes one finished 16-column piece (packed hi/lo words of this thread's row) to the HBM image.  The four warps of
+// a quadrant fill one 32-row x 64-column part of an atom block = 4 KB contiguous bytes of the image per term, staged
+// in the quadrant's buffer `buf` (two alternate) and written with one bulk store per term.  Called by all four warps.
+__device__ __forceinline__ void stage_quad(const EpiThread& t, char* staging, int buf, const uint32_t (&ph)[8],
+                                           const uint32_t (&pl)[8], char* g_hi_atom, char* g_lo_atom) {
+  char* sh = staging + (buf * 4 + t.q) * 8192;
   char* sl = sh + 4096;
-  const bool issuer = ((t.j & 1) == 0) && t.lane == 0;
-  if (issuer) bulk_wait_read0();                         // the previous piece has left the buffer
-  named_bar(1 + t.pb, 64);
+  const bool issuer = (t.j == 0) && t.lane == 0;
+  if (issuer) bulk_wait_read1();                         // the store that used this buffer two pieces ago has read it
+  named_bar(1 + t.q, 128);
   const int r = t.m & 7;
   const int base = ((t.m & 31) >> 3) * 1024 + r * 128;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int off = base + ((((t.j & 1) * 4 + c) ^ r) << 4);
-    *reinterpret_cast<uint4*>(sh + off) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
-    *reinterpret_cast<uint4*>(sl + off) = make_uint4(pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
+  for (int u = 0; u < 2; ++u) {
+    const int off = base + (((t.j * 2 + u) ^ r) << 4);
+    *reinterpret_cast<uint4*>(sh + off) = make_uint4(ph[4 * u], ph[4 * u + 1], ph[4 * u + 2], ph[4 * u + 3]);
+    *reinterpret_cast<uint4*>(sl + off) = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
   }
   fence_proxy_async_smem();
-  named_bar(1 + t.pb, 64);
+  named_bar(1 + t.q, 128);
   if (issuer) {
     bulk_s2g(g_hi_atom + t.q * 4096, sh, 4096);
     bulk_s2g(g_lo_atom + t.q * 4096, sl, 4096);
@@ -461,6 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
     const int m = et.m, j = et.j;
     uint32_t d_par = 0;
     const float inv_scale = 1.0f / S_W;                 // D / (S_a S_w) * S_a : activations stay scaled by S_ACT
+    uint16_t* bits16 = reinterpret_cast<uint16_t*>(P.img.bits);
     for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
       const int gt = ti.global_tile(t);
       const int64_t row = (int64_t)gt * TM + m;
@@ -504,16 +503,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         tc_fence_before();
         mbar_arrive(sm.x_ready);
       } else {
-        // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0), this thread's two 32-column blocks
+        // layer 0 (3 -> 256) on CUDA cores: h0 = relu(W0 x + b0), this thread's four 16-column pieces
         const float4 xv = *reinterpret_cast<const float4*>(P.x + row * 4);
         char* img = P.img.act + (int64_t)gt * TILE_IMG_BYTES;
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int c0 = et.col0(b);
-          uint32_t ph[16], pl[16];
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = et.col0(c);
+          uint32_t ph[8], pl[8];
           uint32_t bw = 0;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
+          for (int i = 0; i < 16; i += 2) {
             float z[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -527,15 +526,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
             }
             split2_f16(z[0], z[1], ph[i / 2], pl[i / 2]);
           }
-          tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
-          tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
+          tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
+          tmem_st8(et.tlane + TM_ALO + c0 / 2, pl);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&sm.a_ready[et.kchunk(b)]);      // this thread's share of k chunk kchunk(b) of A_1 is in TMEM
+          mbar_arrive(&sm.a_ready[c]);                 // this thread's share of k chunk c of A_1 is in TMEM
           if (P.store_images) {
-            char* g = img + et.kchunk(b) * ATOM_BYTES;
-            stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
-            P.img.bits[((int64_t)0 * P.img.rows + row) * 8 + (c0 >> 5)] = bw;
+            char* g = img + c * ATOM_BYTES;
+            stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
+            bits16[((int64_t)0 * P.img.rows + row) * 16 + (c0 >> 4)] = (uint16_t)bw;
           }
         }
       }
@@ -548,24 +547,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
         // drain this thread's 64 accumulator columns, then hand D back to the MMA warp
-        uint32_t raw[2][32];
-        tmem_ld32(et.tlane + TM_D + et.col0(0), raw[0]);
-        tmem_ld32(et.tlane + TM_D + et.col0(1), raw[1]);
+        uint32_t raw[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(et.tlane + TM_D + et.col0(c), raw[c]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(sm.d_free);
         const bool last = (l == LAST_TC);
         char* img = P.img.act + (int64_t)l * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int c0 = et.col0(b);
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = et.col0(c);
           const float* bias = s_bias + l * 256 + c0;
-          uint32_t ph[16], pl[16];
+          uint32_t ph[8], pl[8];
           uint32_t bw = 0;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float z0 = fmaf(__uint_as_float(raw[b][i]), inv_scale, bias[i]);
-            const float z1 = fmaf(__uint_as_float(raw[b][i + 1]), inv_scale, bias[i + 1]);
+          for (int i = 0; i < 16; i += 2) {
+            const float z0 = fmaf(__uint_as_float(raw[c][i]), inv_scale, bias[i]);
+            const float z1 = fmaf(__uint_as_float(raw[c][i + 1]), inv_scale, bias[i + 1]);
             bw |= (z0 > 0.f ? 1u : 0u) << i;
             bw |= (z1 > 0.f ? 1u : 0u) << (i + 1);
             const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
@@ -579,16 +578,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
             split2_f16(v0, v1, ph[i / 2], pl[i / 2]);
           }
           if (!last) {
-            tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
-            tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
+            tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
+            tmem_st8(et.tlane + TM_ALO + c0 / 2, pl);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&sm.a_ready[et.kchunk(b)]);     // next layer's MMAs on this k chunk may start
+            mbar_arrive(&sm.a_ready[c]);                // next layer's MMAs on k chunk c may start
           }
           if (P.store_images) {
-            char* g = img + et.kchunk(b) * ATOM_BYTES;
-            stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
-            P.img.bits[((int64_t)l * P.img.rows + row) * 8 + (c0 >> 5)] = bw;
+            char* g = img + c * ATOM_BYTES;
+            stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
+            bits16[((int64_t)l * P.img.rows + row) * 16 + (c0 >> 4)] = (uint16_t)bw;
           }
         }
       }
@@ -620,7 +619,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       }
       named_bar(BAR_EPI, EPI_THREADS);                   // s_xch / aux tile reuse by the next tile
     }
-    if ((j & 1) == 0 && lane == 0) bulk_wait_all0();
+    if (j == 0 && lane == 0) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -682,6 +681,35 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+// column sums of 16 values over the 32 rows of a warp: lanes 2k and 2k+1 end with sum_rows v[k]
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = (lane & 16) ? v[i] : v[i + 8];
+    const float keep = (lane & 16) ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = (lane & 8) ? a[i] : a[i + 4];
+    const float keep = (lane & 8) ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float c[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = (lane & 4) ? b[i] : b[i + 2];
+    const float keep = (lane & 4) ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = (lane & 2) ? c[0] : c[1];
+  const float keep = (lane & 2) ? c[1] : c[0];
+  const float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 // gmax_bits[0]: max |dL/drgb| (atlas network);  gmax_bits[1]: max |dL/duv| (mapping network: loss head,
 // then raised by the atlas backward, whose positional encoding multiplies gradients by up to 2^9*pi).
 __device__ __forceinline__ void grad_scales(const int* gmax_bits, bool mapping, float& s_g, float& inv_sg) {
@@ -709,7 +737,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
   float* s_wlast = sm.cst;                               // OUT*KLAST (<= 888)
   float* s_bacc = sm.cst + 896;                          // (L-1)*256 (<= 1792)
   float* s_w0acc = s_bacc + (L - 1) * 256;               // mapping: 768   (896+1280+768 = 2944)
-  float* s_xch = sm.cst + SMEM_CONST_FLOATS - TM * 2;    // atlas: [128][2]
+  float* s_xch = sm.cst + SMEM_CONST_FLOATS - 3 * TM * 2; // atlas: [3][128][2] partial dPE sums of slices 1..3
   for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i];
   for (int i = threadIdx.x; i < (L - 1) * 256 + (ATLAS ? 0 : 768); i += blockDim.x) s_bacc[i] = 0.f;
   const uint32_t tmem = setup_cta(sm, warp);
@@ -762,6 +790,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
     const int m = et.m, j = et.j;
     uint32_t d_par = 0, aux_par = 0;
     const float inv_dgrad = inv_sg * (1.0f / S_W);        // D = (S_g dZ)(S_w W)
+    const uint16_t* bits16 = reinterpret_cast<const uint16_t*>(P.img.bits);
+    const int col_lane = lane >> 1;                        // warp_colsum16: lanes 2k, 2k+1 hold column k
     for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
       const int gt = ti.global_tile(t);
       const int64_t row = (int64_t)gt * TM + m;
@@ -799,28 +829,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       {
         char* img = P.img.dz + (int64_t)(L - 2) * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int c0 = et.col0(b);
-          const uint32_t bits = P.img.bits[((int64_t)(L - 2) * P.img.rows + row) * 8 + (c0 >> 5)];
-          float v[32];
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = et.col0(c);
+          const uint32_t bits = bits16[((int64_t)(L - 2) * P.img.rows + row) * 16 + (c0 >> 4)];
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             float a = 0.f;
 #pragma unroll
             for (int jj = 0; jj < OUT; ++jj) a = fmaf(dzl[jj], s_wlast[jj * KLAST + c0 + i], a);
             v[i] = ((bits >> i) & 1u) ? a : 0.f;
           }
-          atomicAdd(&s_bacc[(L - 2) * 256 + c0 + lane], warp_colsum32(v, lane));
-          uint32_t ph[16], pl[16];
+          {
+            const float cs = warp_colsum16(v, lane);
+            if (!(lane & 1)) atomicAdd(&s_bacc[(L - 2) * 256 + c0 + col_lane], cs);
+          }
+          uint32_t ph[8], pl[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
-          tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
-          tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
+          for (int i = 0; i < 8; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
+          tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
+          tmem_st8(et.tlane + TM_ALO + c0 / 2, pl);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&sm.a_ready[et.kchunk(b)]);
-          char* g = img + et.kchunk(b) * ATOM_BYTES;
-          stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
+          mbar_arrive(&sm.a_ready[c]);
+          char* g = img + c * ATOM_BYTES;
+          stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
         }
       }
       // ---------------- hidden layers: dA_l = dZ_l W_l  ->  dZ_{l-1}
@@ -828,9 +861,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       for (int l = L - 2; l >= LOW; --l) {
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
-        uint32_t raw[2][32];
-        tmem_ld32(et.tlane + TM_D + et.col0(0), raw[0]);
-        tmem_ld32(et.tlane + TM_D + et.col0(1), raw[1]);
+        uint32_t raw[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(et.tlane + TM_D + et.col0(c), raw[c]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(sm.d_free);
@@ -841,41 +874,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!ATLAS && slot == 0) xv = *reinterpret_cast<const float4*>(P.x + row * 4);
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int c0 = et.col0(b);
-          const uint32_t bits = P.img.bits[((int64_t)slot * P.img.rows + row) * 8 + (c0 >> 5)];
-          float v[32];
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = et.col0(c);
+          const uint32_t bits = bits16[((int64_t)slot * P.img.rows + row) * 16 + (c0 >> 4)];
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? __uint_as_float(raw[b][i]) * inv_dgrad : 0.f;
-          atomicAdd(&s_bacc[slot * 256 + c0 + lane], warp_colsum32(v, lane));
+          for (int i = 0; i < 16; ++i) v[i] = ((bits >> i) & 1u) ? __uint_as_float(raw[c][i]) * inv_dgrad : 0.f;
+          {
+            const float cs = warp_colsum16(v, lane);
+            if (!(lane & 1)) atomicAdd(&s_bacc[slot * 256 + c0 + col_lane], cs);
+          }
           if (!ATLAS && slot == 0) {
             // layer-0 weight gradient dW0[n][d] = sum_m dZ0[m][n] * x[m][d]
-            const int n = c0 + lane;
-            float w[32];
+            const int n = c0 + col_lane;
+            float w[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.x;
-            atomicAdd(&s_w0acc[n * 3 + 0], warp_colsum32(w, lane));
+            for (int i = 0; i < 16; ++i) w[i] = v[i] * xv.x;
+            float cs = warp_colsum16(w, lane);
+            if (!(lane & 1)) atomicAdd(&s_w0acc[n * 3 + 0], cs);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.y;
-            atomicAdd(&s_w0acc[n * 3 + 1], warp_colsum32(w, lane));
+            for (int i = 0; i < 16; ++i) w[i] = v[i] * xv.y;
+            cs = warp_colsum16(w, lane);
+            if (!(lane & 1)) atomicAdd(&s_w0acc[n * 3 + 1], cs);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = v[i] * xv.z;
-            atomicAdd(&s_w0acc[n * 3 + 2], warp_colsum32(w, lane));
+            for (int i = 0; i < 16; ++i) w[i] = v[i] * xv.z;
+            cs = warp_colsum16(w, lane);
+            if (!(lane & 1)) atomicAdd(&s_w0acc[n * 3 + 2], cs);
           }
           if (need_img || need_tmem) {
-            uint32_t ph[16], pl[16];
+            uint32_t ph[8], pl[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
+            for (int i = 0; i < 8; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
             if (need_tmem) {
-              tmem_st16(et.tlane + TM_AHI + c0 / 2, ph);
-              tmem_st16(et.tlane + TM_ALO + c0 / 2, pl);
+              tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
+              tmem_st8(et.tlane + TM_ALO + c0 / 2, pl);
               tmem_st_wait();
               tc_fence_before();
-              mbar_arrive(&sm.a_ready[et.kchunk(b)]);
+              mbar_arrive(&sm.a_ready[c]);
             }
             if (need_img) {
-              char* g = img + et.kchunk(b) * ATOM_BYTES;
-              stage_pair(et, sm.staging, ph, pl, g, g + P.img.term_stride);
+              char* g = img + c * ATOM_BYTES;
+              stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
             }
           }
         }
@@ -885,38 +924,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
         mbar_wait(&sm.misc[0], aux_par);                  // PE tile of this row block
-        uint32_t raw[32];
-        if (j < 2) {                                      // slices 0 and 1 hold the 64 accumulator columns
-          tmem_ld32(et.tlane + TM_D + j * 32, raw);
-          tmem_ld_wait();
-        }
+        uint32_t raw[16];                                 // slice j holds accumulator columns [16j, 16j + 16)
+        tmem_ld16(et.tlane + TM_D + j * 16, raw);
+        tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(sm.d_free);
         float din[2] = {0.f, 0.f};
-        if (j < 2) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = j * 32 + i;
-            if (col < PE_COLS) {
-              const int k = col >> 2, e = col & 3;         // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
-              const float g = __uint_as_float(raw[i]) * inv_dgrad;
-              const int pcol = (e < 2) ? col + 2 : col - 2;     // d sin = cos * b,  d cos = -sin * b
-              const int off = atom_off(m, pcol);
-              const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
-                                     __half2float(*reinterpret_cast<const __half*>(sm.aux + ATOM_BYTES + off))) *
-                                    (1.0f / S_ACT);
-              const float bk = pe_freq(k);
-              din[e & 1] += (e < 2) ? g * partner * bk : -g * partner * bk;
-            }
+        for (int i = 0; i < 16; ++i) {
+          const int col = j * 16 + i;
+          if (col < PE_COLS) {
+            const int k = col >> 2, e = col & 3;           // e: 0,1 = sin(x0),sin(x1); 2,3 = cos(x0),cos(x1)
+            const float g = __uint_as_float(raw[i]) * inv_dgrad;
+            const int pcol = (e < 2) ? col + 2 : col - 2;       // d sin = cos * b,  d cos = -sin * b
+            const int off = atom_off(m, pcol);
+            const float partner = (__half2float(*reinterpret_cast<const __half*>(sm.aux + off)) +
+                                   __half2float(*reinterpret_cast<const __half*>(sm.aux + ATOM_BYTES + off))) *
+                                  (1.0f / S_ACT);
+            const float bk = pe_freq(k);
+            din[e & 1] += (e < 2) ? g * partner * bk : -g * partner * bk;
           }
-          if (j == 1) { s_xch[m * 2] = din[0]; s_xch[m * 2 + 1] = din[1]; }
         }
+        if (j > 0) { s_xch[((j - 1) * TM + m) * 2] = din[0]; s_xch[((j - 1) * TM + m) * 2 + 1] = din[1]; }
         named_bar(BAR_EPI, EPI_THREADS);
         if (j == 0 && P.d_in) {
           float2* dst = reinterpret_cast<float2*>(P.d_in + row * 2);
           float2 cur = P.d_in_accumulate ? *dst : make_float2(0.f, 0.f);
-          cur.x += P.in_scale * (din[0] + s_xch[m * 2]);
-          cur.y += P.in_scale * (din[1] + s_xch[m * 2 + 1]);
+          cur.x += P.in_scale * (((din[0] + s_xch[m * 2]) + s_xch[(TM + m) * 2]) + s_xch[(2 * TM + m) * 2]);
+          cur.y += P.in_scale * (((din[1] + s_xch[m * 2 + 1]) + s_xch[(TM + m) * 2 + 1]) + s_xch[(2 * TM + m) * 2 + 1]);
           *dst = cur;
           float mx = fmaxf(fabsf(cur.x), fabsf(cur.y));
 #pragma unroll
@@ -929,7 +964,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         aux_par ^= 1;
       }
     }
-    if ((j & 1) == 0 && lane == 0) bulk_wait_all0();
+    if (j == 0 && lane == 0) bulk_wait_all0();
     // flush the per-CTA accumulators
     named_bar(BAR_EPI, EPI_THREADS);
     for (int i = et.tid; i < (L - 1) * 256; i += EPI_THREADS) {
