@@ -272,10 +272,14 @@ constexpr int SMEM_STAGING = 2 * 2 * ATOM_BYTES;             // 64 KB
 constexpr int SMEM_AUX = 2 * ATOM_BYTES;                     // 32 KB
 constexpr int SMEM_CONST_FLOATS = 4608;                      // 18 KB
 constexpr int SMEM_BARS = 256;
+// Both kernels stream the weights through a 4-stage ring (128 KB: a 64 KB k chunk is consumed in ~1.8 k cycles, the
+// bulk copies take 2-4 k cycles to arrive, so three stages starved the atlas kernels' MMA warp).  The atlas kernels
+// pay for the fourth stage and their positional-encoding tile with single-buffered image staging.
 template <bool ATLAS> struct KCfg {
-  static constexpr int NST = ATLAS ? 3 : 4;
-  static constexpr int SMEM = NST * STAGE_BYTES + SMEM_STAGING + (ATLAS ? SMEM_AUX : 0) + SMEM_CONST_FLOATS * 4 +
-                              SMEM_BARS;
+  static constexpr int NST = 4;
+  static constexpr int STAGING_BUFS = ATLAS ? 1 : 2;
+  static constexpr int STAGING = STAGING_BUFS * 4 * 8192;
+  static constexpr int SMEM = NST * STAGE_BYTES + STAGING + (ATLAS ? SMEM_AUX : 0) + SMEM_CONST_FLOATS * 4 + SMEM_BARS;
 };
 
 template <int NST, bool ATLAS>
@@ -286,7 +290,7 @@ struct SmemMap {
   __device__ __forceinline__ void init(char* raw) {
     char* p = raw;                                   // 1024-aligned (checked in setup_cta): keeps the
     stage = p; p += NST * STAGE_BYTES;               // shared address space visible to the compiler (LDS/STS)
-    staging = p; p += SMEM_STAGING;
+    staging = p; p += KCfg<ATLAS>::STAGING;
     aux = p; if (ATLAS) p += SMEM_AUX;
     cst = reinterpret_cast<float*>(p); p += SMEM_CONST_FLOATS * 4;
     full = reinterpret_cast<uint64_t*>(p);
@@ -342,12 +346,15 @@ struct EpiThread {
 // Pushes one finished 16-column piece (packed hi/lo words of this thread's row) to the HBM image.  The four warps of
 // a quadrant fill one 32-row x 64-column part of an atom block = 4 KB contiguous bytes of the image per term, staged
 // in the quadrant's buffer `buf` (two alternate) and written with one bulk store per term.  Called by all four warps.
-__device__ __forceinline__ void stage_quad(const EpiThread& t, char* staging, int buf, const uint32_t (&ph)[8],
+template <int BUFS>
+__device__ __forceinline__ void stage_quad(const EpiThread& t, char* staging, int piece, const uint32_t (&ph)[8],
                                            const uint32_t (&pl)[8], char* g_hi_atom, char* g_lo_atom) {
-  char* sh = staging + (buf * 4 + t.q) * 8192;
+  char* sh = staging + ((BUFS == 2 ? (piece & 1) : 0) * 4 + t.q) * 8192;
   char* sl = sh + 4096;
   const bool issuer = (t.j == 0) && t.lane == 0;
-  if (issuer) bulk_wait_read1();                         // the store that used this buffer two pieces ago has read it
+  if (issuer) {                                          // the previous store out of this buffer has read it
+    if (BUFS == 2) bulk_wait_read1(); else bulk_wait_read0();
+  }
   named_bar(1 + t.q, 128);
   const int r = t.m & 7;
   const int base = ((t.m & 31) >> 3) * 1024 + r * 128;
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           mbar_arrive(&sm.a_ready[c]);                 // this thread's share of k chunk c of A_1 is in TMEM
           if (P.store_images) {
             char* g = img + c * ATOM_BYTES;
-            stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
+            stage_quad<KCfg<ATLAS>::STAGING_BUFS>(et, sm.staging, c, ph, pl, g, g + P.img.term_stride);
             bits16[((int64_t)0 * P.img.rows + row) * 16 + (c0 >> 4)] = (uint16_t)bw;
           }
         }
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           }
           if (P.store_images) {
             char* g = img + c * ATOM_BYTES;
-            stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
+            stage_quad<KCfg<ATLAS>::STAGING_BUFS>(et, sm.staging, c, ph, pl, g, g + P.img.term_stride);
             bits16[((int64_t)l * P.img.rows + row) * 16 + (c0 >> 4)] = (uint16_t)bw;
           }
         }
@@ -853,7 +860,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
           tc_fence_before();
           mbar_arrive(&sm.a_ready[c]);
           char* g = img + c * ATOM_BYTES;
-          stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
+          stage_quad<KCfg<ATLAS>::STAGING_BUFS>(et, sm.staging, c, ph, pl, g, g + P.img.term_stride);
         }
       }
       // ---------------- hidden layers: dA_l = dZ_l W_l  ->  dZ_{l-1}
@@ -914,7 +921,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
             }
             if (need_img) {
               char* g = img + c * ATOM_BYTES;
-              stage_quad(et, sm.staging, c & 1, ph, pl, g, g + P.img.term_stride);
+              stage_quad<KCfg<ATLAS>::STAGING_BUFS>(et, sm.staging, c, ph, pl, g, g + P.img.term_stride);
             }
           }
         }
