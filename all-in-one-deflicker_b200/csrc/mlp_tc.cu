@@ -418,7 +418,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
     s_bias[i] = P.params[P.b_off[i >> 8] + (i & 255)] * S_ACT;
   for (int i = threadIdx.x; i < OUT * KLAST; i += blockDim.x) s_wlast[i] = P.params[P.w_off[L - 1] + i] * (1.0f / S_ACT);
   if (threadIdx.x < OUT) s_blast[threadIdx.x] = P.params[P.b_off[L - 1] + threadIdx.x];
-  if (!ATLAS) for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[i] = P.params[P.w_off[0] + i] * S_ACT;
+  if (!ATLAS)      // W0 (256 x 3) transposed to [3][256] so that column pairs are adjacent (FFMA2)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_w0[(i % 3) * 256 + i / 3] = P.params[P.w_off[0] + i] * S_ACT;
   const uint32_t tmem = setup_cta(sm, warp);
   TileIter ti; ti.init(P.cap, P.n_groups, P.n_valid, P.flow_groups);
   constexpr uint32_t IDESC = make_idesc(128, 256, 0, 0);
@@ -518,20 +519,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           const int c0 = et.col0(c);
           uint32_t ph[8], pl[8];
           uint32_t bw = 0;
+          const uint64_t x0 = pack2f(xv.x, xv.x), x1 = pack2f(xv.y, xv.y), x2 = pack2f(xv.z, xv.z);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            float z[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int n = c0 + i + u;
-              float a = s_bias[n];
-              a = fmaf(xv.x, s_w0[n * 3 + 0], a);
-              a = fmaf(xv.y, s_w0[n * 3 + 1], a);
-              a = fmaf(xv.z, s_w0[n * 3 + 2], a);
-              bw |= (a > 0.f ? 1u : 0u) << (i + u);
-              z[u] = fmaxf(a, 0.f);
-            }
-            split2_f16(z[0], z[1], ph[i / 2], pl[i / 2]);
+            const int n = c0 + i;
+            uint64_t a = *reinterpret_cast<const uint64_t*>(s_bias + n);
+            a = fma2(x0, *reinterpret_cast<const uint64_t*>(s_w0 + n), a);
+            a = fma2(x1, *reinterpret_cast<const uint64_t*>(s_w0 + 256 + n), a);
+            a = fma2(x2, *reinterpret_cast<const uint64_t*>(s_w0 + 512 + n), a);
+            float z0, z1;
+            unpack2f(a, z0, z1);
+            const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
+            bw = push_flag(push_flag(bw, v0), v1);
+            split2_packed(v0, v1, ph[i / 2], pl[i / 2]);
           }
           tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
           tmem_st8(et.tlane + TM_ALO + c0 / 2, pl);
@@ -568,13 +568,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           const float* bias = s_bias + l * 256 + c0;
           uint32_t ph[8], pl[8];
           uint32_t bw = 0;
+          const uint64_t inv2 = pack2f(inv_scale, inv_scale);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float z0 = fmaf(__uint_as_float(raw[c][i]), inv_scale, bias[i]);
-            const float z1 = fmaf(__uint_as_float(raw[c][i + 1]), inv_scale, bias[i + 1]);
-            bw |= (z0 > 0.f ? 1u : 0u) << i;
-            bw |= (z1 > 0.f ? 1u : 0u) << (i + 1);
+            float z0, z1;
+            unpack2f(fma2(pack2u(raw[c][i], raw[c][i + 1]), inv2, *reinterpret_cast<const uint64_t*>(bias + i)), z0, z1);
             const float v0 = fmaxf(z0, 0.f), v1 = fmaxf(z1, 0.f);
+            bw = push_flag(push_flag(bw, v0), v1);      // flag of column i is bit 15 - i
             if (last) {
 #pragma unroll
               for (int jj = 0; jj < OUT; ++jj) {
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
                 outacc[jj] = fmaf(v1, s_wlast[jj * KLAST + c0 + i + 1], outacc[jj]);
               }
             }
-            split2_f16(v0, v1, ph[i / 2], pl[i / 2]);
+            split2_packed(v0, v1, ph[i / 2], pl[i / 2]);
           }
           if (!last) {
             tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
@@ -845,15 +845,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
             float a = 0.f;
 #pragma unroll
             for (int jj = 0; jj < OUT; ++jj) a = fmaf(dzl[jj], s_wlast[jj * KLAST + c0 + i], a);
-            v[i] = ((bits >> i) & 1u) ? a : 0.f;
+            v[i] = ((bits >> (15 - i)) & 1u) ? a : 0.f;
           }
           {
             const float cs = warp_colsum16(v, lane);
             if (!(lane & 1)) atomicAdd(&s_bacc[(L - 2) * 256 + c0 + col_lane], cs);
           }
           uint32_t ph[8], pl[8];
+          const uint64_t sg2 = pack2f(s_g, s_g);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
+          for (int i = 0; i < 8; ++i) {
+            float w0, w1;
+            unpack2f(mul2(pack2f(v[2 * i], v[2 * i + 1]), sg2), w0, w1);
+            split2_packed(w0, w1, ph[i], pl[i]);
+          }
           tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
           tmem_st8(et.tlane + TM_ALO + c0 / 2, pl);
           tmem_st_wait();
@@ -885,8 +890,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
           const int c0 = et.col0(c);
           const uint32_t bits = bits16[((int64_t)slot * P.img.rows + row) * 16 + (c0 >> 4)];
           float v[16];
+          const uint64_t invd2 = pack2f(inv_dgrad, inv_dgrad);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = ((bits >> i) & 1u) ? __uint_as_float(raw[c][i]) * inv_dgrad : 0.f;
+          for (int i = 0; i < 16; i += 2) {
+            float a0, a1;
+            unpack2f(mul2(pack2u(raw[c][i], raw[c][i + 1]), invd2), a0, a1);
+            v[i] = ((bits >> (15 - i)) & 1u) ? a0 : 0.f;
+            v[i + 1] = ((bits >> (14 - i)) & 1u) ? a1 : 0.f;
+          }
           {
             const float cs = warp_colsum16(v, lane);
             if (!(lane & 1)) atomicAdd(&s_bacc[slot * 256 + c0 + col_lane], cs);
@@ -910,8 +921,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
           }
           if (need_img || need_tmem) {
             uint32_t ph[8], pl[8];
+            const uint64_t sg2 = pack2f(s_g, s_g);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) split2_f16(v[2 * i] * s_g, v[2 * i + 1] * s_g, ph[i], pl[i]);
+            for (int i = 0; i < 8; ++i) {
+              float w0, w1;
+              unpack2f(mul2(pack2f(v[2 * i], v[2 * i + 1]), sg2), w0, w1);
+              split2_packed(w0, w1, ph[i], pl[i]);
+            }
             if (need_tmem) {
               tmem_st8(et.tlane + TM_AHI + c0 / 2, ph);
               tmem_st8(et.tlane + TM_ALO + c0 / 2, pl);

@@ -209,3 +209,28 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 }  // namespace ptx
 }  // namespace b200
+
+namespace b200 {
+namespace ptx {
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 issue one instruction for two lanes of a register pair)
+__device__ __forceinline__ uint64_t pack2f(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pack2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void unpack2f(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// 2-term fp16 split of two already-scaled floats: same values as split2_f16, the residual subtraction as one FADD2
+__device__ __forceinline__ void split2_packed(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_pack_f16x2(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  float d0, d1;
+  unpack2f(sub2(pack2f(a, b), pack2f(hf.x, hf.y)), d0, d1);
+  lo = cvt_pack_f16x2(d0, d1);
+}
+// appends the ReLU flag of v (v >= +0: the output of fmaxf(z, 0)) to a bit string: flag = v > 0 <=> 0 - bits(v) is
+// negative.  After n appends the FIRST value's flag is bit n-1.
+__device__ __forceinline__ uint32_t push_flag(uint32_t bw, float v) {
+  return __funnelshift_l((uint32_t)(-(int)__float_as_uint(v)), bw, 1);
+}
+}  // namespace ptx
+}  // namespace b200
