@@ -158,7 +158,7 @@ def convex_upsample(flow, mask):
     return out
 
 
-def corr_build(fmap1, fmap2, impl="tc"):
+def corr_build(fmap1, fmap2, impl="tc", out=None):
     """fmaps (1, C, H8, W8) -> flat pyramid tensor (level 0 [HW][H8][W8] then 3 pooled levels).
     impl 'tc': tcgen05 with (hi, lo) fp16 operand pairs (fp32-grade, like the reference's fp32 matmul);
     'simt': fp32 CUDA-core GEMM."""
@@ -166,7 +166,10 @@ def corr_build(fmap1, fmap2, impl="tc"):
     b, c, h, w = fmap1.shape
     if b != 1:
         raise N.B200Error("correlation kernels take batch 1 (the reference runs one frame pair at a time)")
-    pyr = torch.empty(int(N.lib().b200_corr_pyramid_floats(h, w)), dtype=torch.float32, device=fmap1.device)
+    n_pyr = int(N.lib().b200_corr_pyramid_floats(h, w))
+    pyr = out if out is not None else torch.empty(n_pyr, dtype=torch.float32, device=fmap1.device)
+    if pyr.numel() != n_pyr:
+        raise N.B200Error("corr_build: `out` has the wrong size")
     if impl == "tc":
         nbytes = N.lib().b200_corr_build_tc_workspace_bytes(c, h, w)
         if nbytes <= 0:

@@ -32,6 +32,7 @@ class RAFT(nn.Module):
         self.fnet = BasicEncoder(output_dim=256, norm_fn='instance', dropout=args.dropout)
         self.cnet = BasicEncoder(output_dim=hdim + cdim, norm_fn='batch', dropout=args.dropout)
         self.update_block = BasicUpdateBlock(self.args, hidden_dim=hdim)
+        self._graph_state = {}          # (fmap shape, iters, device) -> captured refinement loop + its buffers
 
     @contextlib.contextmanager
     def _autocast(self):
@@ -71,7 +72,14 @@ class RAFT(nn.Module):
         return out12, out21
 
     def _refine(self, fmap1, fmap2, image1, iters, flow_init, test_mode):
-        corr_fn = CorrBlock(fmap1.float(), fmap2.float(), radius=self.args.corr_radius)
+        """core/raft.py:109-148.  In test mode the `iters` refinement iterations (lookup -> update block -> coordinate
+        update, ~100 launches each plus tensor glue) are captured once per geometry in ONE CUDA graph and replayed:
+        the correlation pyramid, hidden state, context and coordinates live in buffers owned by this module."""
+        use_graph = test_mode and getattr(self.args, "cuda_graph", True) and fmap1.is_cuda
+        key = (tuple(fmap1.shape), int(iters), fmap1.device)
+        st = self._graph_state.get(key) if use_graph else None
+        corr_fn = CorrBlock(fmap1.float(), fmap2.float(), radius=self.args.corr_radius,
+                            out=st["pyr"] if st is not None else None)
         with self._autocast():
             cnet = self.cnet(image1)
         net, inp = torch.split(cnet, [self.hidden_dim, self.context_dim], dim=1)
@@ -79,6 +87,26 @@ class RAFT(nn.Module):
         coords0, coords1 = self.initialize_flow(image1)
         if flow_init is not None:
             coords1 = coords1 + flow_init
+        if use_graph:
+            if st is None:
+                # first call for this geometry: adopt the buffers, run the loop once eagerly (fills the weight-image
+                # caches, so nothing is packed or allocated outside the graph pool during capture), then capture
+                st = dict(pyr=corr_fn.pyramid, net=net.clone(), inp=inp.clone(), c0=coords0.clone(), c1=coords1.clone())
+                corr_fn.pyramid = st["pyr"]
+                self._loop(corr_fn, st["net"].clone(), st["inp"], st["c0"], st["c1"].clone(), iters, True)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["out"] = self._loop(corr_fn, st["net"], st["inp"], st["c0"], st["c1"], iters, True)
+                st["graph"] = g
+                self._graph_state[key] = st
+            st["net"].copy_(net); st["inp"].copy_(inp); st["c0"].copy_(coords0); st["c1"].copy_(coords1)
+            st["graph"].replay()
+            flow_lo, flow_up = st["out"]
+            return flow_lo.clone(), flow_up.clone()
+        return self._loop(corr_fn, net, inp, coords0, coords1, iters, test_mode)
+
+    def _loop(self, corr_fn, net, inp, coords0, coords1, iters, test_mode):
         flow_up, preds = None, []
         for it in range(iters):
             corr = corr_fn(coords1)
