@@ -63,6 +63,18 @@ class AtlasConfig(C.Structure):
                 ("global_rigidity_coeff", C.c_float), ("flow_coeff", C.c_float)]
 
 
+class SegConfig(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("with_global", C.c_int32), ("precision", C.c_int32), ("resx", C.c_int32),
+                ("uv_mapping_scale", C.c_float), ("derivative_amount", C.c_float),
+                ("global_derivative_amount", C.c_float), ("rgb_coeff", C.c_float), ("gradient_coeff", C.c_float),
+                ("rigidity_coeff", C.c_float), ("global_rigidity_coeff_fg", C.c_float),
+                ("global_rigidity_coeff_bg", C.c_float), ("flow_coeff", C.c_float), ("alpha_flow_factor", C.c_float),
+                ("sparsity_coeff", C.c_float), ("bootstrapping_factor", C.c_float),
+                ("mapping1", MlpDesc), ("mapping2", MlpDesc), ("alpha", MlpDesc), ("atlas", MlpDesc)]
+
+
+SEG_LOSS_FLOATS = 16
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -96,6 +108,15 @@ SIGNATURES = {
     "b200_dp_adam_step": (C.c_int, [C.POINTER(DpComm), _P, _P, _I64, _I64, C.c_double, C.c_double, C.c_double, C.c_double,
                                     _P, _P, _P]),
     "b200_dp_slice": (C.c_int, [_I32, _I32, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
+    "b200_mlp_tc_architecture": (C.c_int, [C.POINTER(MlpDesc)]),
+    "b200_seg_param_floats": (_I64, [C.POINTER(SegConfig), C.POINTER(_I64)]),
+    "b200_seg_workspace_bytes": (_I64, [C.POINTER(SegConfig)]),
+    "b200_seg_loss_grad": (C.c_int, [C.POINTER(SegConfig), C.POINTER(Video), _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "b200_mlp_pretrain_workspace_bytes": (_I64, [C.POINTER(MlpDesc), _I32]),
+    "b200_mlp_pretrain_loss_grad": (C.c_int, [C.POINTER(MlpDesc), _I32, _F, _I32, _I32, _I32, _P, _P, _P, _P, _P, C.c_int,
+                                              _P, _I64, _P]),
+    "b200_seg_render_workspace_bytes": (_I64, [C.POINTER(SegConfig), _I64]),
+    "b200_seg_render": (C.c_int, [C.POINTER(SegConfig), _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _I64, _P]),
     "b200_render_workspace_bytes": (_I64, [_I64]),
     "b200_render": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, C.c_int, _P, _I64, _P]),
     "b200_corr_pyramid_floats": (_I64, [_I32, _I32]),
@@ -172,6 +193,7 @@ def hostcheck():
     """CPU build of csrc/loss_math.h for the host-math tests."""
     h = C.CDLL(HOSTCHECK_PATH)
     h.b200_host_sample_loss.argtypes = [_P, _P, _P]
+    h.b200_host_seg_sample_loss.argtypes = [_P, _P, _P]
     h.b200_host_norm_coords.argtypes = [_P, _I64, _F, _P]
     h.b200_host_pe_freq.restype = _F
     h.b200_host_pe_freq.argtypes = [C.c_int]

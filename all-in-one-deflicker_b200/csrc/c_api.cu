@@ -187,6 +187,12 @@ static int tc_architecture(const MlpShape& s) {
   return 0;
 }
 
+int b200_mlp_tc_architecture(const B200MlpDesc* d) {
+  MlpShape s;
+  if (resolve_mlp(d, &s) != B200_OK) return -1;
+  return tc_architecture(s);
+}
+
 // buffers of a stand-alone tensor-core call, carved from the caller's workspace
 struct TcCallPlan { int* gmax2; float* x; float* y; float* dy; float* d_in; char* tc; int64_t bytes; };
 static void plan_tc_call(const MlpShape& s, int arch, int64_t rows_pad, char* base, TcCallPlan* pl) {

@@ -277,6 +277,71 @@ int b200_render(const float* params, int32_t H, int32_t W, int32_t T, int32_t fr
                 void* ws, int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Segmentation variant of the loop — replaces src/stage1_neural_atlas_seg.py:207-315 +
+ * loss.backward(): foreground / background mapping networks, alpha network, one atlas network
+ * sampled in two quadrants (uv*0.5 +- 0.5); two-layer gradient loss (loss_utils.py:173-224),
+ * rigidity of both mappings (:227-278), alpha-weighted flow losses (:299-322, use_alpha=True),
+ * alpha flow loss (:385-408), bootstrapping BCE and sparsity (seg script :249-307).
+ * The four networks may have any IMLP shape; with precision == B200_PREC_TC each network whose
+ * shape has tensor-core kernels (b200_mlp_tc_architecture != 0) uses them, the others the fp32
+ * kernels.  Single device: the whole video must be resident (t_begin = 0, t_end = T).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct B200SegConfig {
+  int32_t batch;             /* samples_batch                                                  */
+  int32_t with_global;       /* include_global_rigidity_loss && i <= stop_global_rigidity      */
+  int32_t precision;         /* B200_PREC_*                                                    */
+  int32_t resx;              /* width (gradient-loss normalisation)                            */
+  float uv_mapping_scale;
+  float derivative_amount;
+  float global_derivative_amount;   /* global_rigidity_derivative_amount_fg == _bg (both 100 in the
+                                       reference's config; different values are not supported)  */
+  float rgb_coeff, gradient_coeff, rigidity_coeff;
+  float global_rigidity_coeff_fg, global_rigidity_coeff_bg;
+  float flow_coeff;          /* optical_flow_coeff                                             */
+  float alpha_flow_factor, sparsity_coeff;
+  float bootstrapping_factor;/* alpha_bootstrapping_factor, 0 after stop_bootstrapping_iteration */
+  B200MlpDesc mapping1, mapping2, alpha, atlas;
+} B200SegConfig;
+
+/* loss vector of b200_seg_loss_grad:
+ *   0 total  1 rgb  2 gradient  3 sparsity  4 rigidity1  5 rigidity2  6 global rigidity1
+ *   7 global rigidity2  8 flow1  9 flow2  10 flow alpha  11 bootstrapping  12 n_fwd  13 n_bwd    */
+#define B200_SEG_LOSS_FLOATS 16
+
+/* 1 = the mapping architecture, 2 = the atlas architecture of the stage-1 scripts (tensor-core
+ * kernels exist), 0 = any other shape (fp32 kernels only), -1 = invalid descriptor */
+int b200_mlp_tc_architecture(const B200MlpDesc* d);
+
+/* parameters / gradients / Adam moments are ONE flat buffer: the four networks in the order of
+ * the script's optimiser groups (mapping1, mapping2, alpha, atlas), each in b200_mlp_layout.
+ * Fills offsets[4] (floats) and returns the total, or -1. */
+int64_t b200_seg_param_floats(const B200SegConfig* cfg, int64_t* offsets);
+int64_t b200_seg_workspace_bytes(const B200SegConfig* cfg);
+
+/* mask: the bootstrapping mask as [T][H][W] fp32 (mask_frames[y, x, t] of load_input_data,
+ * unwrap_utils.py:40-72, frame-major).  grads and losses are overwritten. */
+int b200_seg_loss_grad(const B200SegConfig* cfg, const B200Video* video, const float* mask,
+                       const int64_t* indices, const float* params, float* grads, float* losses,
+                       void* ws, int64_t ws_bytes, void* stream);
+
+/* One pre_train_mapping step (unwrap_utils.py:182-195) for ANY mapping-shaped IMLP (3 -> 2):
+ * gradients of that network (its own flat layout, overwritten); loss -> losses[0]. */
+int64_t b200_mlp_pretrain_workspace_bytes(const B200MlpDesc* d, int32_t batch);
+int b200_mlp_pretrain_loss_grad(const B200MlpDesc* d, int32_t batch, float uv_mapping_scale,
+                                int32_t larger_dim, int32_t T, int32_t frame, const int64_t* ys,
+                                const int64_t* xs, const float* params, float* grads,
+                                float* losses, int precision, void* ws, int64_t ws_bytes,
+                                void* stream);
+
+/* Reconstruction of the seg variant (src/models/stage_1/evaluate.py:293-335): composite
+ * rgb = rgb1*alpha + rgb2*(1-alpha) and alpha for pixels [pix_begin, pix_end) of frame f.
+ * rgb [count][3], rgb_u8 (may be NULL), alpha [count] (may be NULL). */
+int64_t b200_seg_render_workspace_bytes(const B200SegConfig* cfg, int64_t pixels);
+int b200_seg_render(const B200SegConfig* cfg, const float* params, int32_t H, int32_t W, int32_t T,
+                    int32_t frame, int64_t pix_begin, int64_t pix_end, float* rgb,
+                    uint8_t* rgb_u8, float* alpha, void* ws, int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RAFT correlation — replaces CorrBlock (src/models/stage_1/core/corr.py:16-64); the reference's own
  * native hook for this operator is alt_cuda_corr.forward (corr.py:86-91, extension not shipped).
  * fmaps: [dim][H8*W8] fp32 (batch 1).  pyramid: level 0 [H8*W8][H8][W8], then 3 avg-pooled levels,
