@@ -102,6 +102,7 @@ SIGNATURES = {
     "b200_gradient_loss_head": (C.c_int, [_P] * 5 + [_I64] + [_P] * 5),
     "b200_rigidity_loss_head": (C.c_int, [_P, _P, _I64, _F, _F, _F, _P, _P, _P, _P, _P]),
     "b200_flow_loss_head": (C.c_int, [_P, _P, _I64, _F, _F, _P, _P, _P, _P]),
+    "b200_flow_loss_head_weighted": (C.c_int, [_P, _P, _P, _I64, _F, _F, _P, _P, _P, _P, _P]),
     "b200_producer_frame": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "b200_producer_scratch_floats": (_I64, [_I32, _I32]),
     "b200_producer_flow_pair": (C.c_int, [_P, _P] + [_I32] * 7 + [_P, _P, _P, _I32, _I32, _P, _P]),

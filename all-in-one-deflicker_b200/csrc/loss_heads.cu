@@ -94,6 +94,28 @@ __global__ void flow_head_kernel(const float* __restrict__ uv_rel, const float* 
   block_sum_to(part, loss, inv_n);
 }
 
+// mean_rows w * ||uv_match - uv_rel||_2 * resx / (2 uv_mapping_scale): the alpha-weighted form of the segmentation
+// variant (loss_utils.py:316-318, use_alpha=True); also d/d w
+__global__ void flow_head_weighted_kernel(const float* __restrict__ uv_rel, const float* __restrict__ uv_match,
+                                          const float* __restrict__ w, int64_t n, float L, float uv_scale, float inv_n,
+                                          float* __restrict__ loss, float* __restrict__ d_rel, float* __restrict__ d_match,
+                                          float* __restrict__ d_w) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float part[1] = {0.f};
+  if (s < n) {
+    const float u0[2] = {uv_rel[s * 2], uv_rel[s * 2 + 1]};
+    const float um[2] = {uv_match[s * 2], uv_match[s * 2 + 1]};
+    const float ws = w[s];
+    float g0[2] = {0.f, 0.f}, gm[2] = {0.f, 0.f};
+    const float l = flow_term(u0, um, L, uv_scale, inv_n * ws, g0, gm);
+    part[0] = l * ws;
+    d_rel[s * 2] = g0[0]; d_rel[s * 2 + 1] = g0[1];
+    d_match[s * 2] = gm[0]; d_match[s * 2 + 1] = gm[1];
+    d_w[s] = l * inv_n;
+  }
+  block_sum_to(part, loss, inv_n);
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -142,6 +164,25 @@ int b200_flow_loss_head(const float* uv_rel, const float* uv_match, int64_t n, f
   B200_CHECK_CUDA(cudaMemsetAsync(loss, 0, 4, st));
   flow_head_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(uv_rel, uv_match, n, resx, uv_mapping_scale,
                                                                 1.0f / (float)n, loss, d_uv_rel, d_uv_match);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int b200_flow_loss_head_weighted(const float* uv_rel, const float* uv_match, const float* w, int64_t n, float resx,
+                                 float uv_mapping_scale, float* loss, float* d_uv_rel, float* d_uv_match, float* d_w,
+                                 void* stream) {
+  B200_REQUIRE(loss, "null pointer");
+  B200_REQUIRE(n >= 0 && n < (1ll << 31), "row count out of range: %lld", (long long)n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    B200_CHECK_CUDA(cudaMemsetAsync(loss, 0xFF, 4, st));
+    return B200_OK;
+  }
+  B200_REQUIRE(uv_rel && uv_match && w && d_uv_rel && d_uv_match && d_w, "null pointer");
+  B200_REQUIRE(resx > 0.f && uv_mapping_scale != 0.f, "bad flow geometry");
+  B200_CHECK_CUDA(cudaMemsetAsync(loss, 0, 4, st));
+  flow_head_weighted_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(uv_rel, uv_match, w, n, resx, uv_mapping_scale,
+                                                                         1.0f / (float)n, loss, d_uv_rel, d_uv_match, d_w);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -1,6 +1,7 @@
-"""The three loss functions the non-segmentation stage-1 script calls, with the reference's signatures
+"""The loss functions the stage-1 scripts call, with the reference's signatures
 (src/models/stage_1/loss_utils.py:134 `get_gradient_loss_single`, :227 `get_rigidity_loss`,
-:299 `get_optical_flow_loss`), for callers that keep the reference's function-level structure.
+:299 `get_optical_flow_loss`; for the segmentation variant :173 `get_gradient_loss`, `use_alpha=True` of :299 and
+:385 `get_optical_flow_alpha_loss`), for callers that keep the reference's function-level structure.
 
 The training script of this repo does NOT go through these (it runs the whole iteration as one fused CUDA
 graph, b200.atlas.AtlasTrainer); they are the drop-in boundary: same arguments (CPU video tensors in the
@@ -91,6 +92,50 @@ class _FlowHead(torch.autograd.Function):
         return g * d_rel, g * d_match, None, None
 
 
+class _WeightedFlowHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uv_rel, uv_match, w, resx, uv_mapping_scale):
+        uv_rel, uv_match, w = uv_rel.contiguous().float(), uv_match.contiguous().float(), w.contiguous().float()
+        loss = torch.empty((), dtype=torch.float32, device=uv_match.device)
+        d_rel, d_match, d_w = torch.zeros_like(uv_rel), torch.zeros_like(uv_match), torch.zeros_like(w)
+        N.check(N.lib().b200_flow_loss_head_weighted(N.ptr(uv_rel), N.ptr(uv_match), N.ptr(w), uv_rel.shape[0],
+                                                     float(resx), float(uv_mapping_scale), N.ptr(loss), N.ptr(d_rel),
+                                                     N.ptr(d_match), N.ptr(d_w), N.current_stream()),
+                "b200_flow_loss_head_weighted")
+        ctx.save_for_backward(d_rel, d_match, d_w)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d_rel, d_match, d_w = ctx.saved_tensors
+        return g * d_rel, g * d_match, g * d_w, None, None
+
+
+def _alpha_of(raw):
+    """tanh output of the alpha network -> (0.001, 0.991), the three steps of loss_utils.py:186-192."""
+    a = 0.5 * (raw + 1.0)
+    a = a * 0.99
+    return a + 0.001
+
+
+def get_gradient_loss(video_frames_dx, video_frames_dy, jif_current, model_F_mapping1, model_F_mapping2, model_F_atlas,
+                      rgb_output_foreground, device, resx, number_of_frames, model_alpha):
+    """Two-layer form of Eq. 7 (reference :173-224): the shifted reconstructions are alpha composites of the two
+    atlas layers.  Each network sees both offsets in one call; the composite of (rows, 3) tensors is elementwise glue,
+    the loss and its gradient come from the same head as the single-layer form."""
+    cols = (jif_current[0, :], jif_current[1, :], jif_current[2, :])
+    n = cols[0].shape[0]
+    pts = torch.cat((_norm_rows(cols, resx, number_of_frames, (1, 0, 0)),
+                     _norm_rows(cols, resx, number_of_frames, (0, 1, 0)))).to(device)
+    a = _alpha_of(model_alpha(pts))
+    rgb1 = (model_F_atlas(model_F_mapping1(pts) * 0.5 + 0.5) + 1.0) * 0.5
+    rgb2 = (model_F_atlas(model_F_mapping2(pts) * 0.5 - 0.5) + 1.0) * 0.5
+    out = rgb1 * a + rgb2 * (1.0 - a)
+    dx_gt = _dev(video_frames_dx[cols[1], cols[0], :, cols[2]].squeeze(1), device)
+    dy_gt = _dev(video_frames_dy[cols[1], cols[0], :, cols[2]].squeeze(1), device)
+    return _GradientHead.apply(rgb_output_foreground, out[:n], out[n:], dx_gt, dy_gt)
+
+
 def get_gradient_loss_single(video_frames_dx, video_frames_dy, jif_current, model_F_mapping1, model_F_atlas,
                              rgb_output_foreground, device, resx, number_of_frames):
     """Eq. 7: image-gradient consistency for one mapping network (reference :134-170)."""
@@ -131,8 +176,8 @@ def _flow_direction(jif, uv, mask, flows, resx, number_of_frames, forward, model
     if rows.numel() == 0:
         return _FlowHead.apply(uv[rows_d], uv.new_zeros((0, 2)), resx, uv_mapping_scale), rows_d
     uv_match = model_F_mapping(pts.to(device=device, dtype=torch.float32))
-    if alpha is not None:
-        raise NotImplementedError("use_alpha=True belongs to the segmentation variant (stage1_neural_atlas_seg.py)")
+    if alpha is not None:          # (loss * alpha[rows].squeeze()).mean(), loss_utils.py:316-318
+        return _WeightedFlowHead.apply(uv[rows_d], uv_match, alpha[rows_d].reshape(-1), resx, uv_mapping_scale), rows_d
     return _FlowHead.apply(uv[rows_d], uv_match, resx, uv_mapping_scale), rows_d
 
 
@@ -146,3 +191,29 @@ def get_optical_flow_loss(jif_foreground, uv_foreground, optical_flows_reverse, 
     prv, _ = _flow_direction(jif_foreground, uv_foreground, optical_flows_reverse_mask, optical_flows_reverse, resx,
                              number_of_frames, False, model_F_mapping, uv_mapping_scale, device, a)
     return prv * 0.5 + nxt * 0.5
+
+
+def _alpha_direction(jif, mask, flows, resx, number_of_frames, forward, model_alpha, device):
+    """Alpha at the flow-matched points of one direction (get_corresponding_flow_matches with use_uv=False)."""
+    x, y, t = jif[0, :].squeeze(), jif[1, :].squeeze(), jif[2, :].squeeze()
+    rows, level = torch.where(mask[y, x, t, :])
+    step = 2 ** level
+    xs, ys, ts = x[rows], y[rows], t[rows]
+    fl = flows[ys, xs, :, ts, level]
+    mt = ts + step if forward else ts - step
+    pts = torch.stack(((xs + fl[:, 0]) / (resx / 2) - 1, (ys + fl[:, 1]) / (resx / 2) - 1,
+                       mt / (number_of_frames / 2) - 1)).T
+    return _alpha_of(model_alpha(pts.to(device=device, dtype=torch.float32))), rows.to(device)
+
+
+def get_optical_flow_alpha_loss(model_alpha, jif_foreground, alpha, optical_flows_reverse, optical_flows_reverse_mask,
+                                resx, number_of_frames, optical_flows, optical_flows_mask, device):
+    """Eq. 12: alpha of flow-matched points should agree (reference :385-408).  The network evaluations run in the
+    library; the L1 mean of two (rows, 1) tensors is elementwise glue."""
+    a_f, rows_f = _alpha_direction(jif_foreground, optical_flows_mask, optical_flows, resx, number_of_frames, True,
+                                   model_alpha, device)
+    nxt = (alpha[rows_f] - a_f).abs().mean()
+    a_b, rows_b = _alpha_direction(jif_foreground, optical_flows_reverse_mask, optical_flows_reverse, resx,
+                                   number_of_frames, False, model_alpha, device)
+    prv = (a_b - alpha[rows_b]).abs().mean()
+    return (nxt + prv) * 0.5

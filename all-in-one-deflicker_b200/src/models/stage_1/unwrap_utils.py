@@ -2,8 +2,8 @@
 
 `load_input_data_single` is the input producer (reads frames + RAFT flows from disk, CPU, same tensor
 layouts as the reference returns); `get_tuples` and `pre_train_mapping` are provided for drop-in use,
-the latter running on the fused trainer.  The visualisation helper `save_mask_flow` (imageio mp4s) is
-out of scope.
+the latter running on the fused trainer.  `load_input_data` is the segmentation variant's loader (adds the
+bootstrapping masks).  The visualisation helper `save_mask_flow` (imageio mp4s) is out of scope.
 """
 import numpy as np
 import torch
@@ -75,6 +75,33 @@ def load_input_data_single(resy, resx, maximum_number_of_frames, data_folder, us
     return flows_mask, frames, flows_rev_mask, mask_frames, dx, dy, flows_rev, flows
 
 
+def load_mask_frames(resy, resx, number_of_frames, vid_root, vid_name):
+    """(resy, resx, T) bootstrapping masks from `<vid>_seg` (unwrap_utils.py:43,60,67-70).  The reference passes
+    cv2.INTER_NEAREST in the position of cv2.resize's `dst` argument, which OpenCV ignores: the masks are resized
+    with the default bilinear interpolation, and so they are here."""
+    mask_dir = vid_root / f'{vid_name}_seg'
+    files = sorted(list(mask_dir.glob('*.jpg')) + list(mask_dir.glob('*.png')))
+    if len(files) < number_of_frames:
+        raise FileNotFoundError(f"{mask_dir}: {len(files)} mask images for {number_of_frames} frames — the segmentation "
+                                f"variant needs one matte per frame (the reference writes them with "
+                                f"src/preprocess_mask_portrait.py / preprocess_mask_rcnn.py)")
+    masks = torch.zeros((resy, resx, number_of_frames))
+    for i in range(number_of_frames):
+        m = np.array(Image.open(str(files[i]))).astype(np.float64) / 255.
+        masks[:, :, i] = torch.from_numpy(cv2.resize(m, (resx, resy), interpolation=cv2.INTER_LINEAR))
+    return masks
+
+
+def load_input_data(resy, resx, maximum_number_of_frames, data_folder, use_mask_rcnn_bootstrapping, filter_optical_flow,
+                    vid_root, vid_name):
+    """Same return tuple as unwrap_utils.py:40-103: `load_input_data_single` plus the masks of `<vid>_seg`."""
+    out = list(load_input_data_single(resy, resx, maximum_number_of_frames, data_folder, use_mask_rcnn_bootstrapping,
+                                      filter_optical_flow, vid_root, vid_name))
+    if use_mask_rcnn_bootstrapping:
+        out[3] = load_mask_frames(resy, resx, out[1].shape[3], vid_root, vid_name)
+    return tuple(out)
+
+
 def get_tuples(number_of_frames, video_frames):
     """(3, N) int64 [x; y; t] table (unwrap_utils.py:166-173).  The CUDA path never materialises it: the
     kernels decode n -> (n % W, (n // W) % H, n // (H*W)); this is for callers that want the tensor."""
@@ -83,9 +110,14 @@ def get_tuples(number_of_frames, video_frames):
     return torch.stack((n % W, (n // W) % H, n // (H * W)))
 
 
-def pre_train_mapping(trainer, frames_num, uv_mapping_scale, resx, resy, larger_dim, device, pretrain_iters=100):
-    """unwrap_utils.py:176-198 on the fused trainer (`b200.atlas.AtlasTrainer`)."""
+def pre_train_mapping(trainer, frames_num, uv_mapping_scale, resx, resy, larger_dim, device, pretrain_iters=100,
+                      which=None):
+    """unwrap_utils.py:176-198 on the fused trainer (`b200.atlas.AtlasTrainer`), or on one mapping network of the
+    segmentation trainer (`b200.seg.SegTrainer`, which = "mapping1" | "mapping2")."""
     print("pre-training")
     trainer.cfg["uv_mapping_scale"] = uv_mapping_scale
-    trainer.pretrain(frames_num, resy, resx, pretrain_iters)
+    if which is None:
+        trainer.pretrain(frames_num, resy, resx, pretrain_iters)
+    else:
+        trainer.pretrain(which, frames_num, resy, resx, pretrain_iters)
     return trainer

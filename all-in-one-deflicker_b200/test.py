@@ -60,11 +60,9 @@ if __name__ == "__main__":
         stage1 = [sys.executable, os.path.join(HERE, "src", "stage1_neural_atlas.py"), "--vid_name", name,
                   "--gpu", str(args.gpu)]
     else:
-        seg = os.path.join(HERE, "src", "stage1_neural_atlas_seg.py")
-        if not os.path.exists(seg):
-            raise NotImplementedError("--class_name selects the segmentation variant (src/stage1_neural_atlas_seg.py), "
-                                      "which this build does not ship (SURVEY.md §8f rank 3)")
-        stage1 = [sys.executable, seg, "--vid_name", name, "--class_name", args.class_name, "--gpu", str(args.gpu)]
+        # the two-layer variant (reference test.py:39); it needs the mattes of data/test/<name>_seg
+        stage1 = [sys.executable, os.path.join(HERE, "src", "stage1_neural_atlas_seg.py"), "--vid_name", name,
+                  "--class_name", args.class_name, "--gpu", str(args.gpu)]
     rc = subprocess.call(stage1)
     if rc != 0:
         sys.exit(rc)

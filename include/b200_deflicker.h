@@ -254,6 +254,11 @@ int b200_rigidity_loss_head(const float* uv, const float* uv_p, int64_t n, float
 int b200_flow_loss_head(const float* uv_rel, const float* uv_match, int64_t n, float resx,
                         float uv_mapping_scale, float* loss, float* d_uv_rel, float* d_uv_match,
                         void* stream);
+/* the use_alpha=True form (loss_utils.py:316-318, segmentation variant): mean_rows w * ||.|| * resx /
+ * (2 uv_mapping_scale) with per-row weights w [n] (alpha or 1 - alpha of the row's sample); d_w = dL/dw */
+int b200_flow_loss_head_weighted(const float* uv_rel, const float* uv_match, const float* w,
+                                 int64_t n, float resx, float uv_mapping_scale, float* loss,
+                                 float* d_uv_rel, float* d_uv_match, float* d_w, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimiser — replaces torch.optim.Adam.step() (src/stage1_neural_atlas.py:132-134,231) on a

@@ -66,3 +66,20 @@ def test_frame_cap_and_unfiltered_masks(golden_dir, tmp_path):
     # filter_optical_flow=False: every pair with a partner frame is valid (that branch of the reference raises)
     allv = mod.load_input_data_single(int(z["resy"]), int(z["resx"]), 200, folder, True, False, folder.parent, "vid")
     assert float(allv[0][:, :, :T - 1].min()) == 1.0 and float(allv[0][:, :, T - 1].max()) == 0.0
+
+
+def test_seg_loader_mattes_bit_exact(golden_dir, tmp_path):
+    """`load_input_data` (reference unwrap_utils.py:40-103): the seven tensors of the single-layer loader plus the
+    mattes of `<vid>_seg`, resized bilinearly (the reference's INTER_NEAREST lands in cv2.resize's `dst` slot)."""
+    z = np.load(os.path.join(golden_dir, "loader.npz"))
+    zs = np.load(os.path.join(golden_dir, "loader_seg.npz"))
+    folder, T = _write(tmp_path, z)
+    seg = Path(tmp_path) / "vid_seg"
+    seg.mkdir()
+    for i in range(T):
+        Image.fromarray(zs[f"matte{i}"]).save(str(seg / ("%05d.png" % i)))
+    got = _loader().load_input_data(int(z["resy"]), int(z["resx"]), 200, folder, True, True, folder.parent, "vid")
+    for name, t in zip(NAMES, got):
+        want = torch.from_numpy(zs["want_mask_frames"] if name == "mask_frames" else z["want_" + name])
+        assert torch.equal(t, want), name
+    assert len(np.unique(got[3].numpy())) > 8

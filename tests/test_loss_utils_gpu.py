@@ -117,3 +117,76 @@ def test_optical_flow_loss_empty_set_is_nan(golden_dir):
     got = LU.get_optical_flow_loss(jif, m(xyt.to(DEV)), data["flow_bwd"], data["mask_bwd"], max(H, W), T, m,
                                    data["flow_fwd"], data["mask_fwd"], 0.8, DEV)
     assert torch.isnan(got)                      # mean over an empty set, as the reference (loss_utils.py:320-322)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# segmentation-variant functions (reference loss_utils.py:173-224, :299-322 with use_alpha=True, :385-408)
+# ---------------------------------------------------------------------------------------------------------------
+def _seg_setup(golden_dir, B=64):
+    from oracle import seg_oracle as S
+    from seg_common import ORDER, load_fixture
+    from src.models.stage_1.implicit_neural_networks import IMLP
+    z, video, masks, nets = load_fixture(golden_dir)
+    ref = {k: [p.clone().requires_grad_(True) for p in nets[k]] for k in ORDER}
+    mods = dict(
+        mapping1=IMLP(input_dim=3, output_dim=2, hidden_dim=256, use_positional=False, positional_dim=4, num_layers=6,
+                      skip_layers=[], verbose=False),
+        mapping2=IMLP(input_dim=3, output_dim=2, hidden_dim=256, use_positional=False, positional_dim=2, num_layers=4,
+                      skip_layers=[], verbose=False),
+        atlas=IMLP(input_dim=2, output_dim=3, hidden_dim=256, use_positional=True, positional_dim=10, num_layers=8,
+                   skip_layers=[4, 7], verbose=False),
+        alpha=IMLP(input_dim=3, output_dim=1, hidden_dim=256, use_positional=True, positional_dim=5, num_layers=8,
+                   skip_layers=[], verbose=False))
+    for k in ORDER:
+        mods[k].load_state_dict(O.state_dict_of(nets[k]))
+        mods[k] = mods[k].to(DEV)
+    specs = dict(mapping1=S.MAPPING1_SPEC, mapping2=S.MAPPING2_SPEC, alpha=S.ALPHA_SPEC, atlas=S.ATLAS_SPEC)
+    onet = {k: (lambda x, k=k: O.mlp_forward(specs[k], ref[k], x)) for k in ORDER}
+    inds = torch.from_numpy(z["inds"])
+    jif = O.pixel_table(video.T, video.H, video.W)[:, inds]
+    xyt = O.normalise_xyt(jif, max(video.H, video.W), video.T)
+    return S, video, jif, xyt, ref, onet, mods
+
+
+def test_seg_gradient_loss(golden_dir):
+    from src.models.stage_1 import loss_utils as LU
+    S, video, jif, xyt, ref, onet, mods = _seg_setup(golden_dir)
+    a_o = S.alpha_of(onet["alpha"](xyt))
+    out_o = (onet["atlas"](onet["mapping1"](xyt) * 0.5 + 0.5) + 1.0) * 0.5 * a_o \
+        + (onet["atlas"](onet["mapping2"](xyt) * 0.5 - 0.5) + 1.0) * 0.5 * (1.0 - a_o)
+    want = S.gradient_loss_seg(video, jif, onet["mapping1"], onet["mapping2"], onet["atlas"], onet["alpha"], out_o, video.W)
+    want.backward()
+    x = xyt.to(DEV)
+    a = LU._alpha_of(mods["alpha"](x))
+    out = (mods["atlas"](mods["mapping1"](x) * 0.5 + 0.5) + 1.0) * 0.5 * a \
+        + (mods["atlas"](mods["mapping2"](x) * 0.5 - 0.5) + 1.0) * 0.5 * (1.0 - a)
+    got = LU.get_gradient_loss(video.frames_dx, video.frames_dy, jif, mods["mapping1"], mods["mapping2"], mods["atlas"],
+                               out, DEV, video.W, video.T, mods["alpha"])
+    np.testing.assert_allclose(float(got), float(want), rtol=2e-5)
+    got.backward()
+    for k in ("mapping1", "mapping2", "atlas", "alpha"):
+        _check_grads(ref[k], mods[k], f"seg gradient/{k}")
+
+
+def test_seg_alpha_weighted_flow_and_alpha_flow(golden_dir):
+    from src.models.stage_1 import loss_utils as LU
+    S, video, jif, xyt, ref, onet, mods = _seg_setup(golden_dir)
+    L = max(video.H, video.W)
+    a_o = S.alpha_of(onet["alpha"](xyt))
+    want = S.flow_loss_alpha(video, jif, onet["mapping1"](xyt), L, onet["mapping1"], 0.8, a_o) \
+        + S.flow_loss_alpha(video, jif, onet["mapping2"](xyt), L, onet["mapping2"], 0.8, 1 - a_o) \
+        + 10.0 * S.flow_alpha_loss(video, jif, a_o, L, onet["alpha"])
+    want.backward()
+    x = xyt.to(DEV)
+    a = LU._alpha_of(mods["alpha"](x))
+    f1 = LU.get_optical_flow_loss(jif, mods["mapping1"](x), video.flow_bwd, video.mask_bwd, L, video.T, mods["mapping1"],
+                                  video.flow_fwd, video.mask_fwd, 0.8, DEV, use_alpha=True, alpha=a)
+    f2 = LU.get_optical_flow_loss(jif, mods["mapping2"](x), video.flow_bwd, video.mask_bwd, L, video.T, mods["mapping2"],
+                                  video.flow_fwd, video.mask_fwd, 0.8, DEV, use_alpha=True, alpha=1 - a)
+    fa = LU.get_optical_flow_alpha_loss(mods["alpha"], jif, a, video.flow_bwd, video.mask_bwd, L, video.T,
+                                        video.flow_fwd, video.mask_fwd, DEV)
+    got = f1 + f2 + 10.0 * fa
+    np.testing.assert_allclose(float(got), float(want), rtol=2e-5)
+    got.backward()
+    for k in ("mapping1", "mapping2", "alpha"):
+        _check_grads(ref[k], mods[k], f"seg flow/{k}")

@@ -78,3 +78,51 @@ def test_scripts_end_to_end(tmp_path):
     import cv2
     img = cv2.imread(sorted(glob.glob(str(work / "results" / vid / "final" / "output" / "*.png")))[-1])
     assert img.shape == (128, 192, 3)
+
+
+def test_seg_script_end_to_end(tmp_path):
+    """`python src/stage1_neural_atlas_seg.py --vid_name ... --class_name ...` (reference test.py:39) on a tiny clip with
+    synthetic mattes: flow pre-pass, pre-training of both mappings, 201 iterations, checkpoint keys of
+    evaluate.py:216-223, composite frames, alpha mattes, PSNR marker."""
+    import cv2
+    work = tmp_path
+    vid = "tinyseg"
+    T, H, W = 5, 96, 128
+    _write_video(str(work / "data" / "test" / vid), T=T, H=H, W=W)
+    seg_dir = str(work / "data" / "test" / (vid + "_seg"))
+    os.makedirs(seg_dir)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for t in range(T):
+        m = (np.hypot(yy - H * 0.5, xx - W * (0.35 + 0.05 * t)) < H * 0.3).astype(np.uint8) * 255
+        cv2.imwrite(os.path.join(seg_dir, "%05d.png" % t), m)
+    cfg = json.load(open(os.path.join(PKG, "src", "config", "config_flow_100.json")))
+    cfg.update(iters_num=201, evaluate_every=200, pretrain_iter_number=2, samples_batch=1500, stop_global_rigidity=100,
+               stop_bootstrapping_iteration=150)
+    cfg_path = str(work / "cfg.json")
+    json.dump(cfg, open(cfg_path, "w"))
+    env = dict(os.environ, PYTHONPATH=PKG, B200_ALLOW_RANDOM_RAFT="1")
+    r = subprocess.run([sys.executable, os.path.join(PKG, "src", "stage1_neural_atlas_seg.py"), "--vid_name", vid, "--root",
+                        "data/test/", "--down", "1", "--class_name", "person", "--config", cfg_path], cwd=str(work), env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = work / "results" / vid / "stage_1"
+    ck = torch.load(str(res / "checkpoint"), weights_only=False)
+    assert set(ck) == {"F_atlas_state_dict", "iteration", "model_F_mapping1_state_dict", "model_F_mapping2_state_dict",
+                       "model_F_alpha_state_dict", "optimizer_all_state_dict"}
+    assert ck["iteration"] == 200 and len(ck["model_F_mapping2_state_dict"]) == 8 and len(ck["model_F_alpha_state_dict"]) == 16
+    assert ck["model_F_alpha_state_dict"]["hidden.0.weight"].shape == (256, 30)
+    assert len(ck["optimizer_all_state_dict"]["param_groups"]) == 4
+    assert len(glob.glob(str(res / "output" / "*.png"))) == T
+    alphas = sorted(glob.glob(str(res / "000200" / "alpha" / "*.png")))
+    assert len(alphas) == T
+    a = cv2.imread(alphas[2], cv2.IMREAD_GRAYSCALE).astype(np.float64) / 255
+    gt = cv2.imread(os.path.join(seg_dir, "00002.png"), cv2.IMREAD_GRAYSCALE) > 127
+    assert a[gt].mean() > a[~gt].mean() + 0.2          # 150 bootstrapped iterations already separate the matte
+    marker = glob.glob(str(res / "000200" / "PSNR_*"))
+    assert len(marker) == 1 and np.isfinite(float(os.path.basename(marker[0])[len("PSNR_"):]))
+    # a missing matte folder is refused loudly
+    os.rename(seg_dir, seg_dir + "_gone")
+    r = subprocess.run([sys.executable, os.path.join(PKG, "src", "stage1_neural_atlas_seg.py"), "--vid_name", vid, "--root",
+                        "data/test/", "--class_name", "person", "--config", cfg_path], cwd=str(work), env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "holds no mattes" in r.stderr

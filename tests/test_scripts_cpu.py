@@ -27,12 +27,15 @@ def test_flow_prepass_refuses_random_weights(tmp_path):
     assert not any(f.endswith(".npy") for f in os.listdir(str(tmp_path / "vid_flow")))
 
 
-def test_driver_moves_frames_and_rejects_unbuilt_variant(tmp_path):
+def test_driver_moves_frames_and_runs_seg_variant(tmp_path):
     _frames(str(tmp_path / "clip"))
-    seg = os.path.join(PKG, "src", "stage1_neural_atlas_seg.py")
+    env = dict(os.environ)
+    env.pop("B200_ALLOW_RANDOM_RAFT", None)
     r = subprocess.run([sys.executable, os.path.join(PKG, "test.py"), "--video_frame_folder", "clip", "--class_name",
-                        "person"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+                        "person"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
     # the frame folder is moved to ./data/test/<name> as the reference does (test.py:24-31) ...
     assert os.path.isdir(str(tmp_path / "data" / "test" / "clip")) and not os.path.exists(str(tmp_path / "clip"))
-    if not os.path.exists(seg):          # ... and the segmentation variant is refused loudly, never silently ignored
-        assert r.returncode != 0 and "NotImplementedError" in r.stderr
+    # ... and --class_name starts the segmentation variant (reference test.py:39), which stops loudly at the first
+    # missing input (here the RAFT checkpoint of its flow pre-pass), never silently falling back to one layer
+    assert r.returncode != 0 and "stage1_neural_atlas_seg.py" in (r.stdout + r.stderr)
+    assert "raft-things.pth is missing" in r.stderr or "optical-flow pre-pass failed" in r.stderr
