@@ -176,7 +176,8 @@ int64_t b200_mlp_layout(const B200MlpDesc* d, int64_t* w_off, int64_t* b_off) {
 // 2 atlas, 0 neither
 static int tc_architecture(const MlpShape& s) {
   if (s.hidden != 256) return 0;
-  if (s.L == 6 && s.pe == 0 && s.in_dim == 3 && s.out_dim == 2) {
+  if ((s.L == 6 || s.L == 4) && s.pe == 0 && s.in_dim == 3 && s.out_dim == 2) {     // 6: the stage-1 scripts' mapping; 4: the
+    // background mapping of the segmentation variant (same kernels, two hidden 256x256 layers instead of four)
     for (int l = 1; l < s.L; ++l) if (s.skip[l]) return 0;
     return 1;
   }
@@ -224,7 +225,7 @@ static int tc_call_prepare(const B200MlpDesc* d, int64_t rows, void* ws, int64_t
                            int64_t* rows_pad, TcCallPlan* pl) {
   B200_PROPAGATE(resolve_mlp(d, s));
   *arch = tc_architecture(*s);
-  B200_REQUIRE(*arch != 0, "B200_PREC_TC serves the two stage-1 architectures (mapping: 3-256x4-2 without encoding; "
+  B200_REQUIRE(*arch != 0, "B200_PREC_TC serves the stage-1 architectures (mapping: 3-256x{2,4}-2 without encoding; "
                "atlas: 2-PE10-256x6-3 with skips 4, 7); use B200_PREC_FP32 for other shapes");
   if (!b200_device_supports_tc()) { set_error("B200_PREC_TC needs a compute-capability 10.x device"); return B200_ERR_UNSUPPORTED; }
   B200_REQUIRE(rows > 0 && rows < (1ll << 26), "rows out of range: %lld", (long long)rows);

@@ -396,13 +396,13 @@ struct FwdParams {
 // 64-column k chunk at a time (a_ready[kc]: chunks 0, 1 after the block-0 half of the epilogue, 2, 3 after the
 // block-1 half) and the MMA warp consumes them in that order, so the tensor pipe works on layer l+1 underneath the
 // epilogue of layer l.
-template <bool ATLAS>
+template <bool ATLAS, int NL = (ATLAS ? 8 : 6)>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(1024) char smem_raw[];
   constexpr int NST = KCfg<ATLAS>::NST;
   SmemMap<NST, ATLAS> sm; sm.init(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int L = ATLAS ? 8 : 6;
+  constexpr int L = NL;                                   // mapping-shaped networks: 6 (stage-1 script) or 4 layers
   constexpr int FIRST_TC = ATLAS ? 0 : 1;
   constexpr int LAST_TC = L - 2;
   constexpr int OUT = ATLAS ? 3 : 2;
@@ -728,13 +728,13 @@ __device__ __forceinline__ void grad_scales(const int* gmax_bits, bool mapping, 
   inv_sg = ldexpf(1.0f, e - 13);                        // (conversions saturate), small entries keep their lo term
 }
 
-template <bool ATLAS>
+template <bool ATLAS, int NL = (ATLAS ? 8 : 6)>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) char smem_raw[];
   constexpr int NST = KCfg<ATLAS>::NST;
   SmemMap<NST, ATLAS> sm; sm.init(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int L = ATLAS ? 8 : 6;
+  constexpr int L = NL;                                   // mapping-shaped networks: 6 (stage-1 script) or 4 layers
   constexpr int OUT = ATLAS ? 3 : 2;
   constexpr int KLAST = ATLAS ? 296 : 256;
   constexpr int LOW = 1;                                  // dgrad layers L-2 .. 1 (atlas: + the dPE product)
@@ -1205,6 +1205,8 @@ static int ensure_attrs() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   done = true;
   return B200_OK;
@@ -1598,8 +1600,9 @@ static int check_single(const MlpShape& sh, bool is_atlas, int64_t rows, cudaStr
   B200_PROPAGATE(ensure_attrs());
   if (is_atlas) B200_REQUIRE(sh.L == 8 && sh.skip[4] && sh.skip[7] && sh.pe == 10 && sh.hidden == HID && sh.in_dim == 2 &&
                              sh.out_dim == 3, "tensor-core IMLP: not the atlas architecture");
-  else B200_REQUIRE(sh.L == 6 && sh.pe == 0 && sh.hidden == HID && sh.in_dim == 3 && sh.out_dim == 2 && !sh.skip[1] &&
-                    !sh.skip[2] && !sh.skip[3] && !sh.skip[4] && !sh.skip[5], "tensor-core IMLP: not the mapping architecture");
+  else B200_REQUIRE((sh.L == 6 || sh.L == 4) && sh.pe == 0 && sh.hidden == HID && sh.in_dim == 3 && sh.out_dim == 2 &&
+                    !sh.skip[1] && !sh.skip[2] && !sh.skip[3] && !sh.skip[4] && !sh.skip[5],
+                    "tensor-core IMLP: not a mapping architecture (3 -> 256 x {2,4} -> 2, no encoding, no skips)");
   B200_REQUIRE(rows > 0 && rows % TM == 0 && rows / TM < (1 << 20), "rows must be a positive multiple of %d", TM);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);
@@ -1624,6 +1627,7 @@ int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, co
   P.in_scale = 1.0f; P.in_shift = 0.0f; P.store_images = training ? 1 : 0; P.tanh_out = sh.tanh_out ? 1 : 0;
   const int grid = min(sm_count(), (int)(rows / TM));
   if (is_atlas) tc_fwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  else if (sh.L == 4) tc_fwd_kernel<false, 4><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   else tc_fwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -1650,6 +1654,7 @@ int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, f
   for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
   const int grid = min(sm_count(), (int)(rows / TM));
   if (is_atlas) tc_bwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  else if (sh.L == 4) tc_bwd_kernel<false, 4><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   else tc_bwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   B200_CHECK_LAUNCH();
   tc_wgrad_kernel<<<min(wi.n, sm_count()), WG_THREADS, WG_SMEM, st>>>(pl.d_wg, nullptr, gmax2);

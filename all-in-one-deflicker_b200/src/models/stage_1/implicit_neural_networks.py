@@ -61,20 +61,14 @@ class IMLP(nn.Module):
         if apply_softmax:
             raise NotImplementedError("apply_softmax is unused by the stage-1 scripts and not provided")
         self.verbose, self.use_tanh = verbose, use_tanh
-        # The two architectures of the stage-1 scripts (src/stage1_neural_atlas.py:112-128) have tcgen05 kernels:
-        # 1 = mapping (3 -> 256 x 4 -> 2, no encoding), 2 = atlas (2 -> PE 10 -> 256 x 6 -> 3, skips 4 and 7)
-        self._tc_arch = 0
-        if hidden_dim == 256 and not use_positional and input_dim == 3 and output_dim == 2 and num_layers == 6 \
-                and not [k for k in skip_layers if 0 < k < num_layers]:
-            self._tc_arch = 1
-        if hidden_dim == 256 and use_positional and positional_dim == 10 and input_dim == 2 and output_dim == 3 \
-                and num_layers == 8 and sorted(k for k in skip_layers if 0 < k < num_layers) == [4, 7]:
-            self._tc_arch = 2
         self.skip_layers, self.num_layers = list(skip_layers), num_layers
         self.positional_dim, self.use_positional = positional_dim, use_positional
         self._desc = A.make_desc(input_dim, output_dim, hidden_dim, num_layers,
                                  positional_dim if use_positional else 0, self.skip_layers, use_tanh)
         self._w_off, self._b_off, self._total = A.mlp_layout(self._desc)
+        # architectures of the stage-1 scripts with tcgen05 kernels (the library decides): 1 = mapping-shaped
+        # (3 -> 256 x {2,4} -> 2, no encoding), 2 = atlas (2 -> PE 10 -> 256 x 6 -> 3, skips 4 and 7), 0 = fp32 kernels only
+        self._tc_arch = max(0, int(N.lib().b200_mlp_tc_architecture(C.byref(self._desc))))
         # one flat fp32 buffer in the library's layout; the per-layer tensors are views of it
         self.flat = nn.Parameter(torch.zeros(self._total))
         for i, (k, n) in enumerate(A.layer_dims(self._desc)):

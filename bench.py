@@ -3,7 +3,7 @@
 768x432, 10 000 points per iteration) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision tc|fp32]
-                    [--workload atlas|raft|stage2]
+                    [--workload atlas|raft|stage2|seg]
 
 One "step" = one loop trip of src/stage1_neural_atlas.py:151-231 (sampling, 7 mapping + 3 atlas
 evaluations, 4 losses, backward, Adam).  Prints ONE JSON line on rank 0.  Keys beyond the driver's
@@ -19,7 +19,8 @@ contract:
   e2e           same metric through AtlasTrainer.step_host: pinned H2D of the index batch + D2H of
                 the loss vector + sync every step
   pretrain_steps_per_s, render_s   the two other loops of a stage-1 run (pre_train_mapping, full render)
-`--workload raft|stage2` times BASELINE.json configs[3]/[4] (1080p) with the same line format.
+`--workload raft|stage2` times BASELINE.json configs[3]/[4] (1080p) with the same line format; `--workload seg` the
+segmentation variant of the stage-1 loop at the headline geometry.
 """
 import argparse
 import json
@@ -219,7 +220,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="atlas", choices=["atlas", "raft", "stage2"])
+    ap.add_argument("--workload", default="atlas", choices=["atlas", "raft", "stage2", "seg"])
     ap.add_argument("--precision", default=os.environ.get("B200_PRECISION", "auto"), choices=["auto", "tc", "fp32"])
     ap.add_argument("--cpu-sample-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -192,10 +192,98 @@ def _reference_line(args):
                       "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def seg_line(args, rank, world, local):
+    """`bench.py --workload seg`: the segmentation variant of the stage-1 loop at the headline geometry
+    (80 x 432 x 768, 10 000 samples per iteration, config_flow_100.json), one GPU.  A step = one loop trip
+    (b200_seg_loss_grad + b200_adam_step).  `--impl reference` / cpu_baseline: oracle/seg_oracle.py on the host cores,
+    a bounded sample of whole iterations."""
+    import time
+    from b200 import synth
+    T, H, W, B = 80, 432, 768, 10000
+    config = {"workload": "stage-1 atlas loop, segmentation variant (two mappings + alpha + atlas), 80 frames 768x432, "
+                          "10000 samples/iter, config_flow_100.json coefficients", "frames": T, "height": H, "width": W,
+              "samples_batch": B, "regime": "first half of the timed steps with the global rigidity terms, second half without",
+              "l2": "per-step working set (~2 GB of activations) exceeds the 126 MB L2"}
+    metric, unit = "seg_iterations_per_sec", "it/s"
+    data = synth.throughput_set(H, W, T, seed=0)
+    gm = torch.Generator().manual_seed(2)
+    masks = (torch.rand(H, W, T, generator=gm) < 0.4).float()
+
+    def cpu_leg(n_steps, threads):
+        from oracle import atlas_oracle as O, seg_oracle as S
+        torch.set_num_threads(threads)
+        video = O.Video(**data)
+        torch.manual_seed(0)
+        nets = {k: [p.requires_grad_(True) for p in v] for k, v in S.init_nets().items()}
+        opt = S.make_optimizer(nets)
+        g = torch.Generator().manual_seed(1)
+        total = 0.0
+        for i in range(1 + n_steps):
+            inds = torch.randint(H * W * T, (B, 1), generator=g)
+            t0 = time.perf_counter()
+            terms = S.seg_iteration_losses(video, masks, nets, inds, 0 if i <= n_steps // 2 else 6000)
+            opt.zero_grad(); terms["total"].backward(); opt.step()
+            if i >= 1:
+                total += time.perf_counter() - t0
+        return n_steps / total
+
+    cores = os.cpu_count() or 1
+    threads = min(cores, 32)
+    if args.impl == "reference":
+        if rank == 0:
+            n = max(2, min(args.steps, 4))
+            v = cpu_leg(n, threads)
+            print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": n,
+                              "warmup": 1, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
+                              "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+                              "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                                               "sample": f"{n} whole iterations of oracle/seg_oracle.py, {threads} threads"},
+                              "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    assert world == 1, "the segmentation variant is single-GPU (whole video resident)"
+    from b200 import _native as N, atlas as A, seg as SG
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    vid = A.DeviceVideo.from_reference_layout(data, dev)
+    prec = N.PREC_TC if (args.precision != "fp32" and N.lib().b200_device_supports_tc()) else N.PREC_FP32
+    tr = SG.SegTrainer(vid, SG.pack_mask_frames(masks, dev), None, precision=prec, device=dev)
+    torch.manual_seed(0)
+    tr.init_like_reference()
+    steps, warm = max(2, args.steps), max(3, args.warmup)
+    g = torch.Generator().manual_seed(1)
+    inds_d = [torch.randint(H * W * T, (B,), generator=g).to(dev) for _ in range(8)]
+    inds_h = [torch.randint(H * W * T, (B, 1), generator=g) for _ in range(8)]
+    k = [0]
+
+    def step():
+        i = k[0]; k[0] += 1
+        tr.indices.copy_(inds_d[i % 8])
+        tr.step(0 if (i % steps) < steps // 2 else 6000)
+    l0 = N.lib().b200_launch_count()
+    ms = _event_ms(step, steps, warm)
+    n_launch = (N.lib().b200_launch_count() - l0) / (steps + warm)
+    k[0] = 0
+    ems = _event_ms(lambda: (tr.step_host(inds_h[k[0] % 8], 0 if k[0] % steps < steps // 2 else 6000), k.__setitem__(0, k[0] + 1)),
+                    steps, 2)
+    out = {"metric": metric, "value": 1000.0 / ms, "unit": unit, "n_gpus": 1, "steps": steps, "warmup": warm,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": ("mapping1 + atlas: 2-term fp16 split operands / fp32 accumulate (tcgen05); mapping2 + alpha: fp32 CUDA cores"
+                     if prec == N.PREC_TC else "fp32"), "data": "synthetic", "config": config,
+           "e2e": {"value": 1000.0 / ems, "unit": unit, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": N.SEG_LOSS_FLOATS * 4},
+           "gpu_launches": int(round(n_launch * steps)), "launches_per_step": n_launch, "losses_last": tr.loss_dict()}
+    if not args.no_cpu_baseline:
+        v = cpu_leg(2, threads)
+        out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                               "sample": f"2 whole iterations of oracle/seg_oracle.py, {threads} threads"}
+    print(json.dumps(out), flush=True)
+
+
 def driver_line(args, rank, world, local):
     """`bench.py --workload raft|stage2`: a step = one 1080p frame pair (both flow directions, 20 refinement
     iterations) / one 1088x1920 frame through UNet + TransformNet.  Pairs and neural-filter frames are independent
     units: with N GPUs every rank runs its own (weak scaling, no collective)."""
+    if args.workload == "seg":
+        return seg_line(args, rank, world, local)
     if args.impl == "reference":
         if rank == 0:
             _reference_line(args)

@@ -1,0 +1,56 @@
+"""Quality gate (BASELINE north_star: "output PSNR within 0.1 dB of reference"): the WHOLE stage-1 schedule —
+pre-training, 10 001 loop trips, render of all 80 frames at 768x432 — on the B200 through the product path, against the
+oracle's frozen CPU run of the same schedule from the same seed (tests/golden/quality_oracle.npz, produced by
+tests/golden/make_quality_oracle.py).  The run takes ~20 s on a B200.
+
+Bounds: |mean PSNR difference| <= 0.1 dB (the gate); every frame within 0.5 dB; the total loss of the two runs, sampled
+every 50 trips over the whole schedule, within 10 % at the median (the trajectories are chaotic, the curves are not)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURE = os.path.join(ROOT, "tests", "golden", "quality_oracle.npz")
+
+
+def test_quality_fixture_is_consistent():
+    """CPU: the frozen oracle run is self-consistent (parameter counts, PSNR mean, thumbnails re-rendered from the
+    frozen parameters)."""
+    import torch
+    from oracle import atlas_oracle as O
+    fx = np.load(FIXTURE)
+    T, H, W = (int(v) for v in fx["video"])
+    assert (T, H, W) == (80, 432, 768) and int(fx["iters"]) == 10001 and int(fx["pre_sweeps"]) == 100
+    assert fx["psnr"].shape == (T,) and abs(float(fx["psnr_mean"]) - float(fx["psnr"].mean())) < 1e-9
+    assert fx["mapping_params"].size == O.MAPPING_SPEC.num_params() and fx["atlas_params"].size == O.ATLAS_SPEC.num_params()
+    assert fx["losses"].shape == (201, 7) and np.isfinite(fx["losses"][:, 1]).all()
+    assert fx["losses"][-1, 1] < 0.2 * fx["losses"][0, 1]            # the run converged
+
+    def unflat(spec, flat):
+        out, off = [], 0
+        for k, n in spec.layer_dims():
+            out += [torch.from_numpy(flat[off:off + k * n]).view(n, k)]; off += k * n
+            out += [torch.from_numpy(flat[off:off + n])]; off += n
+        return out
+    f = int(fx["thumb_frames"][0])
+    img = O.render_frame(unflat(O.MAPPING_SPEC, fx["mapping_params"]), unflat(O.ATLAS_SPEC, fx["atlas_params"]), f, H, W, T)
+    assert np.abs(O.to_uint8(img)[::4, ::4].astype(int) - fx["thumbs"][0].astype(int)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_full_schedule_psnr_within_0p1_db_of_oracle():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "perf", "quality_vs_oracle.py")], capture_output=True,
+                       text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["iters"] == 10001 and out["pre_sweeps"] == 100 and out["precision"] == "tc"
+    assert abs(out["psnr_diff_mean_db"]) <= 0.1, out["psnr_diff_mean_db"]
+    assert out["gate_0p1_db"]
+    d = out["psnr_diff_per_frame_db"]
+    assert -0.5 <= d["min"] and d["max"] <= 0.5, d
+    assert out["loss_total_rel_diff"]["median"] <= 0.10, out["loss_total_rel_diff"]
+    assert abs(out["oracle_rerender_psnr_mean"] - out["psnr_oracle_mean"]) <= 0.02     # the fixture's parameters reproduce its PSNR
