@@ -1600,9 +1600,11 @@ static int check_single(const MlpShape& sh, bool is_atlas, int64_t rows, cudaStr
   B200_PROPAGATE(ensure_attrs());
   if (is_atlas) B200_REQUIRE(sh.L == 8 && sh.skip[4] && sh.skip[7] && sh.pe == 10 && sh.hidden == HID && sh.in_dim == 2 &&
                              sh.out_dim == 3, "tensor-core IMLP: not the atlas architecture");
-  else B200_REQUIRE((sh.L == 6 || sh.L == 4) && sh.pe == 0 && sh.hidden == HID && sh.in_dim == 3 && sh.out_dim == 2 &&
-                    !sh.skip[1] && !sh.skip[2] && !sh.skip[3] && !sh.skip[4] && !sh.skip[5],
-                    "tensor-core IMLP: not a mapping architecture (3 -> 256 x {2,4} -> 2, no encoding, no skips)");
+  else {
+    bool plain = (sh.L == 6 || sh.L == 4) && sh.pe == 0 && sh.hidden == HID && sh.in_dim == 3 && sh.out_dim == 2;
+    for (int l = 1; plain && l < sh.L; ++l) plain = !sh.skip[l];
+    B200_REQUIRE(plain, "tensor-core IMLP: not a mapping architecture (3 -> 256 x {2,4} -> 2, no encoding, no skips)");
+  }
   B200_REQUIRE(rows > 0 && rows % TM == 0 && rows / TM < (1 << 20), "rows must be a positive multiple of %d", TM);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);
