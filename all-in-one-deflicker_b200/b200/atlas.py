@@ -66,6 +66,13 @@ class DeviceVideo:
     def num_pixels(self):
         return self.H * self.W * self.T
 
+    def mask_fwd_host(self) -> torch.Tensor:
+        """The forward consistency masks as the reference's (H, W, T, 1) fp32 CPU tensor, unpacked from the bitmap."""
+        n = self.num_pixels
+        words = self.bits_f.cpu().numpy().view(np.uint32)
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:n]
+        return torch.from_numpy(bits.reshape(self.T, self.H, self.W).astype(np.float32)).permute(1, 2, 0).unsqueeze(-1).contiguous()
+
     @classmethod
     def from_reference_layout(cls, data: Dict[str, torch.Tensor], device, t_begin: int = 0,
                               t_end: Optional[int] = None, frame_chunk: int = 16) -> "DeviceVideo":
@@ -506,6 +513,28 @@ class AtlasTrainer:
                                          ws.numel(), N.current_stream()), "b200_render")
         out = rgb.view(H, W, 3)
         return (out, u8.view(H, W, 3)) if want_u8 else out
+
+
+    def eval_maps(self, f: int, chunk: Optional[int] = None):
+        """Per-pixel maps of frame f that the reference's evaluation dashboards show (evaluate.py:640-700): uv (H, W, 2),
+        rigidity loss of every pixel (H, W), forward flow error (H, W; zero where the flow is invalid / last frame)."""
+        v = self.video
+        H, W = v.H, v.W
+        chunk = H * W if chunk is None else min(chunk, H * W)
+        uv = torch.empty(H * W * 2, dtype=torch.float32, device=self.device)
+        rig = torch.empty(H * W, dtype=torch.float32, device=self.device)
+        flow = torch.empty(H * W, dtype=torch.float32, device=self.device)
+        nbytes = int(self.lib.b200_eval_maps_workspace_bytes(C.byref(self.map_desc), chunk))
+        ws = getattr(self, "_eval_ws", None)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._eval_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        for p0 in range(0, H * W, chunk):
+            p1 = min(H * W, p0 + chunk)
+            N.check(self.lib.b200_eval_maps(C.byref(self.map_desc), N.ptr(self.params), C.byref(v.struct), f, p0, p1,
+                                            float(self.cfg["derivative_amount"]), float(self.cfg["uv_mapping_scale"]),
+                                            self.precision, N.ptr(uv[p0 * 2:]), N.ptr(rig[p0:]), N.ptr(flow[p0:]),
+                                            N.ptr(ws), ws.numel(), N.current_stream()), "b200_eval_maps")
+        return uv.view(H, W, 2), rig.view(H, W), flow.view(H, W)
 
 
 def psnr(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -3,7 +3,7 @@
 `load_input_data_single` is the input producer (reads frames + RAFT flows from disk, CPU, same tensor
 layouts as the reference returns); `get_tuples` and `pre_train_mapping` are provided for drop-in use,
 the latter running on the fused trainer.  `load_input_data` is the segmentation variant's loader (adds the
-bootstrapping masks).  The visualisation helper `save_mask_flow` (imageio mp4s) is out of scope.
+bootstrapping masks).  `save_mask_flow` writes the reference's two overview videos with OpenCV.
 """
 import numpy as np
 import torch
@@ -121,3 +121,32 @@ def pre_train_mapping(trainer, frames_num, uv_mapping_scale, resx, resy, larger_
     else:
         trainer.pretrain(which, frames_num, resy, resx, pretrain_iters)
     return trainer
+
+
+def save_mask_flow(optical_flows_mask, video_frames, results_folder):
+    """unwrap_utils.py:200-231: `filter_flow_<j>.mp4` (frames with the pixels whose forward flow failed the consistency
+    check painted red; frames without any valid pixel are skipped) and `input_video.mp4` (the video at the working
+    resolution), 10 fps.  Written with OpenCV's mp4 encoder instead of imageio."""
+    H, W = int(video_frames.shape[0]), int(video_frames.shape[1])
+
+    def writer(name):
+        wr = cv2.VideoWriter(str(results_folder / name) if hasattr(results_folder, "joinpath") else
+                             "%s/%s" % (results_folder, name), cv2.VideoWriter_fourcc(*"mp4v"), 10, (W, H))
+        if not wr.isOpened():
+            raise RuntimeError("OpenCV cannot write mp4 here")
+        return wr
+    to_bgr = lambda fr: cv2.cvtColor((fr.numpy() * 255).astype(np.uint8), cv2.COLOR_RGB2BGR)
+    for j in range(optical_flows_mask.shape[3]):
+        wr = writer("filter_flow_%d.mp4" % j)
+        for i in range(video_frames.shape[3]):
+            m = optical_flows_mask[:, :, i, j]
+            if not bool((m == 1).any()):
+                continue
+            cur = video_frames[:, :, :, i].clone()
+            cur[m == 0] = torch.tensor([1.0, 0.0, 0.0])
+            wr.write(to_bgr(cur))
+        wr.release()
+    wr = writer("input_video.mp4")
+    for i in range(video_frames.shape[3]):
+        wr.write(to_bgr(video_frames[:, :, :, i]))
+    wr.release()

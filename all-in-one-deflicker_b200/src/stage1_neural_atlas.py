@@ -24,7 +24,7 @@ from tqdm import tqdm  # noqa: E402
 from b200 import _native as N  # noqa: E402
 from b200 import atlas as A    # noqa: E402
 from src.models.stage_1.evaluate import evaluate_model_single  # noqa: E402
-from src.models.stage_1.unwrap_utils import pre_train_mapping  # noqa: E402
+from src.models.stage_1.unwrap_utils import pre_train_mapping, save_mask_flow  # noqa: E402
 
 
 def main(config, args):
@@ -46,6 +46,11 @@ def main(config, args):
     video, frames = A.DeviceVideo.from_files(data_folder, vid_root, vid_name, resy, resx,
                                              config["maximum_number_of_frames"], device, filter_optical_flow=True)
     T = frames.shape[3]
+    writer = None
+    if not args.no_artefacts:      # the reference's tensorboard log + overview videos (:99,109; unwrap_utils.py:200-231)
+        from torch.utils.tensorboard import SummaryWriter
+        writer = SummaryWriter(log_dir=str(results_folder))
+        save_mask_flow(video.mask_fwd_host(), frames, results_folder)
     precision = N.PREC_TC if N.lib().b200_device_supports_tc() else N.PREC_FP32
     trainer = A.AtlasTrainer(video, config, precision=precision, device=device, resx=resx)
     trainer.init_like_reference()          # mapping then atlas, nn.Linear stream order (:112-128)
@@ -69,7 +74,8 @@ def main(config, args):
         inds = torch.randint(n_pixels, (samples, 1))       # same CPU-generator draw as the reference (:159)
         trainer.step_host(inds, i)
         if i % evaluate_every == 0 and i > start_iteration:
-            evaluate_model_single(trainer, resx, resy, T, frames, results_folder, i, vid_name)
+            evaluate_model_single(trainer, resx, resy, T, frames, results_folder, i, vid_name,
+                                  artefacts=not args.no_artefacts, writer=writer)
 
 
 if __name__ == "__main__":
@@ -79,6 +85,8 @@ if __name__ == "__main__":
     parser.add_argument('--root', type=str, default="data/test/")
     parser.add_argument('--down', type=int, default=4)
     parser.add_argument('--gpu', type=int, default=0)
+    parser.add_argument('--no_artefacts', action='store_true',
+                        help="skip the evaluation videos / tensorboard log (checkpoint, output frames and PSNR only)")
     args = parser.parse_args()
     os.environ["CUDA_VISIBLE_DEVICES"] = "%d" % args.gpu
     args.vid_path = os.path.join(args.root, args.vid_name)

@@ -347,6 +347,21 @@ int b200_seg_render(const B200SegConfig* cfg, const float* params, int32_t H, in
                     uint8_t* rgb_u8, float* alpha, void* ws, int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Evaluation maps of one frame — the per-pixel quantities of the reference's evaluation output
+ * (src/models/stage_1/evaluate.py:640-708): uv of every pixel, its rigidity loss
+ * (get_rigidity_loss(..., return_all=True), loss_utils.py:227-278) and its forward flow error
+ * (get_optical_flow_loss_all, loss_utils.py:283-295; zero where the flow is invalid and for the
+ * last frame).  `mapping` + `mapping_params`: one mapping network in its own flat layout.
+ * Outputs for pixels [pix_begin, pix_end) of `frame` (each may be NULL): uv [count][2],
+ * rigidity [count], flow_error [count].
+ * ------------------------------------------------------------------------------------------ */
+int64_t b200_eval_maps_workspace_bytes(const B200MlpDesc* mapping, int64_t pixels);
+int b200_eval_maps(const B200MlpDesc* mapping, const float* mapping_params, const B200Video* video,
+                   int32_t frame, int64_t pix_begin, int64_t pix_end, float derivative_amount,
+                   float uv_mapping_scale, int precision, float* uv, float* rigidity,
+                   float* flow_error, void* ws, int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RAFT correlation — replaces CorrBlock (src/models/stage_1/core/corr.py:16-64); the reference's own
  * native hook for this operator is alt_cuda_corr.forward (corr.py:86-91, extension not shipped).
  * fmaps: [dim][H8*W8] fp32 (batch 1).  pyramid: level 0 [H8*W8][H8][W8], then 3 avg-pooled levels,

@@ -253,6 +253,35 @@ def flow_loss(video: Video, jif, uv, resx, mapping, uv_scale: float):
     return l_prev.mean() * 0.5 + l_next.mean() * 0.5
 
 
+def flow_loss_all(video: Video, jif, uv, resx, T: int, mapping, uv_scale: float):
+    """``get_optical_flow_loss_all`` loss_utils.py:283-295 (+ ``get_corresponding_flow_matches_all`` :360-382) with
+    alpha == 1: forward flow error of EVERY sample, zero where the flow is invalid."""
+    fl = video.flow_fwd[jif[1], jif[0], :, jif[2], 0].squeeze()
+    ok = video.mask_fwd[jif[1], jif[0], jif[2], 0].squeeze()
+    m = torch.stack((jif[0].squeeze() + fl[:, 0], jif[1].squeeze() + fl[:, 1], jif[2].squeeze() + 1))
+    xyt = torch.stack((m[0] / _half(resx) - 1, m[1] / _half(resx) - 1, m[2] / (T / 2) - 1)).T
+    err = (mapping(xyt) - uv).norm(dim=1)
+    err[(ok > 0) == False] = 0                      # noqa: E712  (the reference's comparison, loss_utils.py:292)
+    return err * resx / (2 * uv_scale)
+
+
+def eval_maps(video: Video, map_params, f: int, d: int = 1, uv_scale: float = 0.8):
+    """Per-pixel maps of frame ``f`` as the reference's evaluation computes them (evaluate.py:640-700): uv (H, W, 2),
+    rigidity loss (H, W), forward flow error (H, W; zero for the last frame)."""
+    H, W, T = video.H, video.W, video.T
+    larger = np.maximum(np.int64(W), np.int64(H))
+    ys, xs = torch.where(torch.ones(H, W) > 0)
+    mapping = lambda x: mlp_forward(MAPPING_SPEC, map_params, x)
+    with torch.no_grad():
+        xyt = torch.cat((xs.unsqueeze(1) / (larger / 2) - 1, ys.unsqueeze(1) / (larger / 2) - 1,
+                         (f / (T / 2.0) - 1) * torch.ones(ys.shape[0], 1)), dim=1)
+        uv = mapping(xyt)
+        jif = torch.cat((xs.unsqueeze(-1), ys.unsqueeze(-1), torch.ones_like(ys.unsqueeze(-1)) * f), dim=1).T.unsqueeze(-1)
+        rig = rigidity_loss(jif, d, larger, T, mapping, uv, uv_scale=uv_scale, per_sample=True)
+        flow = flow_loss_all(video, jif, uv, larger, T, mapping, uv_scale) if f < T - 1 else torch.zeros(ys.shape[0])
+    return uv.view(H, W, 2), rig.view(H, W), flow.view(H, W)
+
+
 # ----------------------------------------------------------------------------------------
 # one iteration of the hot loop  (src/stage1_neural_atlas.py:151-231)
 # ----------------------------------------------------------------------------------------

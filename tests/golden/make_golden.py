@@ -210,6 +210,28 @@ def main():
     img = O.render_frame(map_p, atl_p, 2, H, W, T)
     np.savez(os.path.join(OUT, "render.npz"), frame=2, img=img.numpy(), u8=O.to_uint8(img),
              psnr=O.psnr(video.frames[:, :, :, 2], img))
+    # ---------------- 8. per-pixel evaluation maps (evaluate.py:640-700): uv, rigidity of every pixel, flow error
+    ev = {}
+    for f in (2, T - 1):
+        ys, xs = torch.where(torch.ones(H, W) > 0)
+        with torch.no_grad():
+            xyt = torch.cat((xs.unsqueeze(1) / (larger / 2) - 1, ys.unsqueeze(1) / (larger / 2) - 1,
+                             (f / (T / 2.0) - 1) * torch.ones(ys.shape[0], 1)), dim=1)
+            uv_r = ref_m(xyt)
+            jf = torch.cat((xs.unsqueeze(-1), ys.unsqueeze(-1), torch.ones_like(ys.unsqueeze(-1)) * f), dim=1).T.unsqueeze(-1)
+            rig_r = ref_loss.get_rigidity_loss(jf, 1, larger, T, ref_m, uv_r, "cpu", uv_mapping_scale=0.8, return_all=True)
+            if f < T - 1:
+                fl_r = ref_loss.get_optical_flow_loss_all(jf, uv_r, larger, T, ref_m, video.flow_fwd, video.mask_fwd, 0.8,
+                                                          "cpu", alpha=torch.ones(ys.shape[0], 1))
+            else:
+                fl_r = torch.zeros(ys.shape[0])
+        uv_o, rig_o, fl_o = O.eval_maps(video, [p.detach() for p in ref_m.parameters()], f)
+        same(uv_o.reshape(-1, 2), uv_r, "eval uv")
+        same(rig_o.reshape(-1), rig_r, "eval rigidity")
+        same(fl_o.reshape(-1), fl_r, "eval flow error")
+        ev[f"f{f}_uv"], ev[f"f{f}_rig"], ev[f"f{f}_flow"] = uv_o.numpy(), rig_o.numpy(), fl_o.numpy()
+    np.savez_compressed(os.path.join(OUT, "eval_maps.npz"), frames=np.array([2, T - 1]),
+                        **{f"map{i}": p.detach().numpy() for i, p in enumerate(ref_m.parameters())}, **ev)
     print("golden fixtures written to", OUT)
 
 

@@ -397,3 +397,29 @@ def test_dp_adam_single_rank_equals_adam():
         assert b.value == covered
         covered += c.value
     assert covered == n + extra
+
+
+@pytest.mark.parametrize("precision", [N.PREC_FP32, N.PREC_TC])
+def test_eval_maps_match_reference_fixture(golden_dir, precision):
+    """b200_eval_maps (uv, per-pixel rigidity, forward flow error of a whole frame) against the fixture frozen from the
+    reference's get_rigidity_loss(return_all=True) / get_optical_flow_loss_all (tests/golden/make_golden.py section 8).
+    uv 2e-6; rigidity / flow error 2e-3 relative + small absolute floor (differences of nearby uv values times
+    resx / 2: the uv error is amplified by ~L/2 = 20)."""
+    if precision == N.PREC_TC and not N.lib().b200_device_supports_tc():
+        pytest.skip("needs sm_100")
+    z = np.load(os.path.join(golden_dir, "eval_maps.npz"))
+    data, _ = _golden_video(golden_dir)
+    vid = A.DeviceVideo.from_reference_layout(data, DEV)
+    tr = A.AtlasTrainer(vid, {"samples_batch": 64}, precision=precision, device=DEV)
+    mp = [torch.from_numpy(z[f"map{i}"]) for i in range(12)]
+    _, ap = _params(golden_dir)
+    tr.load_state(O.state_dict_of(mp), O.state_dict_of(ap))
+    for f in (int(v) for v in z["frames"]):
+        uv, rig, flow = tr.eval_maps(f, chunk=300)
+        np.testing.assert_allclose(uv.cpu().numpy(), z[f"f{f}_uv"], atol=2e-6)
+        np.testing.assert_allclose(rig.cpu().numpy(), z[f"f{f}_rig"], rtol=2e-3, atol=1e-3)
+        np.testing.assert_allclose(flow.cpu().numpy(), z[f"f{f}_flow"], rtol=2e-3, atol=2e-4)
+        if f == vid.T - 1:
+            assert float(flow.abs().max()) == 0.0
+        else:
+            assert float((flow > 0).float().mean()) > 0.3

@@ -63,6 +63,21 @@ def test_scripts_end_to_end(tmp_path):
     assert len(marker) == 1
     psnr = float(os.path.basename(marker[0])[len("PSNR_"):])
     assert np.isfinite(psnr) and psnr > 12.0, psnr                         # 300 small iterations already fit the pan roughly
+    # evaluation artefacts of the reference (evaluate.py:714-793, unwrap_utils.py:200-231), written with OpenCV
+    import cv2
+    for name, frames in (("000300/reconstruction_tiny.mp4", 6), ("000300/residuals_tiny.mp4", 6), ("000300/uv_1_tiny.mp4", 6),
+                         ("000300/global_info_tiny.mp4", 6), ("input_video.mp4", 6), ("filter_flow_0.mp4", None)):
+        assert os.path.exists(str(res / name)), name
+        cap = cv2.VideoCapture(str(res / name))
+        if frames is None:        # frames without a single consistent flow are skipped (random-init RAFT: maybe all)
+            assert not cap.isOpened() or int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) <= 6
+        else:
+            assert cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == frames, name
+        cap.release()
+    cap = cv2.VideoCapture(str(res / "000300" / "global_info_tiny.mp4"))
+    ok, dash = cap.read()
+    assert ok and dash.shape == (2 * (128 + 22), 3 * 192, 3)
+    assert glob.glob(str(res / "events.out.tfevents.*"))                   # tensorboard log with the two images
     # stage 2 with random-init checkpoints under the reference's keys
     os.makedirs(str(work / "pretrained_weights"), exist_ok=True)
     torch.manual_seed(0)

@@ -39,3 +39,38 @@ def test_driver_moves_frames_and_runs_seg_variant(tmp_path):
     # missing input (here the RAFT checkpoint of its flow pre-pass), never silently falling back to one layer
     assert r.returncode != 0 and "stage1_neural_atlas_seg.py" in (r.stdout + r.stderr)
     assert "raft-things.pth is missing" in r.stderr or "optical-flow pre-pass failed" in r.stderr
+
+
+def test_evaluation_videos_are_written_with_opencv(tmp_path):
+    """Host side of the evaluation artefacts (reference evaluate.py:714-779, unwrap_utils.py:200-231): the mp4 writers
+    and the dashboard composition, no GPU involved."""
+    import sys as _sys
+    import cv2
+    import torch
+    _sys.path.insert(0, PKG)
+    from src.models.stage_1.evaluate import ArtefactWriter
+    from src.models.stage_1.unwrap_utils import save_mask_flow
+    H, W, T = 32, 48, 4
+    g = torch.Generator().manual_seed(0)
+    frames = torch.full((H, W, 3, T), 0.5) + 0.02 * torch.rand(H, W, 3, T, generator=g)
+    masks = torch.ones(H, W, T, 1)
+    masks[:, :16] = 0                                        # a block of pixels whose flow failed the check
+    masks[:, :, T - 1] = 0                                   # the last frame has no forward flow: skipped (:204-205)
+    save_mask_flow(masks, frames, tmp_path)
+    cap = cv2.VideoCapture(str(tmp_path / "filter_flow_0.mp4"))
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == T - 1
+    ok, fr = cap.read()
+    bad = masks[:, :, 0, 0].numpy() == 0
+    assert ok and fr[bad][:, 2].mean() > 200 and fr[bad][:, 1].mean() < 60     # invalid pixels are red (BGR order)
+    assert abs(float(fr[~bad].mean()) - 130) < 12                              # the others keep the frame's grey
+    assert int(cv2.VideoCapture(str(tmp_path / "input_video.mp4")).get(cv2.CAP_PROP_FRAME_COUNT)) == T
+    art = ArtefactWriter(str(tmp_path), "clip", W, H)
+    for t in range(T):
+        f = frames[:, :, :, t].numpy()
+        art.add(f, f * 0.9, np.zeros((H, W, 2), np.float32), np.full((H, W), 3.0, np.float32), np.zeros((H, W), np.float32))
+    art.close()
+    for name in ("reconstruction", "residuals", "uv_1", "global_info"):
+        cap = cv2.VideoCapture(str(tmp_path / f"{name}_clip.mp4"))
+        assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == T, name
+    ok, dash = cv2.VideoCapture(str(tmp_path / "global_info_clip.mp4")).read()
+    assert ok and dash.shape == (2 * (H + 22), 3 * W, 3)
