@@ -184,6 +184,21 @@ def _from_files(cls, data_folder, vid_root, vid_name, resy: int, resx: int, maxi
 DeviceVideo.from_files = classmethod(_from_files)
 
 
+# architecture keys of config_flow_100.json that the fused single-layer step is specialised to
+# (src/stage1_neural_atlas.py:112-128 reads them; other values need the generic path: IMLP objects + loss_utils, or
+# the segmentation trainer, which takes any IMLP shape)
+FUSED_ARCHITECTURE = dict(number_of_layers_mapping1=6, number_of_channels_mapping1=256, use_positional_encoding_mapping1=False,
+                          number_of_layers_atlas=8, number_of_channels_atlas=256, positional_encoding_num_atlas=10)
+
+
+def check_architecture(config: dict):
+    """Raise instead of silently training a different model than the config describes."""
+    bad = {k: config[k] for k, v in FUSED_ARCHITECTURE.items() if k in config and config[k] != v}
+    if bad:
+        raise N.B200Error(f"the fused stage-1 step is built for {FUSED_ARCHITECTURE}; the config asks for {bad}. "
+                          "Use the IMLP class + src/models/stage_1/loss_utils.py (any shape) for other architectures.")
+
+
 class AtlasTrainer:
     """Flat parameters/optimiser state of (mapping, atlas) + the fused step."""
 
@@ -195,6 +210,7 @@ class AtlasTrainer:
         self.cfg = dict(DEFAULTS)
         if config:
             self.cfg.update({k: v for k, v in config.items() if k in DEFAULTS})
+            check_architecture(config)
         self.precision = precision
         self.device = torch.device(device)
         self.lr = lr

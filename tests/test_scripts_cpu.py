@@ -74,3 +74,18 @@ def test_evaluation_videos_are_written_with_opencv(tmp_path):
         assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == T, name
     ok, dash = cv2.VideoCapture(str(tmp_path / "global_info_clip.mp4")).read()
     assert ok and dash.shape == (2 * (H + 22), 3 * W, 3)
+
+
+def test_fused_trainer_rejects_other_architectures():
+    """A config whose network shapes differ from the ones the fused step is specialised to must not train silently
+    (the reference honours these keys, src/stage1_neural_atlas.py:112-128)."""
+    import sys as _sys
+    import json
+    import pytest
+    _sys.path.insert(0, PKG)
+    from b200 import _native as N, atlas as A
+    cfg = json.load(open(os.path.join(PKG, "src", "config", "config_flow_100.json")))
+    A.check_architecture(cfg)                                   # the shipped config is the supported one
+    for key, val in (("number_of_layers_mapping1", 4), ("positional_encoding_num_atlas", 6), ("number_of_channels_atlas", 128)):
+        with pytest.raises(N.B200Error):
+            A.check_architecture(dict(cfg, **{key: val}))
