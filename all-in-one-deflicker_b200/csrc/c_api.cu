@@ -185,6 +185,10 @@ static int tc_architecture(const MlpShape& s) {
     for (int l = 1; l < s.L; ++l) if (s.skip[l] != (l == 4 || l == 7)) return 0;
     return 2;
   }
+  if (s.L == 8 && s.pe == 5 && s.in_dim == 3 && s.out_dim == 1) {      // alpha network of the segmentation variant
+    for (int l = 1; l < s.L; ++l) if (s.skip[l]) return 0;
+    return 3;
+  }
   return 0;
 }
 
@@ -204,7 +208,7 @@ static void plan_tc_call(const MlpShape& s, int arch, int64_t rows_pad, char* ba
   pl->dy = reinterpret_cast<float*>(carve(p, rows_pad * s.out_dim * 4));
   pl->d_in = reinterpret_cast<float*>(carve(p, rows_pad * 8));
   pl->tc = p;
-  pl->bytes = (p - base) + tc_single_workspace_bytes(s, arch == 2, rows_pad);
+  pl->bytes = (p - base) + tc_single_workspace_bytes(s, arch >= 2, rows_pad);
 }
 
 int64_t b200_mlp_workspace_bytes(const B200MlpDesc* d, int64_t rows, int training) {
@@ -225,7 +229,7 @@ static int tc_call_prepare(const B200MlpDesc* d, int64_t rows, void* ws, int64_t
                            int64_t* rows_pad, TcCallPlan* pl) {
   B200_PROPAGATE(resolve_mlp(d, s));
   *arch = tc_architecture(*s);
-  B200_REQUIRE(*arch != 0, "B200_PREC_TC serves the stage-1 architectures (mapping: 3-256x{2,4}-2 without encoding; "
+  B200_REQUIRE(*arch != 0, "B200_PREC_TC serves the stage-1 architectures (mapping: 3-256x{2,4}-2 without encoding; alpha: 3-PE5-256x6-1; "
                "atlas: 2-PE10-256x6-3 with skips 4, 7); use B200_PREC_FP32 for other shapes");
   if (!b200_device_supports_tc()) { set_error("B200_PREC_TC needs a compute-capability 10.x device"); return B200_ERR_UNSUPPORTED; }
   B200_REQUIRE(rows > 0 && rows < (1ll << 26), "rows out of range: %lld", (long long)rows);
@@ -263,8 +267,8 @@ int b200_mlp_forward(const B200MlpDesc* d, const float* params, const float* x, 
   if (precision == B200_PREC_TC) {
     int arch; int64_t rows_pad; TcCallPlan pl;
     B200_PROPAGATE(tc_call_prepare(d, rows, ws, ws_bytes, &s, &arch, &rows_pad, &pl));
-    B200_PROPAGATE(launch_pack_rows(x, s.in_dim, s.in_dim, pl.x, arch == 1 ? 4 : 2, rows, rows_pad, st));
-    B200_PROPAGATE(tc_single_forward(s, arch == 2, params, pl.x, pl.y, rows_pad, training != 0, pl.tc, st));
+    B200_PROPAGATE(launch_pack_rows(x, s.in_dim, s.in_dim, pl.x, arch == 2 ? 2 : 4, rows, rows_pad, st));
+    B200_PROPAGATE(tc_single_forward(s, arch >= 2, params, pl.x, pl.y, rows_pad, training != 0, pl.tc, st));
     B200_CHECK_CUDA(cudaMemcpyAsync(y, pl.y, (size_t)rows * s.out_dim * 4, cudaMemcpyDeviceToDevice, st));
     return B200_OK;
   }
@@ -297,12 +301,12 @@ int b200_mlp_backward(const B200MlpDesc* d, const float* params, const float* x,
     // the workspace still holds the padded input, the outputs and the activation images of the forward call
     int arch; int64_t rows_pad; TcCallPlan pl;
     B200_PROPAGATE(tc_call_prepare(d, rows, ws, ws_bytes, &s, &arch, &rows_pad, &pl));
-    B200_REQUIRE(arch == 2 || dx == nullptr, "the tensor-core mapping network has no input gradient (its inputs are "
-                 "pixel coordinates); use B200_PREC_FP32 when x requires grad");
+    B200_REQUIRE(arch == 2 || dx == nullptr, "the tensor-core mapping / alpha networks have no input gradient (their inputs "
+                 "are pixel coordinates); use B200_PREC_FP32 when x requires grad");
     B200_PROPAGATE(launch_pack_rows(dy, s.out_dim, s.out_dim, pl.dy, s.out_dim, rows, rows_pad, st));
     B200_CHECK_CUDA(cudaMemsetAsync(pl.gmax2, 0, 8, st));
     B200_PROPAGATE(launch_absmax(pl.dy, rows_pad * s.out_dim, pl.gmax2 + (arch == 1 ? 1 : 0), st));
-    B200_PROPAGATE(tc_single_backward(s, arch == 2, params, dparams, pl.x, pl.y, pl.dy, (arch == 2 && dx) ? pl.d_in : nullptr,
+    B200_PROPAGATE(tc_single_backward(s, arch >= 2, params, dparams, pl.x, pl.y, pl.dy, (arch == 2 && dx) ? pl.d_in : nullptr,
                                       pl.gmax2, rows_pad, pl.tc, st));
     if (arch == 2 && dx) B200_CHECK_CUDA(cudaMemcpyAsync(dx, pl.d_in, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st));
     return B200_OK;

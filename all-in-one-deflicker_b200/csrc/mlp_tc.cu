@@ -396,7 +396,9 @@ struct FwdParams {
 // 64-column k chunk at a time (a_ready[kc]: chunks 0, 1 after the block-0 half of the epilogue, 2, 3 after the
 // block-1 half) and the MMA warp consumes them in that order, so the tensor pipe works on layer l+1 underneath the
 // epilogue of layer l.
-template <bool ATLAS, int NL = (ATLAS ? 8 : 6)>
+// VAR (with ATLAS = true): 0 = the atlas network (2 inputs, 10 frequencies, skips at 4 and 7, 3 outputs), 1 = the alpha
+// network of the segmentation variant (3 inputs, 5 frequencies, no skips, 1 output, no input gradient)
+template <bool ATLAS, int NL = (ATLAS ? 8 : 6), int VAR = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(1024) char smem_raw[];
   constexpr int NST = KCfg<ATLAS>::NST;
@@ -405,8 +407,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
   constexpr int L = NL;                                   // mapping-shaped networks: 6 (stage-1 script) or 4 layers
   constexpr int FIRST_TC = ATLAS ? 0 : 1;
   constexpr int LAST_TC = L - 2;
-  constexpr int OUT = ATLAS ? 3 : 2;
-  constexpr int KLAST = ATLAS ? 296 : 256;
+  constexpr bool ALPHA = ATLAS && VAR == 1;
+  constexpr bool SKIPS = ATLAS && !ALPHA;                 // PE chunk concatenated at layers 4 and L-1
+  constexpr int OUT = ATLAS ? (ALPHA ? 1 : 3) : 2;
+  constexpr int KLAST = SKIPS ? 296 : 256;
   // constants in shared memory: biases of layers 0..L-2 (pre-multiplied by S_ACT) at [l*256], last-layer
   // weights (pre-divided by S_ACT) + bias, (mapping) W0, and an exchange area for the output layer
   float* s_bias = sm.cst;
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
         for (int l = FIRST_TC; l <= LAST_TC; ++l) {
           const char* base = P.img.w_fwd + P.img.w_fwd_layer[l];
           if (ATLAS && l == 0) { produce_items(pp, base, 2); continue; }
-          if (ATLAS && l == 4) produce_items(pp, base + (int64_t)4 * 2 * STAGE_BYTES, 2);      // skip (PE) chunk first
+          if (SKIPS && l == 4) produce_items(pp, base + (int64_t)4 * 2 * STAGE_BYTES, 2);      // skip (PE) chunk first
           produce_items(pp, base, 8);
         }
     }
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
           bool first = true;
           if (ATLAS && l == 0) { mbar_wait(sm.x_ready, x_par); x_par ^= 1; }
           tc_fence_after();
-          if (ATLAS && (l == 0 || l == 4)) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + ATOM_BYTES, IDESC, first);
+          if (ATLAS && (l == 0 || (SKIPS && l == 4))) mma_chunk_ss(pp, tmem, sm.aux, sm.aux + ATOM_BYTES, IDESC, first);
           if (l > 0) {
             for (int kc = 0; kc < 4; ++kc) {
               mbar_wait(&sm.a_ready[kc], ts_pass & 1);
@@ -475,14 +479,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       if (ATLAS) {
         // positional encoding of in = x*in_scale+in_shift (implicit_neural_networks.py:9-13) into the aux tile
         // (K-major SW128, columns k*4 + {sin x0, sin x1, cos x0, cos x1}); slice j does the 8-column chunks 2j, 2j+1
-        const float2 uv = *reinterpret_cast<const float2*>(P.x + row * 2);
-        const float in[2] = {uv.x * P.in_scale + P.in_shift, uv.y * P.in_scale + P.in_shift};
+        float in[3] = {0.f, 0.f, 0.f};
+        if (ALPHA) {                                     // rows padded to 4 floats, like the mapping's
+          const float4 xv = *reinterpret_cast<const float4*>(P.x + row * 4);
+          in[0] = xv.x * P.in_scale + P.in_shift; in[1] = xv.y * P.in_scale + P.in_shift; in[2] = xv.z * P.in_scale + P.in_shift;
+        } else {
+          const float2 uv = *reinterpret_cast<const float2*>(P.x + row * 2);
+          in[0] = uv.x * P.in_scale + P.in_shift; in[1] = uv.y * P.in_scale + P.in_shift;
+        }
         char* a_hi = sm.aux;
         char* a_lo = sm.aux + ATOM_BYTES;
         char* g_hi = P.img.pe + (int64_t)gt * ATOM_BYTES;
         char* g_lo = g_hi + P.img.w64_term_stride;
-        for (int c8 = 2 * j; c8 < 2 * j + 2; ++c8) {     // chunks of 8 columns = 2 frequencies
+        for (int c8 = 2 * j; c8 < 2 * j + 2; ++c8) {     // chunks of 8 columns (atlas: 2 frequencies)
           float vals[8];
+          if (ALPHA) {
+            // column c = k*6 + r: r < 3 -> sin(x_r b_k), else cos(x_{r-3} b_k); 30 real columns
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = c8 * 8 + i;
+              float v = 0.f;
+              if (c < 30) {
+                const int k = c / 6, r = c - k * 6;
+                const float a = in[r < 3 ? r : r - 3] * pe_freq(k);
+                v = r < 3 ? sinf(a) : cosf(a);
+              }
+              vals[i] = v * S_ACT;
+            }
+          } else {
 #pragma unroll
           for (int half_k = 0; half_k < 2; ++half_k) {
             const int k = c8 * 2 + half_k;
@@ -494,6 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
             }
             vals[half_k * 4 + 0] = s0 * S_ACT; vals[half_k * 4 + 1] = s1 * S_ACT;
             vals[half_k * 4 + 2] = c0 * S_ACT; vals[half_k * 4 + 3] = c1 * S_ACT;
+          }
           }
           uint32_t h[4], lo[4];
 #pragma unroll
@@ -600,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fwd_kernel(const __grid_cons
       }
       // ---------------- output layer (+ skip part for the atlas) and tanh; the four column slices of a row
       // combine through shared memory
-      if (ATLAS) {
+      if (SKIPS) {
         const char* a_hi = sm.aux;
         const char* a_lo = sm.aux + ATOM_BYTES;
         for (int k = j * 10; k < j * 10 + 10; ++k) {
@@ -728,17 +753,20 @@ __device__ __forceinline__ void grad_scales(const int* gmax_bits, bool mapping, 
   inv_sg = ldexpf(1.0f, e - 13);                        // (conversions saturate), small entries keep their lo term
 }
 
-template <bool ATLAS, int NL = (ATLAS ? 8 : 6)>
+template <bool ATLAS, int NL = (ATLAS ? 8 : 6), int VAR = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) char smem_raw[];
   constexpr int NST = KCfg<ATLAS>::NST;
   SmemMap<NST, ATLAS> sm; sm.init(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int L = NL;                                   // mapping-shaped networks: 6 (stage-1 script) or 4 layers
-  constexpr int OUT = ATLAS ? 3 : 2;
-  constexpr int KLAST = ATLAS ? 296 : 256;
+  constexpr bool ALPHA = ATLAS && VAR == 1;
+  constexpr bool SKIPS = ATLAS && !ALPHA;                 // PE chunk concatenated at layers 4 and L-1
+  constexpr int OUT = ATLAS ? (ALPHA ? 1 : 3) : 2;
+  constexpr int KLAST = SKIPS ? 296 : 256;
   constexpr int LOW = 1;                                  // dgrad layers L-2 .. 1 (atlas: + the dPE product)
   constexpr int N_DGRAD = L - 2 - LOW + 1;
+  constexpr bool HAS_DPE = ATLAS && !ALPHA;               // input gradient through the positional encoding
   // shared constants: last-layer weights; bias-gradient accumulators for layers 0..L-2; (mapping) dW0; (atlas) the
   // exchange area of the dPE partial sums
   float* s_wlast = sm.cst;                               // OUT*KLAST (<= 888)
@@ -760,7 +788,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       uint32_t h_par = 0;
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
         const int gt = ti.global_tile(t);
-        if (ATLAS) {
+        if (HAS_DPE) {
           // aux tile <- positional-encoding image of this tile (hi, lo), completion on misc[0]
           mbar_wait(&sm.misc[1], h_par ^ 1);             // previous tile's readers are done with aux
           mbar_expect_tx(&sm.misc[0], 2 * ATOM_BYTES);
@@ -769,7 +797,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
                    &sm.misc[0]);
           h_par ^= 1;
         }
-        for (int l = L - 2; l >= (ATLAS ? 0 : LOW); --l) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[l], 8);
+        for (int l = L - 2; l >= (HAS_DPE ? 0 : LOW); --l) produce_items(pp, P.img.w_bwd + P.img.w_bwd_layer[l], 8);
       }
     }
   } else if (warp == 1) {
@@ -777,11 +805,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
       Pipe<NST> pp{sm.full, sm.empty, sm.stage, 0};
       uint32_t pass = 0;
       for (int t = blockIdx.x; t < ti.total; t += gridDim.x) {
-        for (int l = 0; l < N_DGRAD + (ATLAS ? 1 : 0); ++l) {
+        for (int l = 0; l < N_DGRAD + (HAS_DPE ? 1 : 0); ++l) {
           if (pass > 0) mbar_wait(sm.d_free, (pass - 1) & 1);
           tc_fence_after();
           bool first = true;
-          const uint32_t idesc = (ATLAS && l == N_DGRAD) ? IDESC64 : IDESC;
+          const uint32_t idesc = (HAS_DPE && l == N_DGRAD) ? IDESC64 : IDESC;
           for (int kc = 0; kc < 4; ++kc) {
             mbar_wait(&sm.a_ready[kc], pass & 1);        // every pass of this kernel is a TMEM-operand pass
             tc_fence_after();
@@ -819,7 +847,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         }
         // image row: columns 0..OUT-1 = S_g * dz, rest zero
         uint32_t h0, l0, h1 = 0, l1 = 0;
-        split2_f16(dzl[0] * s_g, dzl[1] * s_g, h0, l0);
+        split2_f16(dzl[0] * s_g, OUT > 1 ? dzl[OUT > 1 ? 1 : 0] * s_g : 0.f, h0, l0);
         if (OUT == 3) split2_f16(dzl[OUT - 1] * s_g, 0.f, h1, l1);
         char* g_hi = P.img.dzl + (int64_t)gt * ATOM_BYTES;
         char* g_lo = g_hi + P.img.w64_term_stride;
@@ -881,7 +909,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
         mbar_arrive(sm.d_free);
         const int slot = l - 1;                           // produces dZ_{l-1}
         const bool need_img = ATLAS || slot >= 1;         // mapping dZ_0 feeds only the CUDA-core layer-0 gradient
-        const bool need_tmem = ATLAS ? true : (slot >= 1);
+        const bool need_tmem = HAS_DPE ? true : (slot >= 1);   // dZ_0 is an MMA operand only for the dPE product
         char* img = P.img.dz + (int64_t)slot * P.img.slot_stride + (int64_t)gt * TILE_IMG_BYTES;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!ATLAS && slot == 0) xv = *reinterpret_cast<const float4*>(P.x + row * 4);
@@ -942,7 +970,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_bwd_kernel(const __grid_cons
           }
         }
       }
-      if (ATLAS) {
+      if (HAS_DPE) {
         // ---------------- dPE = dZ_0 W_0 (64 columns, 40 real) -> d(in) -> d_in += in_scale * d(in)
         mbar_wait(sm.d_ready, d_par); d_par ^= 1;
         tc_fence_after();
@@ -1207,6 +1235,8 @@ static int ensure_attrs() {
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<false>::SMEM));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<true, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<true, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg<true>::SMEM));
   B200_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   done = true;
   return B200_OK;
@@ -1250,6 +1280,10 @@ static void add_prep(PrepJobs& pj, const float* W, int ldw, int n_rows, int k0, 
 
 
 // ---- table builders shared by the cached (training loop) and the ephemeral (stand-alone IMLP) paths
+// the atlas network back-propagates to its input (uv) through the positional encoding; the alpha network's inputs
+// are pixel coordinates
+static bool net_has_dpe(const MlpShape& sh, bool is_atlas) { return is_atlas && sh.in_dim == 2; }
+
 static void prep_jobs_for_net(PrepJobs& pj, const MlpShape& sh, const NetImages& im, const float* pp, bool is_atlas,
                               bool with_bwd) {
   for (int l = 0; l < sh.L; ++l) {
@@ -1259,15 +1293,15 @@ static void prep_jobs_for_net(PrepJobs& pj, const MlpShape& sh, const NetImages&
     int item = 0;
     if (l > 0) for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], 256, kc * 64, 64, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
     if (is_atlas && (l == 0 || sh.skip[l]))
-      add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, PE_COLS, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
+      add_prep(pj, W, sh.K[l], 256, l == 0 ? 0 : 256, sh.enc, 0, dst + (int64_t)(item++) * 2 * STAGE_BYTES);
   }
   if (!with_bwd) return;
   for (int l = 0; l < sh.L - 1; ++l) {
-    if (!is_atlas && l < 1) continue;
+    if (l < 1 && !net_has_dpe(sh, is_atlas)) continue;
     char* dst = im.w_bwd + im.w_bwd_layer[l];
     const float* W = pp + sh.w_off[l];
     // image rows = input index k of layer l (256, or 40 for atlas layer 0), chunk over the output index n
-    const int rows = (is_atlas && l == 0) ? PE_COLS : 256;
+    const int rows = (is_atlas && l == 0) ? sh.enc : 256;
     for (int kc = 0; kc < 4; ++kc) add_prep(pj, W, sh.K[l], rows, kc * 64, 64, 1, dst + (int64_t)kc * 2 * STAGE_BYTES);
   }
 }
@@ -1297,11 +1331,14 @@ static void protos_for_net(WgProto* protos, int& np, const MlpShape& sh, const N
       g + sh.w_off[sh.L - 1], sh.K[sh.L - 1], sh.out_dim, 256);
   if (is_atlas) {
     // positional-encoding parts: layer 0 and the skip layers; output layer's skip part
-    add(im.dz, im.term_stride, 256, im.pe, im.w64_term_stride, 64, g + sh.w_off[0], sh.K[0], 256, PE_COLS);
-    add(im.dz + (int64_t)4 * im.slot_stride, im.term_stride, 256, im.pe, im.w64_term_stride, 64, g + sh.w_off[4] + 256,
-        sh.K[4], 256, PE_COLS);
-    add(im.dzl, im.w64_term_stride, 64, im.pe, im.w64_term_stride, 64, g + sh.w_off[sh.L - 1] + 256, sh.K[sh.L - 1],
-        sh.out_dim, PE_COLS);
+    add(im.dz, im.term_stride, 256, im.pe, im.w64_term_stride, 64, g + sh.w_off[0], sh.K[0], 256, sh.enc);
+    for (int l = 1; l <= sh.L - 2; ++l)
+      if (sh.skip[l])
+        add(im.dz + (int64_t)l * im.slot_stride, im.term_stride, 256, im.pe, im.w64_term_stride, 64, g + sh.w_off[l] + 256,
+            sh.K[l], 256, sh.enc);
+    if (sh.skip[sh.L - 1])
+      add(im.dzl, im.w64_term_stride, 64, im.pe, im.w64_term_stride, 64, g + sh.w_off[sh.L - 1] + 256, sh.K[sh.L - 1],
+          sh.out_dim, sh.enc);
   }
 }
 
@@ -1598,8 +1635,14 @@ int64_t tc_single_workspace_bytes(const MlpShape& sh, bool is_atlas, int64_t row
 
 static int check_single(const MlpShape& sh, bool is_atlas, int64_t rows, cudaStream_t st) {
   B200_PROPAGATE(ensure_attrs());
-  if (is_atlas) B200_REQUIRE(sh.L == 8 && sh.skip[4] && sh.skip[7] && sh.pe == 10 && sh.hidden == HID && sh.in_dim == 2 &&
-                             sh.out_dim == 3, "tensor-core IMLP: not the atlas architecture");
+  if (is_atlas) {
+    bool no_skips = true;
+    for (int l = 1; l < sh.L; ++l) no_skips = no_skips && !sh.skip[l];
+    const bool atlas = sh.L == 8 && sh.skip[4] && sh.skip[7] && sh.pe == 10 && sh.hidden == HID && sh.in_dim == 2 && sh.out_dim == 3;
+    const bool alpha = sh.L == 8 && no_skips && sh.pe == 5 && sh.hidden == HID && sh.in_dim == 3 && sh.out_dim == 1;
+    B200_REQUIRE(atlas || alpha, "tensor-core IMLP: neither the atlas (2-PE10-256x6-3, skips 4,7) nor the alpha "
+                 "(3-PE5-256x6-1) architecture");
+  }
   else {
     bool plain = (sh.L == 6 || sh.L == 4) && sh.pe == 0 && sh.hidden == HID && sh.in_dim == 3 && sh.out_dim == 2;
     for (int l = 1; plain && l < sh.L; ++l) plain = !sh.skip[l];
@@ -1628,7 +1671,8 @@ int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, co
   fill_fwd(P, sh, pl.im, x, y, params, (int)rows, 1, nullptr);
   P.in_scale = 1.0f; P.in_shift = 0.0f; P.store_images = training ? 1 : 0; P.tanh_out = sh.tanh_out ? 1 : 0;
   const int grid = min(sm_count(), (int)(rows / TM));
-  if (is_atlas) tc_fwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  if (is_atlas && sh.in_dim == 3) tc_fwd_kernel<true, 8, 1><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  else if (is_atlas) tc_fwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
   else if (sh.L == 4) tc_fwd_kernel<false, 4><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   else tc_fwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   B200_CHECK_LAUNCH();
@@ -1655,7 +1699,8 @@ int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, f
   P.in_scale = 1.0f; P.d_in_accumulate = 0; P.tanh_out = sh.tanh_out ? 1 : 0; P.flow_groups = 0;
   for (int l = 0; l < sh.L; ++l) { P.w_off[l] = sh.w_off[l]; P.b_off[l] = sh.b_off[l]; }
   const int grid = min(sm_count(), (int)(rows / TM));
-  if (is_atlas) tc_bwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  if (is_atlas && sh.in_dim == 3) tc_bwd_kernel<true, 8, 1><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
+  else if (is_atlas) tc_bwd_kernel<true><<<grid, TC_THREADS, KCfg<true>::SMEM, st>>>(P);
   else if (sh.L == 4) tc_bwd_kernel<false, 4><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   else tc_bwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   B200_CHECK_LAUNCH();

@@ -313,8 +313,10 @@ typedef struct B200SegConfig {
  *   7 global rigidity2  8 flow1  9 flow2  10 flow alpha  11 bootstrapping  12 n_fwd  13 n_bwd    */
 #define B200_SEG_LOSS_FLOATS 16
 
-/* 1 = the mapping architecture, 2 = the atlas architecture of the stage-1 scripts (tensor-core
- * kernels exist), 0 = any other shape (fp32 kernels only), -1 = invalid descriptor */
+/* Which tensor-core kernels serve a network shape: 1 = mapping-shaped (3 -> 256 x {2,4} -> 2, no
+ * encoding: both mappings of the scripts), 2 = the atlas network (2 -> PE 10 -> 256 x 6 -> 3, skips 4
+ * and 7), 3 = the alpha network of the segmentation variant (3 -> PE 5 -> 256 x 6 -> 1), 0 = any
+ * other shape (fp32 kernels only), -1 = invalid descriptor */
 int b200_mlp_tc_architecture(const B200MlpDesc* d);
 
 /* parameters / gradients / Adam moments are ONE flat buffer: the four networks in the order of

@@ -4,7 +4,7 @@ from the reference's own functions (tests/golden/seg_iteration.npz).  Needs a GP
 Tolerances:
   fp32 path (every network on the CUDA-core kernels): losses rtol 2e-4; parameter gradients |err| <= 1e-3 max|grad|
   per tensor (+ a network-scale floor for near-cancelling bias gradients); network outputs 2e-5.
-  tensor-core path (both mappings and the atlas on tcgen05, 2-term fp16 split; alpha in fp32): losses rtol 2e-3;
+  tensor-core path (all four networks on tcgen05, 2-term fp16 split operands): losses rtol 2e-3;
   gradients 1.5e-2 max|grad| per tensor (the bound of the stand-alone tensor-core IMLP tests).
 """
 import numpy as np
@@ -44,7 +44,7 @@ def test_param_layout_and_order():
     assert tr.offsets["mapping1"] == 0 and tr.offsets["mapping2"] >= S.MAPPING1_SPEC.num_params()
     assert N.lib().b200_mlp_tc_architecture(tr.descs["mapping1"]) == 1
     assert N.lib().b200_mlp_tc_architecture(tr.descs["mapping2"]) == 1      # 4-layer mapping: same tensor-core kernels
-    assert N.lib().b200_mlp_tc_architecture(tr.descs["alpha"]) == 0
+    assert N.lib().b200_mlp_tc_architecture(tr.descs["alpha"]) == 3         # PE 5 / one output: the alpha variant
     assert N.lib().b200_mlp_tc_architecture(tr.descs["atlas"]) == 2
     torch.manual_seed(int(4321))
     tr.init_like_reference()

@@ -176,7 +176,7 @@ def test_tc_render_parity(golden_dir):
     assert abs(A.psnr(data["frames"][:, :, :, 2], img.cpu()) - O.psnr(data["frames"][:, :, :, 2], ref)) < 1e-3
 
 
-@pytest.mark.parametrize("which", ["mapping", "atlas", "mapping4"])
+@pytest.mark.parametrize("which", ["mapping", "atlas", "mapping4", "alpha"])
 def test_imlp_class_on_tensor_cores(golden_dir, which, monkeypatch):
     """The drop-in `IMLP` class (b200_mlp_forward / b200_mlp_backward with B200_PREC_TC) against the oracle network
     with the same parameters: forward |err| <= 5e-6 (mapping) / 5e-5 (atlas, positional-encoding amplification),
@@ -199,11 +199,18 @@ def test_imlp_class_on_tensor_cores(golden_dir, which, monkeypatch):
         torch.manual_seed(77)
         params = O.init_mlp(spec)
         scale, tol = 2.0, 5e-6
+    elif which == "alpha":           # the alpha network of the segmentation variant: 3 -> PE 5 -> 256 x 6 -> 1, no skips
+        net = IMLP(input_dim=3, output_dim=1, hidden_dim=256, use_positional=True, positional_dim=5, num_layers=8,
+                   skip_layers=[], verbose=False)
+        spec = O.MlpSpec(3, 1, 256, True, 5, (), 8)
+        torch.manual_seed(78)
+        params = O.init_mlp(spec)
+        scale, tol = 2.0, 2e-5
     else:
         net = IMLP(input_dim=2, output_dim=3, hidden_dim=256, use_positional=True, positional_dim=10, num_layers=8,
                    skip_layers=[4, 7], verbose=False)
         spec, params, scale, tol = O.ATLAS_SPEC, ap, 1.0, 5e-5
-    assert net._tc_arch == (2 if which == "atlas" else 1)
+    assert net._tc_arch == {"mapping": 1, "mapping4": 1, "atlas": 2, "alpha": 3}[which]
     net.load_state_dict(O.state_dict_of(params))
     net = net.to(DEV)
     g = torch.Generator().manual_seed(4)
@@ -224,6 +231,7 @@ def test_imlp_class_on_tensor_cores(golden_dir, which, monkeypatch):
         for kind, t in (("weight", p64[2 * i]), ("bias", p64[2 * i + 1])):
             e = (views[f"hidden.{i}.{kind}"].cpu().double() - t.grad).norm() / t.grad.norm()
             assert float(e) <= (1.5e-2 if which == "atlas" else 3e-3), (which, i, kind, float(e))
+    print(which, "tensor-core IMLP: forward max err", float((y.detach().cpu() - y_ref).abs().max()))
     if which == "atlas":
         e = (xd.grad.cpu().double() - x64.grad).norm() / x64.grad.norm()
         assert float(e) <= 1.5e-2, float(e)
