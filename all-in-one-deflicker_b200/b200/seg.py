@@ -92,6 +92,7 @@ class SegTrainer:
         self._pin_loss = torch.zeros(N.SEG_LOSS_FLOATS, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
         self._ws = None
         self._render_ws = None
+        self._graphs = {}
 
     # ------------------------------------------------------------------ parameters / state dicts
     def _views(self, flat, which):
@@ -197,11 +198,37 @@ class SegTrainer:
                                         0.9, 0.999, 1e-8, 1.0, N.ptr(self.step_count if step is None else step),
                                         N.current_stream()), "b200_adam_step")
 
-    def step(self, it: int):
-        """One loop trip on the indices in self.indices (device): losses + gradients, then one Adam update of all four
-        networks (same lr / betas in every group, so one sweep over the flat buffer)."""
+    def _iteration(self, it: int):
         self.loss_grad(it)
         self.adam()
+
+    def step(self, it: int, use_graph: bool = True):
+        """One loop trip on the indices in self.indices (device): losses + gradients, then one Adam update of all four
+        networks (same lr / betas in every group, so one sweep over the flat buffer).  The trip is captured once per
+        regime (global rigidity on / off, bootstrapping on / off) in a CUDA graph and replayed."""
+        if not use_graph or self.device.type != "cuda":
+            self._iteration(it)
+            return self.losses
+        cfg = self._config(it)
+        key = (int(cfg.with_global), float(cfg.bootstrapping_factor))
+        g = self._graphs.get(key)
+        if g is None:
+            # eager warm-up on a side stream (builds the cached job tables), state restored afterwards; then capture
+            state = (self.params, self.exp_avg, self.exp_avg_sq, self.step_count)
+            snap = [t.clone() for t in state]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._iteration(it)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for t, c in zip(state, snap):
+                t.copy_(c)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._iteration(it)
+            self._graphs[key] = g
+        g.replay()
         return self.losses
 
     def step_host(self, inds_cpu: torch.Tensor, it: int) -> np.ndarray:

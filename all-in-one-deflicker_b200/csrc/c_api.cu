@@ -17,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local bool g_persistent_ws = false;
+PersistentWorkspaceScope::PersistentWorkspaceScope() : prev(g_persistent_ws) { g_persistent_ws = true; }
+PersistentWorkspaceScope::~PersistentWorkspaceScope() { g_persistent_ws = prev; }
+
 static long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
@@ -268,7 +272,7 @@ int b200_mlp_forward(const B200MlpDesc* d, const float* params, const float* x, 
     int arch; int64_t rows_pad; TcCallPlan pl;
     B200_PROPAGATE(tc_call_prepare(d, rows, ws, ws_bytes, &s, &arch, &rows_pad, &pl));
     B200_PROPAGATE(launch_pack_rows(x, s.in_dim, s.in_dim, pl.x, arch == 2 ? 2 : 4, rows, rows_pad, st));
-    B200_PROPAGATE(tc_single_forward(s, arch >= 2, params, pl.x, pl.y, rows_pad, training != 0, pl.tc, st));
+    B200_PROPAGATE(tc_single_forward(s, arch >= 2, params, pl.x, pl.y, rows_pad, training != 0, pl.tc, g_persistent_ws, st));
     B200_CHECK_CUDA(cudaMemcpyAsync(y, pl.y, (size_t)rows * s.out_dim * 4, cudaMemcpyDeviceToDevice, st));
     return B200_OK;
   }
@@ -307,7 +311,7 @@ int b200_mlp_backward(const B200MlpDesc* d, const float* params, const float* x,
     B200_CHECK_CUDA(cudaMemsetAsync(pl.gmax2, 0, 8, st));
     B200_PROPAGATE(launch_absmax(pl.dy, rows_pad * s.out_dim, pl.gmax2 + (arch == 1 ? 1 : 0), st));
     B200_PROPAGATE(tc_single_backward(s, arch >= 2, params, dparams, pl.x, pl.y, pl.dy, (arch == 2 && dx) ? pl.d_in : nullptr,
-                                      pl.gmax2, rows_pad, pl.tc, st));
+                                      pl.gmax2, rows_pad, pl.tc, g_persistent_ws, st));
     if (arch == 2 && dx) B200_CHECK_CUDA(cudaMemcpyAsync(dx, pl.d_in, (size_t)rows * 8, cudaMemcpyDeviceToDevice, st));
     return B200_OK;
   }

@@ -1649,23 +1649,69 @@ static int check_single(const MlpShape& sh, bool is_atlas, int64_t rows, cudaStr
     B200_REQUIRE(plain, "tensor-core IMLP: not a mapping architecture (3 -> 256 x {2,4} -> 2, no encoding, no skips)");
   }
   B200_REQUIRE(rows > 0 && rows % TM == 0 && rows / TM < (1 << 20), "rows must be a positive multiple of %d", TM);
+  return B200_OK;
+}
+
+static bool stream_is_capturing(cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);
-  B200_REQUIRE(cs != cudaStreamCaptureStatusActive, "the stand-alone tensor-core IMLP calls are not graph-capturable");
-  return B200_OK;
+  return cs == cudaStreamCaptureStatusActive;
+}
+
+// Job tables of stand-alone calls whose caller keeps ONE workspace and ONE set of parameter / gradient buffers alive
+// across calls (the segmentation step): like the fused loop's tables they are a pure function of pointers and geometry,
+// live in their own device allocations (never recycled) and are uploaded by the first eager call, after which the
+// calls are graph-capturable.  Ephemeral callers (the IMLP class: a fresh workspace per call) keep their tables
+// inside the workspace and upload them on every call.
+struct SingleTab {
+  int dev; const void* ws; int64_t rows; const void* params; const void* grads; bool is_atlas; int L, pe, in_dim; bool training;
+  PrepJobs* d_prep = nullptr; WgradItems* d_wg = nullptr; int n_prep = -1, n_wg = -1;
+};
+static std::vector<SingleTab*> g_single_tabs;
+
+static SingleTab* single_tab(const MlpShape& sh, bool is_atlas, const void* ws, int64_t rows, const void* params,
+                             const void* grads, bool training) {
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_tabs_mutex);
+  for (SingleTab* t : g_single_tabs)
+    if (t->dev == dev && t->ws == ws && t->rows == rows && t->params == params && t->is_atlas == is_atlas && t->L == sh.L &&
+        t->pe == sh.pe && t->in_dim == sh.in_dim && t->training == training && (grads == nullptr || t->grads == nullptr || t->grads == grads)) {
+      if (grads && !t->grads) t->grads = grads;
+      return t;
+    }
+  if ((int)g_single_tabs.size() >= MAX_TABLES) return nullptr;
+  SingleTab* t = new SingleTab{dev, ws, rows, params, grads, is_atlas, sh.L, sh.pe, sh.in_dim, training};
+  g_single_tabs.push_back(t);
+  return t;
 }
 
 // x: mapping [rows][4], atlas [rows][2] (network input itself).  y: [rows][out_dim].
 int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, const float* x, float* y, int64_t rows,
-                      bool training, char* ws, cudaStream_t st) {
+                      bool training, char* ws, bool persistent, cudaStream_t st) {
   B200_PROPAGATE(check_single(sh, is_atlas, rows, st));
   SinglePlan pl;
   plan_single(sh, is_atlas, rows, ws, &pl);
   static thread_local PrepJobs pj;
-  pj.n = 0;
-  prep_jobs_for_net(pj, sh, pl.im, params, is_atlas, training);
-  B200_CHECK_CUDA(cudaMemcpyAsync(pl.d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
-  tc_prep_kernel<<<pj.n * 4, 128, 0, st>>>(pl.d_prep);
+  PrepJobs* d_prep = pl.d_prep;
+  int n_prep = 0;
+  SingleTab* tab = persistent ? single_tab(sh, is_atlas, ws, rows, params, nullptr, training) : nullptr;
+  if (tab && tab->n_prep >= 0) {
+    d_prep = tab->d_prep; n_prep = tab->n_prep;
+  } else {
+    B200_REQUIRE(!stream_is_capturing(st), "stand-alone tensor-core IMLP call under stream capture before its job tables "
+                 "exist: run the same call once eagerly first (persistent workspaces only)");
+    pj.n = 0;
+    prep_jobs_for_net(pj, sh, pl.im, params, is_atlas, training);
+    n_prep = pj.n;
+    if (tab) {
+      B200_CHECK_CUDA(cudaMalloc(&tab->d_prep, sizeof(PrepJobs)));
+      B200_CHECK_CUDA(cudaMemcpy(tab->d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice));
+      tab->n_prep = n_prep; d_prep = tab->d_prep;
+    } else {
+      B200_CHECK_CUDA(cudaMemcpyAsync(pl.d_prep, &pj, sizeof(PrepJobs), cudaMemcpyHostToDevice, st));
+    }
+  }
+  tc_prep_kernel<<<n_prep * 4, 128, 0, st>>>(d_prep);
   B200_CHECK_LAUNCH();
   FwdParams P{};
   fill_fwd(P, sh, pl.im, x, y, params, (int)rows, 1, nullptr);
@@ -1683,16 +1729,32 @@ int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, co
 // rows), gmax: device int holding the bits of max|dy| (>= 0), d_in: atlas only, [rows][2] or null.
 int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, float* grads, const float* x,
                        const float* y, const float* dy, float* d_in, int* gmax2, int64_t rows, char* ws,
-                       cudaStream_t st) {
+                       bool persistent, cudaStream_t st) {
   B200_PROPAGATE(check_single(sh, is_atlas, rows, st));
   SinglePlan pl;
   plan_single(sh, is_atlas, rows, ws, &pl);
   static thread_local WgradItems wi;
-  wi.n = 0;
-  WgProto protos[16]; int np = 0;
-  protos_for_net(protos, np, sh, pl.im, grads, is_atlas, 1);
-  apportion_items(wi, protos, np, (int)rows, 0);
-  B200_CHECK_CUDA(cudaMemcpyAsync(pl.d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice, st));
+  WgradItems* d_wg = pl.d_wg;
+  int n_wg = 0;
+  SingleTab* tab = persistent ? single_tab(sh, is_atlas, ws, rows, params, grads, true) : nullptr;
+  if (tab && tab->n_wg >= 0) {
+    d_wg = tab->d_wg; n_wg = tab->n_wg;
+  } else {
+    B200_REQUIRE(!stream_is_capturing(st), "stand-alone tensor-core IMLP backward under stream capture before its job "
+                 "tables exist: run the same call once eagerly first (persistent workspaces only)");
+    wi.n = 0;
+    WgProto protos[16]; int np = 0;
+    protos_for_net(protos, np, sh, pl.im, grads, is_atlas, 1);
+    apportion_items(wi, protos, np, (int)rows, 0);
+    n_wg = wi.n;
+    if (tab) {
+      B200_CHECK_CUDA(cudaMalloc(&tab->d_wg, sizeof(WgradItems)));
+      B200_CHECK_CUDA(cudaMemcpy(tab->d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice));
+      tab->n_wg = n_wg; d_wg = tab->d_wg;
+    } else {
+      B200_CHECK_CUDA(cudaMemcpyAsync(pl.d_wg, &wi, sizeof(WgradItems), cudaMemcpyHostToDevice, st));
+    }
+  }
   BwdParams P{};
   P.dy = dy; P.y = y; P.x = x; P.d_in = d_in; P.params = params; P.grads = grads; P.img = pl.im;
   P.cap = (int)rows; P.n_groups = 1; P.n_valid = nullptr; P.gmax_bits = gmax2;      // [0] atlas scale, [1] mapping scale
@@ -1704,7 +1766,7 @@ int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, f
   else if (sh.L == 4) tc_bwd_kernel<false, 4><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   else tc_bwd_kernel<false><<<grid, TC_THREADS, KCfg<false>::SMEM, st>>>(P);
   B200_CHECK_LAUNCH();
-  tc_wgrad_kernel<<<min(wi.n, sm_count()), WG_THREADS, WG_SMEM, st>>>(pl.d_wg, nullptr, gmax2);
+  tc_wgrad_kernel<<<min(n_wg, sm_count()), WG_THREADS, WG_SMEM, st>>>(d_wg, nullptr, gmax2);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -10,6 +10,7 @@
 // Networks whose shape has tensor-core kernels run on them when the configuration asks for B200_PREC_TC.
 #include "atlas_internal.cuh"
 #include "seg_loss_math.h"
+#include "tc_api.cuh"
 
 namespace b200 {
 
@@ -321,6 +322,9 @@ int b200_seg_loss_grad(const B200SegConfig* cfg, const B200Video* video, const f
   B200_REQUIRE(video->t_begin == 0 && video->t_end == video->T, "the segmentation variant needs the whole video resident");
   SegPlan pl;
   B200_PROPAGATE(seg_prepare(cfg, ws, ws_bytes, &pl));
+  // the caller keeps `ws`, `params` and `grads` across trips: the networks' job tables are cached after the first
+  // (eager) trip, which also makes the whole trip graph-capturable
+  PersistentWorkspaceScope persistent;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int cap = pl.cap, B = cfg->batch;
   const B200MlpDesc* descs[4] = {&cfg->mapping1, &cfg->mapping2, &cfg->alpha, &cfg->atlas};
@@ -415,6 +419,7 @@ int b200_mlp_pretrain_loss_grad(const B200MlpDesc* d, int32_t batch, float uv_ma
     set_error("workspace too small: need %lld bytes", (long long)(pl.bytes + 1024));
     return B200_ERR_WORKSPACE;
   }
+  PersistentWorkspaceScope persistent;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t total = b200_mlp_layout(d, nullptr, nullptr);
   const int prec = (precision == B200_PREC_TC && b200_mlp_tc_architecture(d) > 0) ? B200_PREC_TC : B200_PREC_FP32;
@@ -482,6 +487,7 @@ int b200_seg_render(const B200SegConfig* cfg, const float* params, int32_t H, in
   }
   int64_t offs[4];
   B200_REQUIRE(b200_seg_param_floats(cfg, offs) > 0, "invalid network descriptor");
+  PersistentWorkspaceScope persistent;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const B200MlpDesc* descs[4] = {&cfg->mapping1, &cfg->mapping2, &cfg->alpha, &cfg->atlas};
   int prec[4];

@@ -40,10 +40,21 @@ int tc_infer_forward(const MlpShape& ms, const MlpShape& as, const float* params
 
 // stand-alone IMLP (one network, autograd): see mlp_tc.cu
 int64_t tc_single_workspace_bytes(const MlpShape& sh, bool is_atlas, int64_t rows);
+// persistent: the caller keeps this workspace and these parameter / gradient buffers across calls -> job tables are
+// cached in their own device allocations and the calls become graph-capturable after one eager call
 int tc_single_forward(const MlpShape& sh, bool is_atlas, const float* params, const float* x, float* y, int64_t rows,
-                      bool training, char* ws, cudaStream_t st);
+                      bool training, char* ws, bool persistent, cudaStream_t st);
 int tc_single_backward(const MlpShape& sh, bool is_atlas, const float* params, float* grads, const float* x,
-                       const float* y, const float* dy, float* d_in, int* gmax2, int64_t rows, char* ws, cudaStream_t st);
+                       const float* y, const float* dy, float* d_in, int* gmax2, int64_t rows, char* ws, bool persistent,
+                       cudaStream_t st);
+
+// Scope guard used by entry points that own a persistent workspace (the segmentation step): while alive,
+// b200_mlp_forward / backward calls made by this thread use the cached-table path above.
+struct PersistentWorkspaceScope {
+  PersistentWorkspaceScope();
+  ~PersistentWorkspaceScope();
+  bool prev;
+};
 
 int tc_debug_wgrad(long long* cycles, int* shapes, int max_ctas);
 

@@ -259,9 +259,11 @@ def seg_line(args, rank, world, local):
         i = k[0]; k[0] += 1
         tr.indices.copy_(inds_d[i % 8])
         tr.step(0 if (i % steps) < steps // 2 else 6000)
+    tr.indices.copy_(inds_d[0])
     l0 = N.lib().b200_launch_count()
+    tr.step(0, use_graph=False)                       # kernels of one trip, counted on an eager (un-captured) trip
+    n_launch = float(N.lib().b200_launch_count() - l0)
     ms = _event_ms(step, steps, warm)
-    n_launch = (N.lib().b200_launch_count() - l0) / (steps + warm)
     k[0] = 0
     ems = _event_ms(lambda: (tr.step_host(inds_h[k[0] % 8], 0 if k[0] % steps < steps // 2 else 6000), k.__setitem__(0, k[0] + 1)),
                     steps, 2)
@@ -270,7 +272,8 @@ def seg_line(args, rank, world, local):
            "dtype": ("mapping1 + atlas: 2-term fp16 split operands / fp32 accumulate (tcgen05); mapping2 + alpha: fp32 CUDA cores"
                      if prec == N.PREC_TC else "fp32"), "data": "synthetic", "config": config,
            "e2e": {"value": 1000.0 / ems, "unit": unit, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": N.SEG_LOSS_FLOATS * 4},
-           "gpu_launches": int(round(n_launch * steps)), "launches_per_step": n_launch, "losses_last": tr.loss_dict()}
+           "gpu_launches": int(round(n_launch * steps)), "launches_per_step": n_launch,
+           "cuda_graph": "one replayed graph per regime (global rigidity on / off)", "losses_last": tr.loss_dict()}
     if not args.no_cpu_baseline:
         v = cpu_leg(2, threads)
         out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",

@@ -96,6 +96,16 @@ def test_seg_trajectory_and_render(golden_dir, precision):
         got = tr.loss_dict(out)
         np.testing.assert_allclose([got[k] for k in keys], z["traj_losses"][it], rtol=5e-3 if tc else 5e-4)
     assert int(tr.step_count) == 3
+    assert len(tr._graphs) == 1                      # the three trips replayed one captured graph
+    # the same three trips launched eagerly (no graph) give the same losses up to atomic summation order
+    tr2 = _trainer(z, video, masks, nets, precision, B)
+    for it in range(3):
+        tr2.indices.copy_(torch.from_numpy(z["traj_inds"][it]).reshape(-1))
+        tr2.step(it, use_graph=False)
+    torch.cuda.synchronize()
+    eager, replay = tr2.loss_dict(), tr.loss_dict()
+    for k in keys:
+        np.testing.assert_allclose(replay[k], eager[k], rtol=2e-3 if tc else 2e-4, err_msg=k)
     for k in ORDER:
         head = tr.param_views(k)["hidden.0.weight"].flatten()[:64].cpu().numpy()
         # three Adam steps move every weight by <= 3e-4; the sign pattern of the first steps is what can differ
