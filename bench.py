@@ -302,13 +302,22 @@ def main():
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
+    mid = torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(Wm, total):
+        if i == half:
+            mid.record()                  # regime switch (i > stop_global_rigidity): an event record, no extra work
         trainer.indices.copy_(inds_dev[i]); trainer.step(it_of(i))
     stop.record()
     barrier()
     wall1 = time.perf_counter()
     ms = start.elapsed_time(stop)
+    n_with = max(0, min(total, half) - Wm)
+    regimes = None
+    if 0 < n_with < K:
+        regimes = {"with_global_rigidity (i <= 5000)": {"steps": n_with, "it_per_s": n_with / (start.elapsed_time(mid) / 1000.0)},
+                   "without (i > 5000)": {"steps": K - n_with, "it_per_s": (K - n_with) / (mid.elapsed_time(stop) / 1000.0)},
+                   "note": "this rank's device time; the headline value is all K steps"}
     losses_last = trainer.losses.cpu().numpy().copy()
     if world > 1:
         tms = torch.tensor([ms], device=dev)
@@ -417,6 +426,8 @@ def main():
                 "roofline": roof,
                 "clocks": sampler.summary(wall0, wall1) if sampler else None,
                 "losses_last": [float(x) for x in losses_last[:6]]}
+        if regimes:
+            line["regimes"] = regimes
         line.update(extras)
         cores = os.cpu_count() or 1
         threads = min(cores, CPU_THREADS)

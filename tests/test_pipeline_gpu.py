@@ -140,6 +140,7 @@ def test_seg_script_end_to_end(tmp_path):
     assert len(alphas) == T
     a = cv2.imread(alphas[2], cv2.IMREAD_GRAYSCALE).astype(np.float64) / 255
     gt = cv2.imread(os.path.join(seg_dir, "00002.png"), cv2.IMREAD_GRAYSCALE) > 127
+    print("seg e2e: alpha inside / outside the matte after 200 trips:", a[gt].mean(), a[~gt].mean())
     assert a[gt].mean() > a[~gt].mean() + 0.1          # 200 bootstrapped iterations already separate the matte
     marker = glob.glob(str(res / "000200" / "PSNR_*"))
     assert len(marker) == 1 and np.isfinite(float(os.path.basename(marker[0])[len("PSNR_"):]))
