@@ -19,6 +19,15 @@ __global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__
   y[i] = (s[0] + s[1] + s[W] + s[W + 1]) * 0.25f;
 }
 
+// launcher for other translation units (conv_tma.cu pools feature maps with it)
+int launch_avgpool2(const float* x, float* y, int64_t planes, int H, int W, cudaStream_t st) {
+  const int64_t total = planes * (H / 2) * (W / 2);
+  if (total <= 0) return B200_OK;
+  avgpool2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, y, planes, H, W);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 struct LookupArgs {
   const float* level[4]; int LH[4], LW[4];
   const float* coords;      // [B][2][H1][W1]  (x, y)

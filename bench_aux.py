@@ -346,7 +346,7 @@ def driver_line(args, rank, world, local):
         roof = {"bound": "tensor", "kernel": "conv2d_tma_kernel (BasicUpdateBlock, one refinement iteration)",
                 "achieved": ub_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ub_tf / peak_tf, "kernel_ms": ub_ms,
                 "share_of_step": 40 * ub_ms / ms, "traffic": None, "peak_source": how,
-                "hbm": {"kernel": "corr_build (conv2d_tma_kernel split + avgpool2_kernel)", "achieved": vol / cb_ms / 1e6,
+                "hbm": {"kernel": "corr_build (conv2d_tma_kernel, split operands: level 0 + three pooled-feature GEMMs)", "achieved": vol / cb_ms / 1e6,
                         "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": vol / cb_ms / 1e6 / float(peaks["hbm_gbs"]),
                         "kernel_ms": cb_ms, "share_of_step": 2 * cb_ms / ms}}
         config = {"workload": "RAFT flow pre-pass, 1080x1920 synthetic frame pair, both directions, 20 refinement "
