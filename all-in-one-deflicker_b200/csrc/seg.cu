@@ -51,6 +51,9 @@ static const int kNetRows[4] = {G_COUNT, G_COUNT, A_COUNT, SEG_ATLAS_ROWS};   //
 
 static int plan_seg(const B200SegConfig* cfg, char* base, SegPlan* pl) {
   B200_REQUIRE(cfg && cfg->batch > 0 && cfg->batch <= 16384, "samples_batch must be in [1, 16384]");
+  B200_REQUIRE(cfg->precision == B200_PREC_FP32 || cfg->precision == B200_PREC_TC, "unknown precision %d", cfg->precision);
+  B200_REQUIRE(cfg->uv_mapping_scale != 0.f && cfg->derivative_amount != 0.f && cfg->global_derivative_amount != 0.f,
+               "uv_mapping_scale and the derivative amounts must be non-zero");
   const B200MlpDesc* descs[4] = {&cfg->mapping1, &cfg->mapping2, &cfg->alpha, &cfg->atlas};
   int64_t off = 0;
   for (int k = 0; k < 4; ++k) {

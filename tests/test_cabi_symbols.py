@@ -102,3 +102,27 @@ def test_conv_tma_geometry_host_side():
     assert lib.b200_corr_build_tc_workspace_bytes(256, 135, 240) > 2 * 135 * 240 * 256 * 2
     assert lib.b200_corr_build_tc_workspace_bytes(256, 4, 240) == -1
     assert lib.b200_corr_pyramid_floats(16, 24) == 384 * (384 + 96 + 24 + 6)
+
+
+def test_seg_entry_points_validate_their_arguments():
+    """Host-side validation of the segmentation entry points (no GPU work): sizes, layouts, loud errors."""
+    import ctypes as C
+    from b200 import seg as SG
+    lib = N.lib()
+    d = SG.seg_descs(SG.SEG_DEFAULTS)
+    cfg = N.SegConfig(10000, 1, N.PREC_FP32, 768, 0.8, 1.0, 100.0, 5000.0, 1000.0, 1.0, 5.0, 50.0, 500.0, 4900.0, 1000.0, 2000.0,
+                      d["mapping1"], d["mapping2"], d["alpha"], d["atlas"])
+    offs = (C.c_int64 * 4)()
+    total = lib.b200_seg_param_floats(C.byref(cfg), offs)
+    assert list(offs) == sorted(offs) and offs[0] == 0 and 1217152 <= total <= 1217152 + 64          # 264706 + 133122 + 402945 + 416379 parameters, each tensor padded to 4 floats
+    assert [lib.b200_mlp_tc_architecture(C.byref(d[k])) for k in ("mapping1", "mapping2", "alpha", "atlas")] == [1, 1, 3, 2]
+    assert lib.b200_seg_workspace_bytes(C.byref(cfg)) > 0 and lib.b200_seg_render_workspace_bytes(C.byref(cfg), 65536) > 0
+    cfg.batch = 0
+    assert lib.b200_seg_workspace_bytes(C.byref(cfg)) == -1 and b"samples_batch" in lib.b200_last_error()
+    cfg.batch, cfg.precision = 64, 7
+    assert lib.b200_seg_workspace_bytes(C.byref(cfg)) == -1 and b"precision" in lib.b200_last_error()
+    cfg.precision = N.PREC_FP32
+    cfg.alpha.output_dim = 2
+    assert lib.b200_seg_workspace_bytes(C.byref(cfg)) == -1 and b"alpha network" in lib.b200_last_error()
+    assert lib.b200_mlp_pretrain_workspace_bytes(C.byref(d["atlas"]), 10000) == -1      # pre-training is for 3 -> 2 networks
+    assert lib.b200_eval_maps_workspace_bytes(C.byref(d["mapping1"]), 432 * 768) > 0
