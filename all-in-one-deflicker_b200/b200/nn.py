@@ -60,10 +60,47 @@ def _check(t):
     return t
 
 
+_chain_buffers = {}        # (device, n, cin, h, w, kh, kw, ph, pw, tag) -> zero-initialised packed-input buffer
+
+
+class Chain:
+    """The packed fp16 NHWC input of ONE consumer convolution (stride 1, zero padding, Cin * KW > 64), filled directly
+    by the epilogues of the convolutions that produce it (`conv2d(..., chain_out=chain)`), then consumed by
+    `conv2d(chain, w, ...)`: no fp32 tensor in between and no repack kernel.  tcgen05 path only.  Buffers are cached per
+    geometry and zeroed once: producers overwrite the whole interior every time, halo and channel padding stay zero."""
+
+    def __init__(self, n, cin, h, w, kernel, pad, device, tag=""):
+        kh, kw = kernel
+        ph, pw = (pad, pad) if isinstance(pad, int) else pad
+        self.n, self.cin, self.h, self.w = n, cin, h, w
+        self.desc = N.ConvDesc(n, cin, h, w, cin, 0, 8, kh, kw, 1, ph, pw, 0, 1, 8, 0, 0, 1.0, 0, 0, 0)
+        if not N.lib().b200_conv_tma_chainable(C.byref(self.desc)):
+            raise N.B200Error("this convolution cannot consume a chained (pre-packed) input")
+        # `tag` separates buffers of equal geometry that are alive at the same time (a consumer whose own output is
+        # chained into another buffer of the same shape must not read and write one allocation)
+        key = (str(device), n, cin, h, w, kh, kw, ph, pw, tag)
+        buf = _chain_buffers.get(key)
+        if buf is None:
+            nbytes = int(N.lib().b200_conv_tma_workspace_bytes(C.byref(self.desc)))
+            buf = _chain_buffers[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.buf = buf
+
+    @staticmethod
+    def available():
+        return _conv_precision == "tc"
+
+
 def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", upsample=1, out=None, out_c_off=0,
-           in_slice=None, residual=None, res_c_off=0, out_scale=1.0, precision=None, upsample_mode="nearest"):
+           in_slice=None, residual=None, res_c_off=0, out_scale=1.0, precision=None, upsample_mode="nearest",
+           chain_out=None, chain_c_off=0, keep_fp32=True):
     """y = act(conv(pad(upsample(x[:, in_slice]))) + b) * out_scale (+ residual[:, res slice]) written into
-    out[:, out_c_off:out_c_off+Cout] (allocated when None).  Restates nn.Conv2d / ReflectionPad2d / Upsample."""
+    out[:, out_c_off:out_c_off+Cout] (allocated when None).  Restates nn.Conv2d / ReflectionPad2d / Upsample.
+    `x` may be a `Chain` (input already packed by its producers); `chain_out` additionally writes the result into the
+    consumer's packed input at channel `chain_c_off`, and with keep_fp32=False the fp32 tensor is not produced (returns
+    None)."""
+    if isinstance(x, Chain) or chain_out is not None:
+        return _conv2d_chained(x, w, b, stride, pad, pad_mode, act, upsample, out, out_c_off, in_slice, residual, res_c_off,
+                               out_scale, upsample_mode, chain_out, chain_c_off, keep_fp32)
     _check(x); _check(w); _check(b); _check(residual)
     mode = _conv_precision if precision is None else precision
     bilinear = 0
@@ -106,6 +143,53 @@ def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", ups
     else:
         N.check(N.lib().b200_conv2d(C.byref(d), N.ptr(x), N.ptr(w), N.ptr(b), N.ptr(residual), N.ptr(out),
                                     N.current_stream()), "b200_conv2d")
+    return out
+
+
+def _conv2d_chained(x, w, b, stride, pad, pad_mode, act, upsample, out, out_c_off, in_slice, residual, res_c_off, out_scale,
+                    upsample_mode, chain_out, chain_c_off, keep_fp32):
+    """b200_conv2d_tma_chain: packed input and / or packed output (tcgen05 path, see `Chain`)."""
+    _check(w); _check(b); _check(residual)
+    packed_in = isinstance(x, Chain)
+    bilinear = 1 if upsample_mode == "bilinear" else 0
+    if packed_in:
+        if in_slice is not None or stride != 1 or upsample != 1 or pad_mode != "zeros":
+            raise N.B200Error("a chained input feeds a plain stride-1 zero-padded convolution of the whole tensor")
+        n, c_total, h, wd = x.n, x.cin, x.h, x.w
+        dev = x.buf.device
+    else:
+        _check(x)
+        n, c_total, h, wd = x.shape
+        dev = x.device
+    c_off, cin = (0, c_total) if in_slice is None else (in_slice[0], in_slice[1] - in_slice[0])
+    cout, cin_w, kh, kw = w.shape
+    if cin_w != cin:
+        raise N.B200Error(f"weight expects {cin_w} input channels, got {cin}")
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    hu, wu = h * upsample, wd * upsample
+    oh, ow = (hu + 2 * ph - kh) // stride + 1, (wu + 2 * pw - kw) // stride + 1
+    if keep_fp32 or chain_out is None:
+        if out is None:
+            out = torch.empty(n, cout, oh, ow, dtype=torch.float32, device=dev)
+        _check(out)
+    else:
+        out = None
+    d = N.ConvDesc(n, cin, h, wd, c_total, c_off, cout, kh, kw, stride, ph, pw, 1 if pad_mode == "reflect" else 0, upsample,
+                   out.shape[1] if out is not None else cout, out_c_off if out is not None else 0, ACT[act], float(out_scale),
+                   residual.shape[1] if residual is not None else 0, res_c_off, bilinear)
+    if packed_in and (x.desc.KH, x.desc.KW, x.desc.pad_h, x.desc.pad_w) != (kh, kw, ph, pw):
+        raise N.B200Error("the chained input was packed for another filter geometry")
+    ws, nbytes = None, 0
+    if not packed_in:
+        nbytes = N.lib().b200_conv_tma_workspace_bytes(C.byref(d))
+        if nbytes <= 0:
+            raise N.B200Error("b200_conv_tma_workspace_bytes: " + N.last_error())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    N.check(N.lib().b200_conv2d_tma_chain(
+        C.byref(d), None if packed_in else N.ptr(x), N.ptr(x.buf) if packed_in else None, N.ptr(_images_for(d, w, True)),
+        N.ptr(b), N.ptr(residual), N.ptr(out), N.ptr(chain_out.buf) if chain_out is not None else None,
+        C.byref(chain_out.desc) if chain_out is not None else None, int(chain_c_off), N.ptr(ws), nbytes,
+        N.current_stream()), "b200_conv2d_tma_chain")
     return out
 
 

@@ -38,6 +38,9 @@ struct ConvTmaArgs {
   int b_group, b_stage;                                // weight chunks (x taps) per B stage, bytes per B stage
   int split;                                           // 1: both operands are (hi, lo) fp16 pairs, 3 MMAs per product
   int resident;                                        // 1: the whole weight image stays in shared memory (narrow layers)
+  // chained output: the result is ALSO (or only, y == nullptr) written as fp16 into the packed input of the next
+  // convolution: [n][yp_hp2][yp_wp2][yp_cp] with its zero halo (yp_pad_h, yp_pad_w), at channel offset yp_c_off
+  __half* yp; int yp_hp2, yp_wp2, yp_cp, yp_pad_h, yp_pad_w, yp_c_off;
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -46,6 +49,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 template <int ACT>
@@ -57,11 +65,12 @@ __device__ __forceinline__ float tm_act(float v) {
   return v;
 }
 
-// 32 accumulator columns of one pixel -> bias, activation, scale, residual, NCHW stores (one channel plane apart)
+// 32 accumulator columns of one pixel -> bias, activation, scale, residual; NCHW fp32 stores (one channel plane apart,
+// yq may be null) and / or 32 consecutive fp16 channels of the pixel's vector in the next layer's packed input (ypk)
 template <int ACT>
 __device__ __forceinline__ void tm_store32(const uint32_t (&raw)[32], const float* __restrict__ bias, float scale,
                                            const float* __restrict__ resp, float* __restrict__ yq, int64_t oplane,
-                                           int ncols, bool live, int lane) {
+                                           int ncols, bool live, int lane, __half* __restrict__ ypk) {
   const float bl = (bias && lane < ncols) ? __ldg(bias + lane) : 0.f;      // lane i holds bias[i] (ncols is warp-uniform)
   const int nvalid = live ? ncols : 0;
 #pragma unroll
@@ -72,13 +81,26 @@ __device__ __forceinline__ void tm_store32(const uint32_t (&raw)[32], const floa
 #pragma unroll
       for (int i = 0; i < 16; ++i, rp += oplane) radd[i] = (h * 16 + i) < nvalid ? __ldg(rp) : 0.f;
     }
-    float* p = yq + (int64_t)(h * 16) * oplane;
+    float* p = yq ? yq + (int64_t)(h * 16) * oplane : nullptr;
+    float v16[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i, p += oplane) {
+    for (int i = 0; i < 16; ++i) {
       float val = __uint_as_float(raw[h * 16 + i]) + __shfl_sync(0xffffffffu, bl, h * 16 + i);
       val = tm_act<ACT>(val) * scale;
       if (resp) val += radd[i];
-      if (h * 16 + i < nvalid) *p = val;
+      v16[i] = val;
+      if (p && h * 16 + i < nvalid) p[(int64_t)i * oplane] = val;
+    }
+    if (ypk) {                                             // channels are consecutive in NHWC: two 16-byte stores
+#pragma unroll
+      for (int g8 = 0; g8 < 2; ++g8) {
+        if (h * 16 + g8 * 8 < nvalid) {                    // ncols is a multiple of 8 on this path
+          uint4 w;
+          w.x = pack_half2(v16[g8 * 8 + 0], v16[g8 * 8 + 1]); w.y = pack_half2(v16[g8 * 8 + 2], v16[g8 * 8 + 3]);
+          w.z = pack_half2(v16[g8 * 8 + 4], v16[g8 * 8 + 5]); w.w = pack_half2(v16[g8 * 8 + 6], v16[g8 * 8 + 7]);
+          *reinterpret_cast<uint4*>(ypk + h * 16 + g8 * 8) = w;
+        }
+      }
     }
   }
 }
@@ -251,7 +273,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
       const bool live = x < a.OW;
       const int64_t sp = (int64_t)oy * a.OW + x;
       const float* resp = a.res ? a.res + ((int64_t)n * d.res_c_total + d.res_c_off) * oplane + sp : nullptr;
-      float* yp = a.y + ((int64_t)n * d.out_c_total + d.out_c_off) * oplane + sp;
+      float* yp = a.y ? a.y + ((int64_t)n * d.out_c_total + d.out_c_off) * oplane + sp : nullptr;
+      __half* ypix = (a.yp && live) ? a.yp + ((((int64_t)n * a.yp_hp2 + oy + a.yp_pad_h) * a.yp_wp2 + x + a.yp_pad_w) * a.yp_cp +
+                                               a.yp_c_off) : nullptr;
       mbar_wait(&d_full[acc], phd);
       tc_fence_after();
       for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
@@ -264,13 +288,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv2d_tma_kernel(const __grid_
         if (nvalid > 32) nvalid = 32;
         const float* bq = a.bias ? a.bias + jb : nullptr;
         const float* rq = resp ? resp + (int64_t)jb * oplane : nullptr;
-        float* yq = yp + (int64_t)jb * oplane;
+        float* yq = yp ? yp + (int64_t)jb * oplane : nullptr;
+        __half* yk = ypix ? ypix + jb : nullptr;
         switch (d.act) {
-          case 1: tm_store32<1>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
-          case 2: tm_store32<2>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
-          case 3: tm_store32<3>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
-          case 4: tm_store32<4>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
-          default: tm_store32<0>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane); break;
+          case 1: tm_store32<1>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane, yk); break;
+          case 2: tm_store32<2>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane, yk); break;
+          case 3: tm_store32<3>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane, yk); break;
+          case 4: tm_store32<4>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane, yk); break;
+          default: tm_store32<0>(raw, bq, d.out_scale, rq, yq, oplane, nvalid, live, lane, yk); break;
         }
       }
       tc_fence_before();
@@ -482,12 +507,18 @@ static int launch_weight_images(const B200ConvDesc* d, const TmaGeom& g, const f
 }
 
 // repack x into `base` (fp16, hi then lo when split) and run the convolution
+struct ChainOut { __half* yp = nullptr; int hp2 = 0, wp2 = 0, cp = 0, pad_h = 0, pad_w = 0, c_off = 0; };
+
+// x == nullptr: `base` already holds the packed input (written by the producing convolution's epilogue)
 static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float* x, char* base, const void* w_images,
-                           const float* bias, const float* residual, float* y, int split, float in_scale, cudaStream_t st) {
+                           const float* bias, const float* residual, float* y, int split, float in_scale, cudaStream_t st,
+                           const ChainOut* chain = nullptr) {
   B200_REQUIRE(g.HP2 <= 65535 && (int64_t)d->N * g.phases * g.cchunks <= 65535, "input too large for the repack grid");
-  conv_pack_input_kernel<<<dim3((g.WP2 + 31) / 32, g.HP2, d->N * g.phases * g.cchunks), 256, 0, st>>>(
-      x, reinterpret_cast<__half*>(base), *d, g.HP2, g.WP2, g.Cp, g.phases, in_scale, split ? g.pack_bytes / 2 : 0, g.fold_cf);
-  B200_CHECK_LAUNCH();
+  if (x) {
+    conv_pack_input_kernel<<<dim3((g.WP2 + 31) / 32, g.HP2, d->N * g.phases * g.cchunks), 256, 0, st>>>(
+        x, reinterpret_cast<__half*>(base), *d, g.HP2, g.WP2, g.Cp, g.phases, in_scale, split ? g.pack_bytes / 2 : 0, g.fold_cf);
+    B200_CHECK_LAUNCH();
+  }
 
   EncodeTiledFn enc = encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200_ERR_UNSUPPORTED; }
@@ -514,6 +545,10 @@ static int launch_conv_tma(const B200ConvDesc* d, const TmaGeom& g, const float*
   }
   ConvTmaArgs a{};
   a.d = *d; a.w_img = reinterpret_cast<const char*>(w_images); a.bias = bias; a.res = residual; a.y = y;
+  if (chain && chain->yp) {
+    a.yp = chain->yp; a.yp_hp2 = chain->hp2; a.yp_wp2 = chain->wp2; a.yp_cp = chain->cp; a.yp_pad_h = chain->pad_h;
+    a.yp_pad_w = chain->pad_w; a.yp_c_off = chain->c_off;
+  }
   if (g.fold_cf) { a.d.KW = 1; a.d.Cin = g.fold_cf * d->KW; }
   a.OH = g.OH; a.OW = g.OW; a.x_tiles = (g.OW + 127) / 128; a.cchunks = g.cchunks; a.n_chunks = g.n_chunks;
   a.n_tile = g.n_tile; a.n_tiles_n = g.n_tiles_n; a.phases = g.phases; a.shift = g.shift;
@@ -601,6 +636,53 @@ int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images,
     return B200_ERR_WORKSPACE;
   }
   return launch_conv_tma(d, g, x, base, w_images, bias, residual, y, 0, 1.0f, reinterpret_cast<cudaStream_t>(stream));
+}
+
+/* A convolution can consume a packed input written by its producers when its packing is the plain one: stride 1, no
+ * upsampling, zero padding, x taps not folded into the channel vector. */
+int b200_conv_tma_chainable(const B200ConvDesc* next) {
+  TmaGeom g;
+  if (!next || tma_geometry(next, &g) != B200_OK) return 0;
+  return (next->stride == 1 && next->upsample == 1 && next->pad_mode == 0 && g.fold_cf == 0 && next->in_c_off == 0 &&
+          next->in_c_total == next->Cin) ? 1 : 0;
+}
+
+int b200_conv2d_tma_chain(const B200ConvDesc* d, const float* x, void* in_packed, const void* w_images, const float* bias,
+                          const float* residual, float* y, void* out_packed, const B200ConvDesc* next, int32_t next_c_off,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+  B200_REQUIRE(d && w_images && (x || in_packed) && (y || out_packed), "null pointer");
+  TmaGeom g;
+  if (int rc = tma_geometry(d, &g)) return rc;
+  B200_REQUIRE(d->in_c_off >= 0 && d->in_c_off + d->Cin <= d->in_c_total && d->out_c_off >= 0 &&
+               d->out_c_off + d->Cout <= d->out_c_total, "channel slice out of range");
+  if (!b200_device_supports_tc()) { set_error("b200_conv2d_tma_chain needs a compute-capability 10.x device"); return B200_ERR_UNSUPPORTED; }
+  char* base = nullptr;
+  if (in_packed) {
+    B200_REQUIRE(b200_conv_tma_chainable(d), "this convolution cannot take a pre-packed input");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(in_packed) & 255) == 0, "packed input must be 256-byte aligned");
+    base = reinterpret_cast<char*>(in_packed);
+  } else {
+    B200_REQUIRE(workspace, "null workspace");
+    base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    if (base + g.pack_bytes > reinterpret_cast<char*>(workspace) + workspace_bytes) {
+      set_error("b200_conv2d_tma_chain: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)(g.pack_bytes + 256));
+      return B200_ERR_WORKSPACE;
+    }
+  }
+  ChainOut co;
+  if (out_packed) {
+    B200_REQUIRE(next && b200_conv_tma_chainable(next), "the consumer convolution cannot take a pre-packed input");
+    TmaGeom gn;
+    if (int rc = tma_geometry(next, &gn)) return rc;
+    B200_REQUIRE(next->N == d->N && next->H == g.OH && next->W == g.OW, "consumer geometry does not match this output");
+    B200_REQUIRE(next_c_off >= 0 && next_c_off + d->Cout <= next->Cin && (next_c_off & 7) == 0 && (d->Cout & 7) == 0,
+                 "chained channel slice must lie inside the consumer's input and be a multiple of 8 channels");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(out_packed) & 255) == 0, "packed output must be 256-byte aligned");
+    co.yp = reinterpret_cast<__half*>(out_packed); co.hp2 = gn.HP2; co.wp2 = gn.WP2; co.cp = gn.Cp;
+    co.pad_h = next->pad_h; co.pad_w = next->pad_w; co.c_off = next_c_off;
+  }
+  return launch_conv_tma(d, g, in_packed ? nullptr : x, base, w_images, bias, residual, y, 0, 1.0f,
+                         reinterpret_cast<cudaStream_t>(stream), &co);
 }
 
 /* ---- all-pairs correlation (RAFT CorrBlock level 0, src/models/stage_1/core/corr.py:56-64) as a 1x1 "convolution":

@@ -34,6 +34,13 @@ class UNet(nn.Module):
     @staticmethod
     def _run_block(block, x, out=None, out_c_off=0):
         convs = [m for m in block if isinstance(m, nn.Conv2d)]
+        if K.Chain.available():
+            # tcgen05 path: conv1's epilogue writes conv2's packed fp16 input directly — the intermediate tensor is
+            # never written in fp32 nor repacked
+            n, _, h, w = x.shape
+            ch = K.Chain(n, convs[1].in_channels, h, w, (3, 3), 1, x.device)
+            K.conv2d(x, convs[0].weight, None, pad=1, act="relu", chain_out=ch, keep_fp32=False)
+            return K.conv2d(ch, convs[1].weight, None, pad=1, act="relu", out=out, out_c_off=out_c_off)
         t = K.conv2d(x, convs[0].weight, None, pad=1, act="relu")
         return K.conv2d(t, convs[1].weight, None, pad=1, act="relu", out=out, out_c_off=out_c_off)
 

@@ -74,6 +74,21 @@ class BasicMotionEncoder(nn.Module):
 
     def forward(self, flow, corr):
         n, _, h, w = flow.shape
+        if K.Chain.available():
+            # tcgen05 path: each convolution's epilogue writes the packed fp16 input of the next one (the 192 + 64
+            # channel concat included) — three fp32 intermediates and three repack kernels less per iteration
+            dev = flow.device
+            c2 = K.Chain(n, 256, h, w, (3, 3), 1, dev, tag="convc2")
+            _c(self.convc1, corr, "relu", chain_out=c2, keep_fp32=False)
+            f2 = K.Chain(n, 128, h, w, (3, 3), 1, dev, tag="convf2")
+            _c(self.convf1, flow, "relu", chain_out=f2, keep_fp32=False)
+            cf = K.Chain(n, 256, h, w, (3, 3), 1, dev, tag="cor_flo")
+            _c(self.convc2, c2, "relu", chain_out=cf, chain_c_off=0, keep_fp32=False)
+            _c(self.convf2, f2, "relu", chain_out=cf, chain_c_off=192, keep_fp32=False)
+            out = torch.empty(n, 128, h, w, dtype=torch.float32, device=dev)
+            _c(self.conv, cf, "relu", out=out, out_c_off=0)
+            out[:, 126:] = flow
+            return out
         cor_flo = torch.empty(n, 256, h, w, dtype=torch.float32, device=flow.device)
         _c(self.convc2, _c(self.convc1, corr, "relu"), "relu", out=cor_flo, out_c_off=0)
         _c(self.convf2, _c(self.convf1, flow, "relu"), "relu", out=cor_flo, out_c_off=192)

@@ -433,6 +433,19 @@ int64_t b200_conv_tma_weight_image_bytes(const B200ConvDesc* d);
 int b200_conv_tma_weight_images(const B200ConvDesc* d, const float* w, void* images, void* stream);
 int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images, const float* bias,
                     const float* residual, float* y, void* workspace, int64_t workspace_bytes, void* stream);
+/* Chained form: the fp16 NHWC repack of a convolution's input is skipped when its producers wrote it directly.
+ *   in_packed  (or NULL): the packed input of `d` — b200_conv_tma_workspace_bytes(d) bytes, 256-byte aligned, zeroed once
+ *              by the caller (halo and padded channels stay zero), interior written by the producers; x is then ignored
+ *   out_packed (or NULL) + next + next_c_off: ALSO write act(conv) as fp16 into the packed input of the consumer
+ *              convolution `next` at its input channel next_c_off (several producers may fill one consumer: concat);
+ *              y may then be NULL (no fp32 NCHW output at all)
+ * `next` / `d` with a packed input must satisfy b200_conv_tma_chainable: stride 1, no upsampling, zero padding, whole
+ * input tensor (no channel slice), Cin * KW > 64. */
+int b200_conv_tma_chainable(const B200ConvDesc* next);
+int b200_conv2d_tma_chain(const B200ConvDesc* d, const float* x, void* in_packed, const void* w_images,
+                          const float* bias, const float* residual, float* y, void* out_packed,
+                          const B200ConvDesc* next, int32_t next_c_off, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 int b200_maxpool2(const float* x, float* y, int64_t planes, int32_t H, int32_t W, void* stream);
 int b200_upsample_bilinear2(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
                             int32_t out_c_total, int32_t out_c_off, void* stream);

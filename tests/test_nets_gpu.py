@@ -258,3 +258,44 @@ def test_raft_both_directions_share_the_encoder(golden_dir):
     r21 = model(b, a, iters=3, test_mode=True)
     assert torch.equal(up12, r12[1]) and torch.equal(lo12, r12[0])
     assert torch.equal(up21, r21[1]) and torch.equal(lo21, r21[0])
+
+
+def test_chained_convolutions_equal_unchained():
+    """conv -> conv with the intermediate written by the first epilogue straight into the second one's packed fp16 input
+    (b200_conv2d_tma_chain) against the same two tcgen05 convolutions with an fp32 tensor + repack in between: the
+    consumer sees the same fp16 operands, so the results are bit-identical.  Also a two-producer concat (192 + 64
+    channels, RAFT motion encoder) and an odd width (ragged last tile)."""
+    from b200 import nn as K
+    g = torch.Generator().manual_seed(31)
+    prev = K.set_conv_precision("tc")
+    try:
+        for (n, cin, h, w, mid, cout) in ((1, 6, 24, 37, 32, 32), (1, 64, 19, 130, 96, 40), (2, 32, 16, 24, 128, 8)):
+            x = torch.randn(n, cin, h, w, generator=g).to(DEV)
+            w1 = (torch.randn(mid, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(DEV)
+            w2 = (torch.randn(cout, mid, 3, 3, generator=g) / (3 * mid ** 0.5)).to(DEV)
+            b2 = torch.randn(cout, generator=g).to(DEV)
+            t = K.conv2d(x, w1, None, pad=1, act="relu")
+            ref = K.conv2d(t, w2, b2, pad=1, act="tanh")
+            ch = K.Chain(n, mid, h, w, (3, 3), 1, DEV)
+            both = K.conv2d(x, w1, None, pad=1, act="relu", chain_out=ch)           # fp32 AND packed
+            assert torch.equal(both, t)
+            got = K.conv2d(ch, w2, b2, pad=1, act="tanh")
+            assert torch.equal(got, ref), float((got - ref).abs().max())
+            assert K.conv2d(x, w1, None, pad=1, act="relu", chain_out=ch, keep_fp32=False) is None
+            assert torch.equal(K.conv2d(ch, w2, b2, pad=1, act="tanh"), ref)
+        # two producers fill one consumer input (torch.cat in the reference, core/update.py:95)
+        a = torch.randn(1, 256, 17, 29, generator=g).to(DEV); bsrc = torch.randn(1, 128, 17, 29, generator=g).to(DEV)
+        wa = (torch.randn(192, 256, 3, 3, generator=g) / 48).to(DEV); wb = (torch.randn(64, 128, 3, 3, generator=g) / 34).to(DEV)
+        wc = (torch.randn(126, 256, 3, 3, generator=g) / 48).to(DEV)
+        cat = torch.empty(1, 256, 17, 29, device=DEV)
+        K.conv2d(a, wa, None, pad=1, act="relu", out=cat, out_c_off=0)
+        K.conv2d(bsrc, wb, None, pad=1, act="relu", out=cat, out_c_off=192)
+        ref = K.conv2d(cat, wc, None, pad=1, act="relu")
+        ch = K.Chain(1, 256, 17, 29, (3, 3), 1, DEV, tag="test_concat")
+        K.conv2d(a, wa, None, pad=1, act="relu", chain_out=ch, chain_c_off=0, keep_fp32=False)
+        K.conv2d(bsrc, wb, None, pad=1, act="relu", chain_out=ch, chain_c_off=192, keep_fp32=False)
+        assert torch.equal(K.conv2d(ch, wc, None, pad=1, act="relu"), ref)
+        with pytest.raises(Exception):
+            K.Chain(1, 8, 16, 16, (3, 3), 1, DEV)          # 8 channels x 3 taps are folded: not chainable
+    finally:
+        K.set_conv_precision(prev)
