@@ -32,15 +32,17 @@ class UNet(nn.Module):
                                           (name + "relu2", nn.ReLU(inplace=True))]))
 
     @staticmethod
-    def _run_block(block, x, out=None, out_c_off=0):
+    def _run_block(block, x, out=None, out_c_off=0, chain_out=None, chain_c_off=0, keep_fp32=True):
         convs = [m for m in block if isinstance(m, nn.Conv2d)]
         if K.Chain.available():
             # tcgen05 path: conv1's epilogue writes conv2's packed fp16 input directly — the intermediate tensor is
-            # never written in fp32 nor repacked
-            n, _, h, w = x.shape
-            ch = K.Chain(n, convs[1].in_channels, h, w, (3, 3), 1, x.device)
+            # never written in fp32 nor repacked.  `x` may itself be a chained input, and conv2 may feed a chain.
+            n, h, w = (x.n, x.h, x.w) if isinstance(x, K.Chain) else (x.shape[0], x.shape[2], x.shape[3])
+            dev = x.buf.device if isinstance(x, K.Chain) else x.device
+            ch = K.Chain(n, convs[1].in_channels, h, w, (3, 3), 1, dev)
             K.conv2d(x, convs[0].weight, None, pad=1, act="relu", chain_out=ch, keep_fp32=False)
-            return K.conv2d(ch, convs[1].weight, None, pad=1, act="relu", out=out, out_c_off=out_c_off)
+            return K.conv2d(ch, convs[1].weight, None, pad=1, act="relu", out=out, out_c_off=out_c_off, chain_out=chain_out,
+                            chain_c_off=chain_c_off, keep_fp32=keep_fp32)
         t = K.conv2d(x, convs[0].weight, None, pad=1, act="relu")
         return K.conv2d(t, convs[1].weight, None, pad=1, act="relu", out=out, out_c_off=out_c_off)
 
@@ -50,6 +52,23 @@ class UNet(nn.Module):
         n, _, h, w = x.shape
         dev = x.device
         cur = x
+        if K.Chain.available():
+            # tcgen05 path: the skip concatenations [upconv | encoder] exist only as the packed fp16 inputs of the decoder
+            # blocks, filled by the epilogues of the two convolutions that produce them
+            dec_in = []
+            for i, enc in enumerate((self.encoder1, self.encoder2, self.encoder3, self.encoder4)):
+                c = enc[0].out_channels
+                ch = K.Chain(n, 2 * c, h >> i, w >> i, (3, 3), 1, dev, tag=f"unet_dec{i + 1}")
+                e = UNet._run_block(enc, cur, chain_out=ch, chain_c_off=c)      # fp32 copy only for the pooling
+                dec_in.append(ch)
+                cur = K.maxpool2(e)
+            cur = UNet._run_block(self.bottleneck, cur)
+            for i, ch in zip((4, 3, 2, 1), reversed(dec_in)):
+                up = getattr(self, f"upconv{i}")[1]
+                K.conv2d(cur, up.weight, up.bias.detach(), pad=1, upsample=2, upsample_mode="bilinear", chain_out=ch,
+                         chain_c_off=0, keep_fp32=False)
+                cur = UNet._run_block(getattr(self, f"decoder{i}"), ch)
+            return K.conv2d(cur, self.conv.weight, self.conv.bias.detach())
         cats = []
         for i, enc in enumerate((self.encoder1, self.encoder2, self.encoder3, self.encoder4)):
             c = enc[0].out_channels
