@@ -64,21 +64,22 @@ _chain_buffers = {}        # (device, n, cin, h, w, kh, kw, ph, pw, tag) -> zero
 
 
 class Chain:
-    """The packed fp16 NHWC input of ONE consumer convolution (stride 1, zero padding, Cin * KW > 64), filled directly
+    """The packed fp16 NHWC input of ONE consumer convolution (stride 1, zero or reflection padding, Cin * KW > 64), filled directly
     by the epilogues of the convolutions that produce it (`conv2d(..., chain_out=chain)`), then consumed by
     `conv2d(chain, w, ...)`: no fp32 tensor in between and no repack kernel.  tcgen05 path only.  Buffers are cached per
     geometry and zeroed once: producers overwrite the whole interior every time, halo and channel padding stay zero."""
 
-    def __init__(self, n, cin, h, w, kernel, pad, device, tag=""):
+    def __init__(self, n, cin, h, w, kernel, pad, device, tag="", pad_mode="zeros"):
         kh, kw = kernel
         ph, pw = (pad, pad) if isinstance(pad, int) else pad
-        self.n, self.cin, self.h, self.w = n, cin, h, w
-        self.desc = N.ConvDesc(n, cin, h, w, cin, 0, 8, kh, kw, 1, ph, pw, 0, 1, 8, 0, 0, 1.0, 0, 0, 0)
+        self.n, self.cin, self.h, self.w, self.pad_mode = n, cin, h, w, pad_mode
+        self.desc = N.ConvDesc(n, cin, h, w, cin, 0, 8, kh, kw, 1, ph, pw, 1 if pad_mode == "reflect" else 0, 1, 8, 0, 0, 1.0,
+                               0, 0, 0)
         if not N.lib().b200_conv_tma_chainable(C.byref(self.desc)):
             raise N.B200Error("this convolution cannot consume a chained (pre-packed) input")
         # `tag` separates buffers of equal geometry that are alive at the same time (a consumer whose own output is
         # chained into another buffer of the same shape must not read and write one allocation)
-        key = (str(device), n, cin, h, w, kh, kw, ph, pw, tag)
+        key = (str(device), n, cin, h, w, kh, kw, ph, pw, pad_mode, tag)
         buf = _chain_buffers.get(key)
         if buf is None:
             nbytes = int(N.lib().b200_conv_tma_workspace_bytes(C.byref(self.desc)))
@@ -153,8 +154,8 @@ def _conv2d_chained(x, w, b, stride, pad, pad_mode, act, upsample, out, out_c_of
     packed_in = isinstance(x, Chain)
     bilinear = 1 if upsample_mode == "bilinear" else 0
     if packed_in:
-        if in_slice is not None or stride != 1 or upsample != 1 or pad_mode != "zeros":
-            raise N.B200Error("a chained input feeds a plain stride-1 zero-padded convolution of the whole tensor")
+        if in_slice is not None or stride != 1 or upsample != 1 or pad_mode != x.pad_mode:
+            raise N.B200Error("a chained input feeds a plain stride-1 convolution of the whole tensor, padded as declared")
         n, c_total, h, wd = x.n, x.cin, x.h, x.w
         dev = x.buf.device
     else:

@@ -397,6 +397,34 @@ __global__ void __launch_bounds__(256) conv_pack_input_kernel(const float* __res
   }
 }
 
+// nn.ReflectionPad2d on a packed input whose interior was written by the producing convolutions: every halo pixel of
+// [N][HP2][WP2][Cp] copies the vector of its mirror pixel.  One thread per (halo pixel, 8-channel group).
+__global__ void conv_reflect_halo_kernel(__half* __restrict__ xp, int N, int H, int W, int pad_h, int pad_w, int Cp) {
+  const int HP2 = H + 2 * pad_h, WP2 = W + 2 * pad_w;
+  const int c8n = Cp / 8;
+  const int64_t halo_px = (int64_t)HP2 * WP2 - (int64_t)H * W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * halo_px * c8n) return;
+  const int c8 = (int)(i % c8n);
+  int64_t r = i / c8n;
+  const int n = (int)(r / halo_px);
+  r -= (int64_t)n * halo_px;
+  // halo pixels in order: pad_h full rows on top, pad_h full rows at the bottom, then the side columns of the H rows
+  int Y, X;
+  const int64_t band = (int64_t)pad_h * WP2;
+  if (r < band) { Y = (int)(r / WP2); X = (int)(r % WP2); }
+  else if (r < 2 * band) { r -= band; Y = pad_h + H + (int)(r / WP2); X = (int)(r % WP2); }
+  else {
+    r -= 2 * band;
+    Y = pad_h + (int)(r / (2 * pad_w));
+    const int k = (int)(r % (2 * pad_w));
+    X = k < pad_w ? k : W + k;                     // left columns 0..pad_w-1, right columns pad_w+W ..
+  }
+  const int sy = tm_reflect(Y - pad_h, H) + pad_h, sx = tm_reflect(X - pad_w, W) + pad_w;
+  const uint4 v = *reinterpret_cast<const uint4*>(xp + (((int64_t)n * HP2 + sy) * WP2 + sx) * Cp + c8 * 8);
+  *reinterpret_cast<uint4*>(xp + (((int64_t)n * HP2 + Y) * WP2 + X) * Cp + c8 * 8) = v;
+}
+
 // weights [Cout][Cin][KH][KW] fp32 -> per cout tile, per (tap, channel block): [n_tile rows x 64 channels] fp16,
 // K-major, 128-byte swizzle, zero padded
 // (w_co, w_ci, w_tap = element strides of the weight tensor; split: chunk = [hi rows | lo rows], values pre-scaled)
@@ -639,11 +667,12 @@ int b200_conv2d_tma(const B200ConvDesc* d, const float* x, const void* w_images,
 }
 
 /* A convolution can consume a packed input written by its producers when its packing is the plain one: stride 1, no
- * upsampling, zero padding, x taps not folded into the channel vector. */
+ * upsampling, x taps not folded into the channel vector.  Zero padding: the halo of the buffer stays zero; reflection
+ * padding: the consumer call first mirrors the interior into the halo (conv_reflect_halo_kernel). */
 int b200_conv_tma_chainable(const B200ConvDesc* next) {
   TmaGeom g;
   if (!next || tma_geometry(next, &g) != B200_OK) return 0;
-  return (next->stride == 1 && next->upsample == 1 && next->pad_mode == 0 && g.fold_cf == 0 && next->in_c_off == 0 &&
+  return (next->stride == 1 && next->upsample == 1 && g.fold_cf == 0 && next->in_c_off == 0 &&
           next->in_c_total == next->Cin) ? 1 : 0;
 }
 
@@ -680,6 +709,12 @@ int b200_conv2d_tma_chain(const B200ConvDesc* d, const float* x, void* in_packed
     B200_REQUIRE((reinterpret_cast<uintptr_t>(out_packed) & 255) == 0, "packed output must be 256-byte aligned");
     co.yp = reinterpret_cast<__half*>(out_packed); co.hp2 = gn.HP2; co.wp2 = gn.WP2; co.cp = gn.Cp;
     co.pad_h = next->pad_h; co.pad_w = next->pad_w; co.c_off = next_c_off;
+  }
+  if (in_packed && d->pad_mode == 1 && (d->pad_h > 0 || d->pad_w > 0)) {
+    const int64_t threads = (int64_t)d->N * ((int64_t)g.HP2 * g.WP2 - (int64_t)d->H * d->W) * (g.Cp / 8);
+    conv_reflect_halo_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__half*>(base), d->N, d->H, d->W, d->pad_h, d->pad_w, g.Cp);
+    B200_CHECK_LAUNCH();
   }
   return launch_conv_tma(d, g, in_packed ? nullptr : x, base, w_images, bias, residual, y, 0, 1.0f,
                          reinterpret_cast<cudaStream_t>(stream), &co);

@@ -46,6 +46,15 @@ class ResidualBlock(nn.Module):
     def run(self, x):
         return self.conv2.run(self.conv1.run(x, "leaky"), residual=x)
 
+    def run_chained(self, x_chain, x, next_chain, tag):
+        """tcgen05 path: `x_chain` is this block's packed input (written by the previous convolution), `x` the same
+        tensor in fp32 (the residual); conv1's output exists only as conv2's packed input; conv2's output is written in
+        fp32 (next residual) and into `next_chain` (the packed input of the next convolution)."""
+        n, c, h, w = x.shape
+        mid = K.Chain(n, c, h, w, (3, 3), 1, x.device, tag=tag, pad_mode="reflect")
+        self.conv1.run(x_chain, "leaky", chain_out=mid, keep_fp32=False)
+        return self.conv2.run(mid, residual=x, chain_out=next_chain)
+
 
 class ConvLSTM(nn.Module):
     def __init__(self, input_size, hidden_size, kernel_size):
@@ -93,16 +102,37 @@ class TransformNet(nn.Module):
         c1 = torch.empty(n, 2 * nf, h, w, dtype=torch.float32, device=dev)          # [D1 | E1a]
         c2 = torch.empty(n, 4 * nf, h // 2, w // 2, dtype=torch.float32, device=dev)  # [D2 | E2a]
         e2 = torch.empty(n, 4 * nf, h // 2, w // 2, dtype=torch.float32, device=dev)  # [E2a | E2b]
-        self.conv1a.run(X, "leaky", in_slice=(0, 6), out=c1, out_c_off=nf)
+        chained = K.Chain.available()
+        # tcgen05 path: the last convolution's input [D1 | E1a] (64 channels at full resolution, the largest repack of the
+        # network) is filled by the epilogues of deconv2 and conv1a
+        c1_chain = K.Chain(n, 2 * nf, h, w, (7, 7), 3, dev, tag="tn_c1", pad_mode="reflect") if chained else None
+        self.conv1a.run(X, "leaky", in_slice=(0, 6), out=c1, out_c_off=nf, chain_out=c1_chain, chain_c_off=nf)
         e1b = self.conv1b.run(X, "leaky", in_slice=(6, 12))
         self.conv2a.run(c1, "leaky", in_slice=(nf, 2 * nf), out=e2, out_c_off=0)
         self.conv2b.run(e1b, "leaky", out=e2, out_c_off=2 * nf)
         c2[:, 2 * nf:] = e2[:, :2 * nf]
-        rb = self.conv3.run(e2, "leaky")
-        for blk in self.ResBlocks:
-            rb = blk.run(rb)
-        hidden, cell = self.convlstm.run(rb, prev_state)
+        if K.Chain.available() and prev_state is None:
+            # tcgen05 path: conv3 -> 5 residual blocks -> ConvLSTM gates run as one chain of packed fp16 inputs (the
+            # residuals stay fp32 tensors); eleven fp32 -> fp16 repack kernels less
+            hq, wq = rb_shape = (h // 4, w // 4)
+            chains = [K.Chain(n, 4 * nf, hq, wq, (3, 3), 1, dev, tag=f"tn_rb{i & 1}", pad_mode="reflect")
+                      for i in range(len(self.ResBlocks))]
+            gates_in = K.Chain(n, 4 * nf, hq, wq, (3, 3), 1, dev, tag="tn_gates")            # zero padding (nn.Conv2d)
+            rb = self.conv3.run(e2, "leaky", chain_out=chains[0] if chains else gates_in)
+            for i, blk in enumerate(self.ResBlocks):
+                nxt = chains[i + 1] if i + 1 < len(chains) else gates_in
+                rb = blk.run_chained(chains[i], rb, nxt, tag="tn_mid")
+            hidden, cell = self.convlstm.run(gates_in, prev_state)
+        else:
+            rb = self.conv3.run(e2, "leaky")
+            for blk in self.ResBlocks:
+                rb = blk.run(rb)
+            hidden, cell = self.convlstm.run(rb, prev_state)
         self.deconv1.run(hidden, "leaky", out=c2, out_c_off=0)
-        self.deconv2.run(c2, "leaky", out=c1, out_c_off=0)
-        y = self.deconv3.run(c1, "tanh")
+        if chained:
+            self.deconv2.run(c2, "leaky", chain_out=c1_chain, chain_c_off=0, keep_fp32=False)
+            y = self.deconv3.run(c1_chain, "tanh")
+        else:
+            self.deconv2.run(c2, "leaky", out=c1, out_c_off=0)
+            y = self.deconv3.run(c1, "tanh")
         return y, (hidden, cell)

@@ -299,3 +299,24 @@ def test_chained_convolutions_equal_unchained():
             K.Chain(1, 8, 16, 16, (3, 3), 1, DEV)          # 8 channels x 3 taps are folded: not chainable
     finally:
         K.set_conv_precision(prev)
+
+
+def test_chained_reflection_padded_convolution():
+    """A chained consumer with nn.ReflectionPad2d: the consumer call mirrors the interior of the packed buffer into its
+    halo before the convolution (7x7 / pad 3 and 3x3 / pad 1): bit-identical with the unchained tcgen05 pair."""
+    from b200 import nn as K
+    g = torch.Generator().manual_seed(32)
+    prev = K.set_conv_precision("tc")
+    try:
+        for (cin, mid, cout, k, h, w) in ((16, 64, 3, 7, 21, 45), (32, 128, 128, 3, 18, 34)):
+            x = torch.randn(1, cin, h, w, generator=g).to(DEV)
+            w1 = (torch.randn(mid, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(DEV)
+            w2 = (torch.randn(cout, mid, k, k, generator=g) / (k * mid ** 0.5)).to(DEV)
+            t = K.conv2d(x, w1, None, pad=1, pad_mode="reflect", act="leaky")
+            ref = K.conv2d(t, w2, None, pad=k // 2, pad_mode="reflect", act="tanh")
+            ch = K.Chain(1, mid, h, w, (k, k), k // 2, DEV, pad_mode="reflect", tag="test_reflect")
+            K.conv2d(x, w1, None, pad=1, pad_mode="reflect", act="leaky", chain_out=ch, keep_fp32=False)
+            got = K.conv2d(ch, w2, None, pad=k // 2, pad_mode="reflect", act="tanh")
+            assert torch.equal(got, ref), float((got - ref).abs().max())
+    finally:
+        K.set_conv_precision(prev)
