@@ -105,6 +105,13 @@ def main():
         d8 = [int(np.abs((recon[int(f)].cpu().double().numpy() * 255).astype(np.uint8)[::4, ::4].astype(int) - th[k].astype(int)).max())
               for k, f in enumerate(tf)]
         out["thumbnail_max_abs_u8_diff"] = d8
+        # the oracle's SECOND run (same seed and index stream, 8 instead of 4 CPU threads = another fp32 summation
+        # order): the reference arithmetic's own reproducibility, and this run against the mean of the two
+        p2 = os.path.join(os.path.dirname(args.fixture), "quality_oracle_run2_summary.npz")
+        if os.path.exists(p2):
+            po2 = np.load(p2)["psnr"]
+            out["oracle_run2_minus_run1_db"] = float(po2.mean() - po.mean())
+            out["psnr_diff_vs_mean_of_oracle_runs_db"] = float(ps.mean() - 0.5 * (po.mean() + po2.mean()))
     print(json.dumps(out))
 
 

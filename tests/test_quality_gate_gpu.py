@@ -3,16 +3,17 @@ pre-training, 10 001 loop trips, render of all 80 frames at 768x432 — on the B
 oracle's frozen CPU run of the same schedule from the same seed (tests/golden/quality_oracle.npz, produced by
 tests/golden/make_quality_oracle.py).  The run takes ~20 s on a B200.
 
-Measured (profiles/r2_quality_runs.json, 7 runs of the tensor-core path): PSNR(B200) - PSNR(oracle) = -0.073 dB on
-average, individual runs -0.037 ... -0.161 dB (std 0.04): the runs differ only in the order of fp32 atomic additions,
-which 10 001 chaotic optimisation steps amplify; one run of the fp32 CUDA-core path (true fp32 products) gives -0.128 dB,
-so the spread is not a tensor-core precision effect.  The north-star figure (0.1 dB) holds for the mean; a single run
-is gated at 0.25 dB.
+Measured (profiles/r2_quality_runs.json).  The oracle itself, run twice on the CPU from the same seed and index stream
+with 4 and with 8 threads (only the summation order of its fp32 matrix products differs): 27.273 dB and 27.150 dB, i.e.
+the reference arithmetic reproduces its own PSNR to 0.124 dB (per frame up to 1.47 dB, loss curves 0.9 % median / 9.5 %
+max apart).  Seven runs of the tensor-core path on the B200: 27.112 ... 27.236 dB, mean 27.200 dB = -0.073 dB against the
+first oracle run, +0.051 dB against the second, -0.011 dB against their mean; one run of the fp32 CUDA-core path:
+27.145 dB.  All of it is the chaotic amplification of fp32 summation order over 10 001 steps, not arithmetic precision.
 
-Bounds for ONE run: |mean PSNR difference| <= 0.25 dB; per frame within 0.8 dB where the oracle's PSNR is below 36 dB
-and within 2 dB elsewhere (at 40-44 dB an MSE difference of 1e-5 is already 1 dB; measured worst 1.4 dB); total loss of the
-two runs, sampled every 50 trips over the whole schedule, within 10 % at the median (measured 0.4-0.9 %); the two
-reconstructions agree to >= 40 dB (measured 44.7-46.6)."""
+Bounds for ONE run: |mean PSNR - mean of the two oracle runs| <= 0.2 dB and within 0.25 dB of the first run; per frame
+within 0.8 dB of the first oracle run where its PSNR is below 36 dB and within 2 dB elsewhere (the two oracle runs differ
+by 0.67 / 1.47 dB there); total loss of the two runs, sampled every 50 trips over the whole schedule, within 10 % at the
+median (measured 0.4-0.9 %); the two reconstructions agree to >= 40 dB (measured 44.7-46.6)."""
 import json
 import os
 import subprocess
@@ -37,6 +38,10 @@ def test_quality_fixture_is_consistent():
     assert fx["mapping_params"].size == O.MAPPING_SPEC.num_params() and fx["atlas_params"].size == O.ATLAS_SPEC.num_params()
     assert fx["losses"].shape == (201, 7) and np.isfinite(fx["losses"][:, 1]).all()
     assert fx["losses"][-1, 1] < 0.2 * fx["losses"][0, 1]            # the run converged
+    f2 = np.load(os.path.join(os.path.dirname(FIXTURE), "quality_oracle_run2_summary.npz"))
+    assert f2["psnr"].shape == (T,) and int(f2["iters"]) == 10001 and int(f2["seed"]) == int(fx["seed"])
+    # the reference arithmetic's own run-to-run spread (4 vs 8 CPU threads): what "within 0.1 dB" is measured against
+    assert 0.05 < abs(float(f2["psnr"].mean() - fx["psnr"].mean())) < 0.2
 
     def unflat(spec, flat):
         out, off = [], 0
@@ -57,6 +62,8 @@ def test_full_schedule_psnr_within_0p1_db_of_oracle():
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["iters"] == 10001 and out["pre_sweeps"] == 100 and out["precision"] == "tc"
     assert abs(out["psnr_diff_mean_db"]) <= 0.25, out["psnr_diff_mean_db"]
+    assert abs(out["psnr_diff_vs_mean_of_oracle_runs_db"]) <= 0.2, out["psnr_diff_vs_mean_of_oracle_runs_db"]
+    assert abs(out["oracle_run2_minus_run1_db"] + 0.1237) < 1e-3            # the frozen second oracle run
     po = np.load(FIXTURE)["psnr"]
     diff = np.array(out["psnr_b200"]) - po
     assert np.abs(diff[po < 36.0]).max() <= 0.8, diff[po < 36.0]
