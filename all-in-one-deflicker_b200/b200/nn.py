@@ -91,6 +91,12 @@ class Chain:
         return _conv_precision == "tc"
 
 
+def clear_chain_buffers():
+    """Drop the cached packed-input buffers (they persist per geometry: ~1.2 GB for the stage-2 networks at 1088x1920).
+    Only when no captured CUDA graph still refers to them."""
+    _chain_buffers.clear()
+
+
 def conv2d(x, w, b=None, stride=1, pad=(0, 0), pad_mode="zeros", act="none", upsample=1, out=None, out_c_off=0,
            in_slice=None, residual=None, res_c_off=0, out_scale=1.0, precision=None, upsample_mode="nearest",
            chain_out=None, chain_c_off=0, keep_fp32=True):
