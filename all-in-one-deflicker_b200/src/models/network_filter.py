@@ -63,12 +63,16 @@ class UNet(nn.Module):
                 dec_in.append(ch)
                 cur = K.maxpool2(e)
             cur = UNet._run_block(self.bottleneck, cur)
+            last = K.Chain(n, self.conv.in_channels, h, w, (1, 1), 0, dev, tag="unet_out")     # input of the final 1x1
             for i, ch in zip((4, 3, 2, 1), reversed(dec_in)):
                 up = getattr(self, f"upconv{i}")[1]
                 K.conv2d(cur, up.weight, up.bias.detach(), pad=1, upsample=2, upsample_mode="bilinear", chain_out=ch,
                          chain_c_off=0, keep_fp32=False)
-                cur = UNet._run_block(getattr(self, f"decoder{i}"), ch)
-            return K.conv2d(cur, self.conv.weight, self.conv.bias.detach())
+                if i == 1:
+                    UNet._run_block(self.decoder1, ch, chain_out=last, keep_fp32=False)
+                else:
+                    cur = UNet._run_block(getattr(self, f"decoder{i}"), ch)
+            return K.conv2d(last, self.conv.weight, self.conv.bias.detach())
         cats = []
         for i, enc in enumerate((self.encoder1, self.encoder2, self.encoder3, self.encoder4)):
             c = enc[0].out_channels
