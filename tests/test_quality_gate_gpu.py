@@ -4,10 +4,11 @@ oracle's frozen CPU run of the same schedule from the same seed (tests/golden/qu
 tests/golden/make_quality_oracle.py).  The run takes ~20 s on a B200.
 
 Measured (profiles/r2_quality_runs.json).  The oracle itself, run twice on the CPU from the same seed and index stream
-with 4, 8 and 6 threads (only the summation order of its fp32 matrix products differs): 27.273, 27.150 and 27.275 dB, i.e.
+with 4, 8, 6 and 7 threads (only the summation order of its fp32 matrix products differs): 27.273, 27.150, 27.275 and
+27.264 dB, i.e.
 the reference arithmetic reproduces its own PSNR to 0.124 dB (per frame up to 1.47 dB, loss curves 0.9 % median / 9.5 %
 max apart).  Eleven runs of the tensor-core path on the B200: 27.103 ... 27.248 dB, mean 27.188 dB = -0.085 dB against the
-first oracle run, +0.038 dB against the second, -0.045 dB against the mean of the three; one run of the fp32 CUDA-core path:
+first oracle run, +0.038 dB against the second, -0.052 dB against the mean of the four; one run of the fp32 CUDA-core path:
 27.145 dB.  All of it is the chaotic amplification of fp32 summation order over 10 001 steps, not arithmetic precision.
 
 Bounds for ONE run: |mean PSNR - mean of the two oracle runs| <= 0.2 dB and within 0.25 dB of the first run; per frame
