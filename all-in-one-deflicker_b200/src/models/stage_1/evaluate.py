@@ -1,6 +1,8 @@
 """Checkpoint + full-video render + PSNR + evaluation artefacts of the reference's `evaluate_model_single`
-(src/models/stage_1/evaluate.py:605-793) and of `evaluate_model` (:203-602, segmentation variant).  The dashboards / mp4 dumps / tensorboard images of the
-reference are visualisation and out of scope."""
+(src/models/stage_1/evaluate.py:605-793) and of `evaluate_model` (:203-602, segmentation variant).  Reconstruction,
+per-pixel maps and PSNR run in libb200deflicker.so; the reconstruction / residual / uv / dashboard videos (:714-779) are
+composed with OpenCV (`ArtefactWriter`), tensorboard images go through torch.utils.tensorboard.  The texture-editing
+part of the segmentation variant's evaluation (:234-262, :340-600) is interactive-editing tooling and is not provided."""
 import os
 
 import cv2
